@@ -1,0 +1,184 @@
+"""Pin the oracle (oracle/recpack_oracle.py) to outputs of the real reference.
+
+The fixtures in tests/golden/ were produced by tests/golden/make_golden.py, which imports
+the unmodified reference from /root/reference.  CPU only."""
+import math
+
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+from conftest import load_golden, unpack
+from oracle import recpack_oracle as orc
+
+UNIT = ["unit_cosine", "unit_empty_col", "unit_condprob", "unit_condprob_pd1", "unit_condprob_pd0.2", "unit_condprob_pd0.5"]
+SMALL = ["small_cosine", "small_condprob", "small_condprob_pd"]
+
+
+def _params(g):
+    pd_ = float(g["pop_discount"])
+    return int(g["K"]), str(g["similarity"]), (None if math.isnan(pd_) else pd_)
+
+
+def _same_csr(A, B):
+    A, B = csr_matrix(A), csr_matrix(B)
+    A.sort_indices()
+    B.sort_indices()
+    return A.shape == B.shape and np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices) and np.array_equal(A.data, B.data)
+
+
+@pytest.mark.parametrize("name", UNIT + SMALL)
+def test_ref_tier_reproduces_reference_bit_for_bit(name):
+    g = load_golden(name)
+    K, sim, pd_ = _params(g)
+    S = orc.ref_fit(unpack(g, "X"), K=K, similarity=sim, pop_discount=pd_)
+    assert _same_csr(S, unpack(g, "S"))
+    pred = orc.ref_predict(unpack(g, "Xin"), S)
+    assert _same_csr(pred, unpack(g, "pred"))
+    assert _same_csr(orc.ref_remove_history(pred, unpack(g, "Xin")), unpack(g, "pred_nohist"))
+
+
+def test_ref_tier_normalize_sim():
+    g = load_golden("unit_normalize_sim")
+    S = orc.ref_fit(unpack(g, "X"), K=2, normalize_sim=True)
+    assert _same_csr(S, unpack(g, "S"))
+
+
+def test_ref_row_blocked_equals_unblocked():
+    g = load_golden("small_cosine")
+    X = unpack(g, "X")
+    S = orc.ref_fit_row_blocked(X, K=int(g["K"]), block=32)
+    assert _same_csr(S, unpack(g, "S"))
+
+
+def test_unit_closed_forms():
+    """recpack/tests/test_algorithms/test_nearest_neighbour.py:44-70,119-152."""
+    g = load_golden("unit_cosine")
+    got = orc.canon_fit(unpack(g, "X"), K=2)
+    S = orc.topk_to_csr(got["idx"], got["val"], got["len"], 3).toarray()
+    e = 2 / math.sqrt(6)
+    np.testing.assert_almost_equal(S, [[0, 0.5, e], [0.5, 0, e], [e, e, 0]])
+    g = load_golden("unit_condprob")
+    got = orc.canon_fit(unpack(g, "X"), K=2, similarity="conditional_probability")
+    S = orc.topk_to_csr(got["idx"], got["val"], got["len"], 3).toarray()
+    np.testing.assert_almost_equal(S, [[0, 0.5, 1], [0.5, 0, 1], [2 / 3, 2 / 3, 0]])
+    g = load_golden("unit_empty_col")
+    got = orc.canon_fit(unpack(g, "X"), K=2)
+    S = orc.topk_to_csr(got["idx"], got["val"], got["len"], 3).toarray()
+    np.testing.assert_almost_equal(S, [[0, 0, 0], [0, 0, e], [0, e, 0]])
+    assert got["len"].tolist() == [0, 1, 1]
+
+
+@pytest.mark.parametrize("name", UNIT + SMALL + ["mid_cosine"])
+def test_canonical_fit_vs_reference_tie_aware(name):
+    g = load_golden(name)
+    K = int(g["K"])
+    sim = str(g["similarity"]) if "similarity" in g else "cosine"
+    pd_ = None
+    if "pop_discount" in g and not math.isnan(float(g["pop_discount"])):
+        pd_ = float(g["pop_discount"])
+    X = unpack(g, "X")
+    S_ref = unpack(g, "S")
+    got = orc.canon_fit(X, K=K, similarity=sim, pop_discount=pd_)
+    Xb = orc.binarize(X)
+    if pd_:
+        # irrational keys: the canonical order is the float64 key; compare values only
+        S = orc.topk_to_csr(got["idx"], got["val"], got["len"], X.shape[1])
+        a, b = np.sort(S.data), np.sort(S_ref.data)
+        np.testing.assert_allclose(a, b, rtol=1e-12)
+        return
+    stats = orc.compare_topk_tie_aware(S_ref, got, Xb, similarity=sim)
+    assert stats["rows_checked"] == X.shape[1]
+    # kept values are reproduced with the reference's own operation order: wherever the two
+    # sides keep the same item the float64 value must be IDENTICAL
+    S = orc.topk_to_csr(got["idx"], got["val"], got["len"], X.shape[1])
+    common = S.multiply(S_ref.astype(bool)).tocsr()
+    ref_common = S_ref.multiply(S.astype(bool)).tocsr()
+    common.sort_indices()
+    ref_common.sort_indices()
+    assert np.array_equal(common.data, ref_common.data)
+    if name == "mid_cosine":
+        assert stats["rows_with_diff"] > 0  # the reference's tie picks are arbitrary
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_canonical_predict_and_metrics_vs_reference(name):
+    g = load_golden(name)
+    S_ref = unpack(g, "S")
+    Xin = unpack(g, "Xin")
+    # scoring with the REFERENCE's S isolates the scoring / metric definitions from fit ties
+    full = orc.canon_predict_csr(Xin, S_ref)
+    ref_pred = unpack(g, "pred")
+    ref_pred.sort_indices()
+    assert np.array_equal(full.indices, ref_pred.indices) and np.array_equal(full.indptr, ref_pred.indptr)
+    np.testing.assert_allclose(full.data, ref_pred.data, rtol=1e-9, atol=1e-10)
+    top = orc.canon_predict_topn(Xin, S_ref, 20, remove_history=True)
+    ytrue = unpack(g, "ytrue")
+    nohist = unpack(g, "pred_nohist")
+    # (1) the restated reference metrics reproduce the reference's numbers (same arbitrary ties)
+    np.testing.assert_allclose(orc.ref_ndcg(ytrue, nohist, 10)[0], float(g["ndcg10_value"]), rtol=1e-12)
+    np.testing.assert_allclose(orc.ref_recall(ytrue, nohist, 20)[0], float(g["recall20_value"]), rtol=1e-12)
+    # (2) canonical lists vs the reference's own rank matrix: identical score multisets per user;
+    #     item differences are tie picks (metrics/base.py:189 -> util.py:68 argpartition)
+    ref_ranks = orc.ref_top_k_ranks(nohist, 20)
+    nohist.sort_indices()
+    same_list = np.zeros(Xin.shape[0], dtype=bool)
+    for u in range(Xin.shape[0]):
+        row = ref_ranks[u]
+        ref_items = row.indices[np.argsort(row.data)]
+        m = int(top["len"][u])
+        assert len(ref_items) == m
+        dense = nohist[u].toarray().ravel()
+        np.testing.assert_allclose(np.sort(dense[ref_items]), np.sort(top["val"][u, :m]), rtol=1e-9, atol=1e-11)
+        same_list[u] = np.array_equal(ref_items, top["idx"][u, :m])
+    res = orc.canon_metrics_from_lists(top["idx"], top["len"], ytrue, [("ndcg", 10), ("recall", 20), ("dcg", 10), ("calibrated_recall", 20)])
+    for (kind, k), (value, per_user, users) in res.items():
+        order = np.argsort(g[f"{kind}{k}_users"])
+        assert np.array_equal(np.sort(g[f"{kind}{k}_users"]), users)
+        ref_scores = g[f"{kind}{k}_scores"][order]
+        ok = same_list[users]
+        np.testing.assert_allclose(per_user[ok], ref_scores[ok], rtol=1e-12, atol=1e-15)
+        if ok.all():
+            np.testing.assert_allclose(value, float(g[f"{kind}{k}_value"]), rtol=1e-12)
+    if name == "small_cosine":
+        assert same_list.mean() > 0.5
+
+
+def test_metric_unit_vectors():
+    """recpack/tests/test_metrics/test_dcg.py:30-156, test_recall.py:13-42 (values from the reference)."""
+    g = load_golden("metrics_unit")
+    pred = unpack(g, "pred")
+    for tname in ("true", "simplified", "unrecommended"):
+        yt = unpack(g, "true_" + tname)
+        for k in (1, 2, 3):
+            ranks = orc.canon_top_k_ranks(pred, k)
+            U = pred.shape[0]
+            idx = np.full((U, k), -1, dtype=np.int32)
+            ln = np.zeros(U, dtype=np.int32)
+            for u in range(U):
+                row = ranks[u]
+                for c, r in zip(row.indices, row.data):
+                    idx[u, int(r) - 1] = c
+                ln[u] = row.nnz
+            res = orc.canon_metrics_from_lists(idx, ln, yt, [("ndcg", k), ("recall", k), ("dcg", k), ("calibrated_recall", k)])
+            for (kind, kk), (value, per_user, users) in res.items():
+                np.testing.assert_allclose(value, float(g[f"{tname}_{kind}{kk}_value"]), rtol=1e-12)
+                assert np.array_equal(np.sort(g[f"{tname}_{kind}{kk}_users"]), users)
+            # restated reference metrics agree as well
+            np.testing.assert_allclose(orc.ref_ndcg(yt, pred, k)[0], float(g[f"{tname}_ndcg{k}_value"]), rtol=1e-12)
+            np.testing.assert_allclose(orc.ref_recall(yt, pred, k)[0], float(g[f"{tname}_recall{k}_value"]), rtol=1e-12)
+    # closed forms quoted in the reference tests
+    np.testing.assert_almost_equal(float(g["true_recall2_value"]), 2 / 3)
+    np.testing.assert_almost_equal(float(g["unrecommended_recall2_value"]), 4 / 9)
+    idcg2 = 1 + 1 / np.log2(3)
+    np.testing.assert_almost_equal(float(g["true_ndcg2_value"]), ((1 / np.log2(3)) / idcg2 + (1 + 1 / np.log2(3)) / idcg2) / 2)
+
+
+def test_top_k_ranks_fixture():
+    """recpack/tests/test_util.py:14-25."""
+    g = load_golden("topk_ranks")
+    mat = unpack(g, "mat")
+    ref = unpack(g, "ranks20")
+    got = orc.canon_top_k_ranks(mat, 20)
+    assert (got != ref).nnz == 0  # no ties in this fixture -> identical
+    assert _same_csr(orc.ref_top_k_ranks(mat, 20), ref)
