@@ -1,0 +1,157 @@
+/*
+ * rpk.h -- C ABI of the B200 item-similarity library (librpk.so).
+ *
+ * The reference (LienM/recpack, pure Python) has no native boundary on this path; these
+ * entry points are what a binding for its hot path replaces, one per reference call site:
+ *
+ *   rpk_fit_topk        ItemKNN._fit: compute_cosine_similarity /
+ *                       compute_conditional_probability + get_top_K_values
+ *                       (recpack/algorithms/nearest_neighbour.py:22-84,204-224,
+ *                        recpack/util.py:50-96)
+ *   rpk_model_load_*    the fitted `similarity_matrix_` attribute
+ *                       (recpack/algorithms/base.py:220-255)
+ *   rpk_predict_topn    ItemSimilarityMatrixAlgorithm._predict (base.py:237-255) fused
+ *                       with history removal (recpack/pipelines/pipeline.py:174-175) and
+ *                       the top-K ranking of MetricTopK.calculate (metrics/base.py:189)
+ *   rpk_predict_csr_*   _predict with the reference's full CSR output
+ *   rpk_topk_csr        get_top_K_ranks on an arbitrary prediction matrix (util.py:50-77)
+ *   rpk_metrics_topn    NDCGK / DCGK / RecallK / CalibratedRecallK._calculate
+ *                       (metrics/dcg.py:21-128, metrics/recall.py:21-85)
+ *
+ * Conventions
+ *   - plain C types only; every call returns 0 on success, non-zero on failure, with a
+ *     message available from rpk_last_error().  No C++ exception crosses the boundary.
+ *   - every data pointer may be a HOST pointer or a DEVICE pointer of the context's device;
+ *     the library detects which (cudaPointerGetAttributes).  Host inputs are copied to the
+ *     device inside the call, host outputs are copied back and the call returns after the
+ *     copy completed.  With device pointers only, calls are asynchronous on the context's
+ *     stream (rpk_set_stream) and stream-ordered with each other.
+ *   - the caller owns all inputs and outputs; the context owns only workspace and the
+ *     loaded model.  A context is bound to one device and is not re-entrant; use one
+ *     context per (process, device) -- multi-GPU is one process per GPU.
+ *   - interaction matrices are CSR (users x items): indptr int64[U+1], indices int32[nnz],
+ *     rows with strictly increasing column indices (scipy "canonical format").  Values are
+ *     not passed: the path is defined on the binarised matrix (base.py:129-151).
+ */
+#ifndef RPK_H
+#define RPK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RPK_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define RPK_EXPORT __attribute__((visibility("default")))
+#else
+#define RPK_EXPORT
+#endif
+
+typedef struct rpk_ctx rpk_ctx;
+
+enum { RPK_SIM_COSINE = 0, RPK_SIM_CONDPROB = 1 };
+enum { RPK_METRIC_NDCG = 0, RPK_METRIC_RECALL = 1, RPK_METRIC_DCG = 2, RPK_METRIC_CALIBRATED_RECALL = 3 };
+
+RPK_EXPORT int rpk_abi_version(void);
+
+/* Create / destroy a context on CUDA device `device`. */
+RPK_EXPORT int rpk_create(int device, rpk_ctx** out);
+RPK_EXPORT void rpk_destroy(rpk_ctx* ctx);
+/* Message of the last failed call on this context (or of a failed rpk_create when ctx is NULL). */
+RPK_EXPORT const char* rpk_last_error(const rpk_ctx* ctx);
+/* Use `cuda_stream` (a cudaStream_t, may be NULL for the default stream) for all later calls. */
+RPK_EXPORT int rpk_set_stream(rpk_ctx* ctx, void* cuda_stream);
+/* Block until everything queued on the context's stream has finished. */
+RPK_EXPORT int rpk_sync(rpk_ctx* ctx);
+/* Number of kernels this context has launched since creation (for the bench's gpu_launches). */
+RPK_EXPORT int64_t rpk_launch_count(const rpk_ctx* ctx);
+/* Test hook: force a code path.  bit 0: wide (64-bit CAS) score accumulators in predict;
+ * bit 1: tiny candidate-list capacity in the selection routine (exercises its refinement and
+ * tie paths on small inputs); bit 2: more than one item-range pass in fit/predict. */
+RPK_EXPORT int rpk_debug_flags(rpk_ctx* ctx, int flags);
+
+/*
+ * Fit: for every item row i in [item_begin, item_end) compute the co-occurrence counts
+ * c_ij = |users(i) & users(j)| against ALL items j, and keep the K best j != i with c_ij > 0.
+ *
+ *   similarity = RPK_SIM_COSINE:   order by c_ij^2 / n_j   (exact rational; n_i is constant per row)
+ *                                  value  = sum of c_ij copies of fl(a_i * a_j), a = 1/sqrt(n), added
+ *                                  one at a time in float64 -- the reference's own operation order
+ *   similarity = RPK_SIM_CONDPROB: order by c_ij, value = fl(fl(1/n_i) * c_ij)            (item_pow NULL)
+ *                                  order by fl(c_ij * item_pow[j]), value = fl(fl(fl(1/n_i) * c_ij) * item_pow[j])
+ *                                  item_pow[j] = (1/n_j)^pop_discount, float64[I], computed by the caller
+ *   ties: ascending item index.
+ *
+ * Outputs (row-major, [item_end - item_begin] x K, rank order, best first):
+ *   out_idx int32 (-1 padded), out_cnt int32 (c_ij, 0 padded), out_val float64 (0 padded),
+ *   out_len int32[item_end - item_begin].  out_cnt / out_val may be NULL.
+ */
+RPK_EXPORT int rpk_fit_topk(rpk_ctx* ctx, int64_t U, int64_t I, int64_t nnz,
+                 const int64_t* indptr, const int32_t* indices,
+                 int similarity, const double* item_pow, int K,
+                 int64_t item_begin, int64_t item_end,
+                 int32_t* out_idx, int32_t* out_cnt, double* out_val, int32_t* out_len);
+
+/* Item popularities n_j of the matrix passed to the last rpk_fit_topk (int32[I]). */
+RPK_EXPORT int rpk_fit_item_counts(rpk_ctx* ctx, int32_t* out_counts, int64_t I);
+
+/*
+ * Load the similarity model used by the predict calls.
+ *   _topk: from [I x K] lists as rpk_fit_topk writes them (any order inside a row).
+ *   _csr:  from a CSR item x item matrix (indptr int64[I+1], column indices unique per row).
+ * Values must lie in [0, 2); scoring is defined on q = rint(v * 2^39) | 1 (exact integer sums).
+ */
+RPK_EXPORT int rpk_model_load_topk(rpk_ctx* ctx, int64_t I, int K,
+                        const int32_t* idx, const double* val, const int32_t* len);
+RPK_EXPORT int rpk_model_load_csr(rpk_ctx* ctx, int64_t I, int64_t nnz,
+                       const int64_t* indptr, const int32_t* indices, const double* values);
+
+/*
+ * Score U users: score_uj = sum over history items i of S_ij; optionally drop the user's own
+ * history items; keep the N best (score desc, item index asc).
+ *   out_idx int32 [U x N] (-1 padded), out_val float64 [U x N] (score, 0 padded; may be NULL),
+ *   out_len int32 [U].
+ */
+RPK_EXPORT int rpk_predict_topn(rpk_ctx* ctx, int64_t U, int64_t nnz,
+                     const int64_t* indptr, const int32_t* indices,
+                     int N, int mask_history,
+                     int32_t* out_idx, double* out_val, int32_t* out_len);
+
+/* Full score matrix in CSR, as the reference's predict() returns it.  Two steps: _count fills
+ * out_row_nnz int64[U]; the caller prefix-sums it into out_indptr and allocates; _fill writes
+ * the column indices (ascending per row) and float64 scores. */
+RPK_EXPORT int rpk_predict_csr_count(rpk_ctx* ctx, int64_t U, int64_t nnz,
+                          const int64_t* indptr, const int32_t* indices,
+                          int mask_history, int64_t* out_row_nnz);
+RPK_EXPORT int rpk_predict_csr_fill(rpk_ctx* ctx, int64_t U, int64_t nnz,
+                         const int64_t* indptr, const int32_t* indices,
+                         int mask_history, const int64_t* out_indptr,
+                         int32_t* out_indices, double* out_values);
+
+/* Per row of an arbitrary CSR (values float64), the K best stored entries
+ * (value desc, column asc): out_idx int32 [rows x K] (-1 padded), out_len int32[rows]. */
+RPK_EXPORT int rpk_topk_csr(rpk_ctx* ctx, int64_t rows, int64_t nnz,
+                 const int64_t* indptr, const int32_t* indices, const double* values,
+                 int K, int32_t* out_idx, int32_t* out_len);
+
+/*
+ * Metrics on rank-ordered lists.  For every user u with a non-empty y_true row and every
+ * metric m: per_user[m * U + u] = metric value (users with an empty y_true row get NaN and are
+ * not counted).  sums[m] = sum over counted users, *n_users = number of counted users.
+ *   discount float64[maxK] = 1/log2(r+2), idcg float64[maxK+1] -- tables computed by the caller
+ *   (metrics/dcg.py:98-104) so that they are the reference's own numbers.
+ */
+RPK_EXPORT int rpk_metrics_topn(rpk_ctx* ctx, int64_t U, int N,
+                     const int32_t* top_idx, const int32_t* top_len,
+                     const int64_t* true_indptr, const int32_t* true_indices, int64_t true_nnz,
+                     int n_metrics, const int32_t* kinds, const int32_t* Ks,
+                     const double* discount, const double* idcg, int maxK,
+                     double* per_user, double* sums, int64_t* n_users);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RPK_H */

@@ -1,0 +1,12 @@
+"""recpack_b200 -- B200-native drop-in for RecPack's item-similarity hot path.
+
+``ItemKNN`` (fit / predict) and ``NDCGK`` / ``RecallK`` keep the reference's contracts and run on
+hand-written sm_100a CUDA kernels through the C ABI in include/rpk.h.  There is no CPU fallback:
+without ``recpack_b200/librpk.so`` and a B200 every compute call raises."""
+from .base import Algorithm, ItemSimilarityMatrixAlgorithm, TopKItemSimilarityMatrixAlgorithm  # noqa: F401
+from .matrix import UnsupportedTypeError, to_csr_matrix  # noqa: F401
+from .metrics import NDCGK, DCGK, RecallK, CalibratedRecallK  # noqa: F401
+from .nearest_neighbour import ItemKNN  # noqa: F401
+from .util import get_top_K_ranks, get_top_K_values  # noqa: F401
+
+__version__ = "0.1.0"

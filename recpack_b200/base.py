@@ -1,0 +1,186 @@
+"""Algorithm base classes with the reference's fit / predict contract.
+
+Mirror of recpack/algorithms/base.py:33-304 (Algorithm, ItemSimilarityMatrixAlgorithm,
+TopKItemSimilarityMatrixAlgorithm): same names, same wrappers, same log line and warnings.  The
+scoring of ItemSimilarityMatrixAlgorithm runs on the GPU (rpk_predict_*), there is no CPU path."""
+from __future__ import annotations
+
+import logging
+import time
+import warnings
+
+import numpy as np
+from scipy.sparse import csr_matrix
+from sklearn.base import BaseEstimator
+from sklearn.utils.validation import check_is_fitted
+
+from .engine import get_engine
+from .matrix import binary_structure, to_csr_matrix
+
+logger = logging.getLogger("recpack")
+
+
+class Algorithm(BaseEstimator):
+    """recpack/algorithms/base.py:33-217."""
+
+    def __init__(self):
+        super().__init__()
+
+    @property
+    def name(self):
+        return self.__class__.__name__
+
+    @property
+    def identifier(self):
+        paramstring = ",".join((f"{k}={v}" for k, v in self.get_params().items()))
+        return self.name + "(" + paramstring + ")"
+
+    def __str__(self):
+        return self.name
+
+    def set_params(self, **params):
+        super().set_params(**params)
+
+    def _fit(self, X: csr_matrix):
+        raise NotImplementedError("Please implement _fit")
+
+    def _predict(self, X: csr_matrix) -> csr_matrix:
+        raise NotImplementedError("Please implement _predict")
+
+    def _check_fit_complete(self):
+        check_is_fitted(self)
+
+    def _check_prediction(self, X_pred: csr_matrix, X: csr_matrix) -> None:
+        """Warn when a user with history got no recommendation (base.py:108-127); computed from the
+        row pointers instead of Python sets over nonzero()."""
+        has_hist = np.diff(X.indptr) > 0
+        has_pred = np.diff(X_pred.indptr) > 0
+        if X_pred.nnz and not np.all(X_pred.data):  # explicit zeros do not count as recommendations
+            has_pred = np.asarray((X_pred != 0).sum(axis=1)).ravel() > 0
+        missing = int(np.count_nonzero(has_hist & ~has_pred))
+        if missing > 0:
+            warnings.warn(f"{self.name} failed to recommend any items for {missing} users")
+
+    def _transform_fit_input(self, X):
+        return to_csr_matrix(X, binary=True)
+
+    def _transform_predict_input(self, X):
+        return to_csr_matrix(X, binary=True)
+
+    def fit(self, X):
+        start = time.time()
+        X = self._transform_fit_input(X)
+        self._fit(X)
+        self._check_fit_complete()
+        end = time.time()
+        logger.info(f"Fitting {self.name} complete - Took {end - start :.3}s")
+        return self
+
+    def predict(self, X) -> csr_matrix:
+        self._check_fit_complete()
+        X = self._transform_predict_input(X)
+        X_pred = self._predict(X)
+        self._check_prediction(X_pred, X)
+        return X_pred
+
+
+class ItemSimilarityMatrixAlgorithm(Algorithm):
+    """recpack/algorithms/base.py:220-279: predict = X @ similarity_matrix_, on the GPU.
+
+    Two additions follow the reference's own precedent ``predict_topK`` ("Use when the user x item
+    output matrix would become too large for RAM", base.py:427-430):
+
+    * ``predict_topK``: keep only the N best scores per user (score desc, item index asc);
+    * ``remove_history``: drop the user's own history items inside predict -- before the truncation,
+      which is where the pipeline removes them (pipelines/pipeline.py:174-175).
+
+    With both unset the full score matrix of the reference is returned."""
+
+    predict_topK = None
+    remove_history = False
+
+    # -- device model management ---------------------------------------------------------------
+    def _device_model_key(self):
+        S = self.similarity_matrix_
+        return (id(S), S.shape, S.nnz, S.data.ctypes.data, S.indices.ctypes.data)
+
+    def _ensure_device_model(self, engine):
+        S = self.similarity_matrix_
+        if not isinstance(S, csr_matrix):
+            S = csr_matrix(S)
+            self.similarity_matrix_ = S
+        key = (engine.device,) + self._device_model_key()
+        if getattr(engine, "_model_key", None) == key:
+            return
+        lists = getattr(self, "_fit_lists", None)
+        if lists is not None and lists.get("key") == self._device_model_key():
+            engine.model_load_topk(S.shape[0], lists["idx"].shape[1], lists["idx"], lists["val"], lists["len"])
+        else:
+            if not S.has_canonical_format:
+                S = S.copy()
+                S.sum_duplicates()
+            if S.nnz and not np.all(S.data):
+                S = S.copy()
+                S.eliminate_zeros()
+            engine.model_load_csr(S.shape[0], np.ascontiguousarray(S.indptr, dtype=np.int64),
+                                  np.ascontiguousarray(S.indices, dtype=np.int32),
+                                  np.ascontiguousarray(S.data, dtype=np.float64))
+        engine._model_key = key
+
+    def _predict(self, X: csr_matrix) -> csr_matrix:
+        engine = get_engine()
+        S = self.similarity_matrix_
+        if X.shape[1] != S.shape[0]:
+            raise ValueError("matmul: dimension mismatch with signature (n?,k),(k,m?)->(n?,m?)")
+        self._ensure_device_model(engine)
+        X, indptr, indices = binary_structure(X)
+        U = X.shape[0]
+        if self.predict_topK is None:
+            o_ptr, o_idx, o_val = engine.predict_csr(U, indptr, indices, mask_history=bool(self.remove_history))
+            return csr_matrix((o_val, o_idx, o_ptr), shape=(U, S.shape[1]))
+        N = int(self.predict_topK)
+        top = engine.predict_topn(U, indptr, indices, N, mask_history=bool(self.remove_history))
+        return lists_to_csr(top["idx"], top["val"], top["len"], S.shape[1], attach=True)
+
+    def _check_fit_complete(self):
+        super()._check_fit_complete()
+        assert hasattr(self, "similarity_matrix_")
+        S = self.similarity_matrix_
+        lists = getattr(self, "_fit_lists", None)
+        if lists is not None and lists.get("key") == self._device_model_key():
+            missing = int(np.count_nonzero(lists["len"] == 0))
+        else:
+            S = csr_matrix(S)
+            rows_with_score = np.diff(S.indptr) > 0
+            if S.nnz and not np.all(S.data):
+                rows_with_score = np.asarray((S != 0).sum(axis=1)).ravel() > 0
+            missing = int(S.shape[0] - np.count_nonzero(rows_with_score))
+        if missing > 0:
+            warnings.warn(f"{self.name} missing similar items for {missing} items.")
+
+
+class TopKItemSimilarityMatrixAlgorithm(ItemSimilarityMatrixAlgorithm):
+    """recpack/algorithms/base.py:282-304."""
+
+    def __init__(self, K):
+        super().__init__()
+        self.K = K
+
+
+def lists_to_csr(idx, val, ln, n_cols, attach=False) -> csr_matrix:
+    """[rows x K] rank-ordered lists (-1 padded) -> CSR whose rows keep the rank order.
+
+    When every row is full the arrays are used as they are (no copy)."""
+    rows, K = idx.shape
+    ln = np.asarray(ln)
+    if rows and int(ln.min()) == K:
+        indptr = np.arange(rows + 1, dtype=np.int64) * K
+        M = csr_matrix((val.reshape(-1), idx.reshape(-1), indptr), shape=(rows, n_cols))
+    else:
+        mask = np.arange(K, dtype=np.int32)[None, :] < ln[:, None]
+        indptr = np.zeros(rows + 1, dtype=np.int64)
+        np.cumsum(ln, out=indptr[1:])
+        M = csr_matrix((val[mask], idx[mask], indptr), shape=(rows, n_cols))
+    if attach:
+        M._rpk_topn = (idx, ln)
+    return M

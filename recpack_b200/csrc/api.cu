@@ -1,0 +1,157 @@
+// extern "C" surface of librpk.so (include/rpk.h).  Every entry point catches all C++ exceptions
+// and turns them into a status code + message.
+#include <string.h>
+
+#include "common.cuh"
+#include "internal.h"
+
+static thread_local std::string g_create_error;
+
+#define RPK_API_BEGIN(ctx)                       \
+  if (!(ctx)) return 1;                          \
+  try {                                          \
+    if (cudaSetDevice((ctx)->device) != cudaSuccess) throw rpk::Error("cudaSetDevice failed");
+
+#define RPK_API_END(ctx)                         \
+  }                                              \
+  catch (const std::exception& e) {              \
+    (ctx)->err = e.what();                       \
+    (ctx)->host_out_pending = false;             \
+    cudaGetLastError();                          \
+    return 1;                                    \
+  }                                              \
+  catch (...) {                                  \
+    (ctx)->err = "unknown error";                \
+    return 1;                                    \
+  }                                              \
+  return 0;
+
+extern "C" {
+
+int rpk_abi_version(void) { return RPK_ABI_VERSION; }
+
+int rpk_create(int device, rpk_ctx** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  try {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess) throw rpk::Error(std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) throw rpk::Error("device index out of range");
+    RPK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RPK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+      throw rpk::Error(std::string("librpk is built for sm_100a (Blackwell); device is ") + prop.name);
+    rpk_ctx* c = new rpk_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_max = (int)prop.sharedMemPerBlockOptin;
+    *out = c;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    cudaGetLastError();
+    return 1;
+  }
+  return 0;
+}
+
+void rpk_destroy(rpk_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->bufs)
+    if (kv.second.p) cudaFree(kv.second.p);
+  delete ctx;
+}
+
+const char* rpk_last_error(const rpk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rpk_set_stream(rpk_ctx* ctx, void* cuda_stream) {
+  RPK_API_BEGIN(ctx)
+  ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  RPK_API_END(ctx)
+}
+
+int rpk_sync(rpk_ctx* ctx) {
+  RPK_API_BEGIN(ctx)
+  RPK_CUDA(cudaStreamSynchronize(ctx->stream));
+  RPK_API_END(ctx)
+}
+
+int64_t rpk_launch_count(const rpk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int rpk_debug_flags(rpk_ctx* ctx, int flags) {
+  RPK_API_BEGIN(ctx)
+  ctx->flags = flags;
+  ctx->m_P = 0;  // predict geometry may change
+  RPK_API_END(ctx)
+}
+
+int rpk_fit_topk(rpk_ctx* ctx, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                 int similarity, const double* item_pow, int K, int64_t item_begin, int64_t item_end, int32_t* out_idx,
+                 int32_t* out_cnt, double* out_val, int32_t* out_len) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_fit(ctx, U, I, nnz, indptr, indices, similarity, item_pow, K, item_begin, item_end, out_idx, out_cnt, out_val,
+               out_len);
+  RPK_API_END(ctx)
+}
+
+int rpk_fit_item_counts(rpk_ctx* ctx, int32_t* out_counts, int64_t I) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_fit_item_counts(ctx, out_counts, I);
+  RPK_API_END(ctx)
+}
+
+int rpk_model_load_topk(rpk_ctx* ctx, int64_t I, int K, const int32_t* idx, const double* val, const int32_t* len) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_model_load_topk(ctx, I, K, idx, val, len);
+  RPK_API_END(ctx)
+}
+
+int rpk_model_load_csr(rpk_ctx* ctx, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                       const double* values) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_model_load_csr(ctx, I, nnz, indptr, indices, values);
+  RPK_API_END(ctx)
+}
+
+int rpk_predict_topn(rpk_ctx* ctx, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices, int N,
+                     int mask_history, int32_t* out_idx, double* out_val, int32_t* out_len) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_predict_topn(ctx, U, nnz, indptr, indices, N, mask_history, out_idx, out_val, out_len);
+  RPK_API_END(ctx)
+}
+
+int rpk_predict_csr_count(rpk_ctx* ctx, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                          int mask_history, int64_t* out_row_nnz) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_predict_csr_count(ctx, U, nnz, indptr, indices, mask_history, out_row_nnz);
+  RPK_API_END(ctx)
+}
+
+int rpk_predict_csr_fill(rpk_ctx* ctx, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                         int mask_history, const int64_t* out_indptr, int32_t* out_indices, double* out_values) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_predict_csr_fill(ctx, U, nnz, indptr, indices, mask_history, out_indptr, out_indices, out_values);
+  RPK_API_END(ctx)
+}
+
+int rpk_topk_csr(rpk_ctx* ctx, int64_t rows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                 const double* values, int K, int32_t* out_idx, int32_t* out_len) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_topk_csr(ctx, rows, nnz, indptr, indices, values, K, out_idx, out_len);
+  RPK_API_END(ctx)
+}
+
+int rpk_metrics_topn(rpk_ctx* ctx, int64_t U, int N, const int32_t* top_idx, const int32_t* top_len,
+                     const int64_t* true_indptr, const int32_t* true_indices, int64_t true_nnz, int n_metrics,
+                     const int32_t* kinds, const int32_t* Ks, const double* discount, const double* idcg, int maxK,
+                     double* per_user, double* sums, int64_t* n_users) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_metrics_topn(ctx, U, N, top_idx, top_len, true_indptr, true_indices, true_nnz, n_metrics, kinds, Ks, discount,
+                        idcg, maxK, per_user, sums, n_users);
+  RPK_API_END(ctx)
+}
+
+}  // extern "C"

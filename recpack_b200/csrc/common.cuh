@@ -1,0 +1,162 @@
+// Context, workspace and host<->device staging shared by all translation units of librpk.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/rpk.h"
+
+namespace rpk {
+
+typedef unsigned long long u64;
+
+struct Error : std::runtime_error {
+  explicit Error(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define RPK_CUDA(call)                                                                             \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      throw rpk::Error(std::string(#call) + " failed: " + cudaGetErrorString(e_) + " (" + __FILE__ + \
+                       ":" + std::to_string(__LINE__) + ")");                                      \
+  } while (0)
+
+#define RPK_REQUIRE(cond, msg)               \
+  do {                                       \
+    if (!(cond)) throw rpk::Error(msg);      \
+  } while (0)
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+enum {
+  DBG_WIDE_ACC = 1,    // predict: 64-bit CAS accumulators for every user
+  DBG_TINY_LIST = 2,   // selection: smallest legal candidate list
+  DBG_MULTI_PASS = 4,  // fit / predict: at least two item-range passes
+};
+
+}  // namespace rpk
+
+struct rpk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int flags = 0;
+  int sm_count = 0;
+  int smem_max = 0;  // max opt-in dynamic shared memory per block
+  std::map<std::string, rpk::Buf> bufs;
+  bool host_out_pending = false;
+
+  // ---- state of the last fit (device pointers into bufs)
+  int64_t fit_I = 0;
+
+  // ---- loaded model
+  int64_t m_I = 0;
+  int64_t m_nnz = 0;
+  int m_P = 0;        // item-range passes of predict
+  int m_R = 0;        // items per pass
+  int m_max_len = 0;  // longest model row
+
+  // ---- per-pass candidate counts of the last rpk_predict_csr_count
+  int64_t pc_U = 0;
+
+  template <class T>
+  T* buf(const std::string& name, size_t count) {
+    rpk::Buf& b = bufs[name];
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    if (b.cap < bytes) {
+      if (b.p) RPK_CUDA(cudaFree(b.p));
+      b.p = nullptr;
+      b.cap = 0;
+      size_t want = bytes + bytes / 8 + 256;
+      RPK_CUDA(cudaMalloc(&b.p, want));
+      b.cap = want;
+    }
+    return reinterpret_cast<T*>(b.p);
+  }
+  template <class T>
+  T* get(const std::string& name) {
+    auto it = bufs.find(name);
+    RPK_REQUIRE(it != bufs.end() && it->second.p, "internal: workspace '" + name + "' missing");
+    return reinterpret_cast<T*>(it->second.p);
+  }
+};
+
+namespace rpk {
+
+inline bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  cudaError_t e = cudaPointerGetAttributes(&a, p);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Input staging: returns a device pointer holding `count` elements of `p`.
+template <class T>
+const T* stage_in(rpk_ctx* c, const T* p, size_t count, const char* name) {
+  if (count == 0) return c->buf<T>(name, 1);
+  RPK_REQUIRE(p != nullptr, std::string("null input pointer: ") + name);
+  if (is_device_ptr(p)) return p;
+  T* d = c->buf<T>(name, count);
+  RPK_CUDA(cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  return d;
+}
+
+// Output staging: kernels write to .dev; finish() copies back when the caller's pointer is host memory.
+template <class T>
+struct Out {
+  T* user = nullptr;
+  T* dev = nullptr;
+  size_t count = 0;
+  bool host = false;
+  void init(rpk_ctx* c, T* p, size_t n, const char* name) {
+    user = p;
+    count = n;
+    if (!p) {
+      dev = nullptr;
+      return;
+    }
+    if (is_device_ptr(p)) {
+      dev = p;
+      host = false;
+    } else {
+      dev = c->buf<T>(name, n);
+      host = true;
+    }
+  }
+  void finish(rpk_ctx* c) {
+    if (user && host && count) {
+      RPK_CUDA(cudaMemcpyAsync(user, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+      c->host_out_pending = true;
+    }
+  }
+};
+
+inline void finish_call(rpk_ctx* c) {
+  if (c->host_out_pending) {
+    RPK_CUDA(cudaStreamSynchronize(c->stream));
+    c->host_out_pending = false;
+  }
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+#define RPK_LAUNCH_CHECK(ctx)          \
+  do {                                 \
+    (ctx)->launches++;                 \
+    RPK_CUDA(cudaGetLastError());      \
+  } while (0)
+
+}  // namespace rpk

@@ -1,0 +1,476 @@
+// ItemKNN fit on the GPU: exact co-occurrence counts per item row accumulated in shared memory,
+// with the similarity ordering, diagonal removal and top-K selection fused on the row while it
+// is still in shared memory -- the item x item matrix is never written to HBM.
+//
+// Replaces (reference, /root/reference):
+//   recpack/algorithms/nearest_neighbour.py:22-84   compute_conditional_probability / compute_cosine_similarity
+//   recpack/util.py:50-96                           get_top_K_ranks / get_top_K_values
+// Row i of the Gram is  c_ij = sum_{u in users(i)} [j in hist(u)]: one CTA owns (row i, item range p),
+// walks users(i) through the CSC copy of X and bumps 32-bit shared-memory counters (native ATOMS.ADD).
+#include "common.cuh"
+#include "internal.h"
+#include "prims.cuh"
+#include "select.cuh"
+
+namespace rpk {
+
+// ------------------------------------------------------------------------------------------
+// CSR preparation: item popularities, CSC transpose, per-row work estimate
+// ------------------------------------------------------------------------------------------
+__global__ void k_item_counts(const int* __restrict__ indices, int64_t nnz, int* __restrict__ n) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) atomicAdd(&n[indices[e]], 1);
+}
+
+// One warp per user: scatter the user id into the lists of its items; work[j] += d_u.
+__global__ void k_fill_csc(const int64_t* __restrict__ indptr, const int* __restrict__ indices, int64_t U,
+                           const int64_t* __restrict__ cscptr, int* __restrict__ cursor, int* __restrict__ csc_users,
+                           u64* __restrict__ work) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t u = warp; u < U; u += nwarps) {
+    int64_t b = indptr[u], e = indptr[u + 1];
+    u64 d = (u64)(e - b);
+    for (int64_t k = b + lane; k < e; k += 32) {
+      int j = indices[k];
+      int pos = atomicAdd(&cursor[j], 1);
+      csc_users[cscptr[j] + pos] = (int)u;
+      atomicAdd(&work[j], d);
+    }
+  }
+}
+
+__global__ void k_recip_f32(const int* __restrict__ n, float* __restrict__ rnf, int64_t I) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < I) rnf[j] = n[j] > 0 ? __frcp_rn((float)n[j]) : 0.f;
+}
+
+// usplit[u*(P+1)+p] = first position in row u whose item id >= p*R  (p = 0..P)
+__global__ void k_user_split(const int64_t* __restrict__ indptr, const int* __restrict__ indices, int64_t U, int P, int R,
+                             int64_t* __restrict__ usplit) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= U * (P + 1)) return;
+  int64_t u = t / (P + 1);
+  int p = (int)(t % (P + 1));
+  int64_t lo = indptr[u], hi = indptr[u + 1];
+  if (p == P) {
+    usplit[t] = hi;
+    return;
+  }
+  int64_t target = (int64_t)p * R;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (indices[mid] < target) lo = mid + 1;
+    else hi = mid;
+  }
+  usplit[t] = lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// Candidate sources for the selection routine
+// ------------------------------------------------------------------------------------------
+struct SimKey {
+  const int* n;
+  const float* rnf;
+  const double* pw;
+  int mode;  // 0 cosine, 1 conditional probability, 2 conditional probability with pop_discount
+
+  __device__ __forceinline__ u64 margin() const { return mode == 0 ? 32ull : 0ull; }
+
+  // cosine: approximate fp32 key c^2/n_j (a few ulp of error, covered by margin()), exact order restored by cmp3
+  __device__ __forceinline__ void make(int c, int j, Entry& e, u64& k) const {
+    e.idx = j;
+    e.aux = c;
+    if (mode == 0) {
+      float a = (float)c;
+      float f = __fmul_rn(__fmul_rn(a, a), rnf[j]);
+      k = (u64)__float_as_uint(f);
+      e.key = (u64)(unsigned)n[j];
+    } else if (mode == 1) {
+      k = (u64)__double_as_longlong((double)c);
+      e.key = k;
+    } else {
+      k = (u64)__double_as_longlong(__dmul_rn((double)c, pw[j]));
+      e.key = k;
+    }
+  }
+  __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const {
+    if (mode == 0) {
+      // c_a^2 / n_a  vs  c_b^2 / n_b   <=>   c_a^2 * n_b  vs  c_b^2 * n_a   (128-bit exact)
+      u64 ca2 = (u64)(unsigned)a.aux * (u64)(unsigned)a.aux;
+      u64 cb2 = (u64)(unsigned)b.aux * (u64)(unsigned)b.aux;
+      u64 l_lo = ca2 * b.key, l_hi = __umul64hi(ca2, b.key);
+      u64 r_lo = cb2 * a.key, r_hi = __umul64hi(cb2, a.key);
+      if (l_hi != r_hi) return l_hi > r_hi ? 1 : -1;
+      if (l_lo != r_lo) return l_lo > r_lo ? 1 : -1;
+      return 0;
+    }
+    if (a.key != b.key) return a.key > b.key ? 1 : -1;
+    return 0;
+  }
+};
+
+struct RowCountSrc {  // dense shared-memory counters of one (row, item range)
+  SimKey sk;
+  const int* cnt;
+  int r0, ns, self;
+  __device__ __forceinline__ int nslots() const { return ns; }
+  __device__ __forceinline__ u64 margin() const { return sk.margin(); }
+  __device__ __forceinline__ bool load(int slot, Entry& e, u64& k) const {
+    int c = cnt[slot];
+    int j = r0 + slot;
+    if (c == 0 || j == self) return false;
+    sk.make(c, j, e, k);
+    return true;
+  }
+  __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const { return sk.cmp3(a, b); }
+};
+
+struct PairListSrc {  // (idx, cnt) pairs in global memory, idx < 0 = empty slot
+  SimKey sk;
+  const int* idx;
+  const int* cnt;
+  int ns;
+  __device__ __forceinline__ int nslots() const { return ns; }
+  __device__ __forceinline__ u64 margin() const { return sk.margin(); }
+  __device__ __forceinline__ bool load(int slot, Entry& e, u64& k) const {
+    int j = idx[slot];
+    if (j < 0) return false;
+    sk.make(cnt[slot], j, e, k);
+    return true;
+  }
+  __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const { return sk.cmp3(a, b); }
+};
+
+// ------------------------------------------------------------------------------------------
+// The fit kernel
+// ------------------------------------------------------------------------------------------
+struct FitParams {
+  const int64_t* indptr;
+  const int* indices;
+  const int64_t* usplit;  // null when P == 1
+  const int64_t* cscptr;
+  const int* csc_users;
+  SimKey sk;
+  const int* order;
+  int nrows, P, R, I, K;
+  int64_t item_begin;
+  int cap, direct_cap;
+  int* queue;
+  int* out_idx;
+  int* out_cnt;
+  int* out_len;
+};
+
+__device__ __forceinline__ size_t sel_smem_bytes(int cap) {
+  return (size_t)cap * sizeof(Entry) + SEL_BINS * sizeof(int) + ((sizeof(SelShared) + 15) / 16) * 16;
+}
+
+__global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Entry* list = reinterpret_cast<Entry*>(smem);
+  int* hist = reinterpret_cast<int*>(smem + (size_t)p.cap * sizeof(Entry));
+  SelShared* sh = reinterpret_cast<SelShared*>(hist + SEL_BINS);
+  int* cnt = reinterpret_cast<int*>(smem + sel_smem_bytes(p.cap));
+  __shared__ int s_work;
+
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const int total = p.nrows * p.P;
+  for (;;) {
+    if (tid == 0) s_work = atomicAdd(p.queue, 1);
+    __syncthreads();
+    const int w = s_work;
+    __syncthreads();
+    if (w >= total) break;
+    const int i = p.order[w / p.P];
+    const int pass = w % p.P;
+    const int r0 = pass * p.R;
+    const int ns = min(p.R, p.I - r0);
+    const int64_t ub = p.cscptr[i], ue = p.cscptr[i + 1];
+    const int64_t orow = ((int64_t)i - p.item_begin) * p.P + pass;
+    int* o_idx = p.out_idx + orow * p.K;
+    int* o_cnt = p.out_cnt + orow * p.K;
+    if (ue == ub) {  // item never seen: empty row (base.py:257-279 warns about these)
+      for (int t = tid; t < p.K; t += nt) {
+        o_idx[t] = -1;
+        o_cnt[t] = 0;
+      }
+      if (tid == 0) p.out_len[orow] = 0;
+      continue;
+    }
+    for (int s = tid; s < ns; s += nt) cnt[s] = 0;
+    __syncthreads();
+    // ---- accumulate: each warp takes 32 users of the item at a time
+    for (int64_t base = ub + (int64_t)warp * 32; base < ue; base += (int64_t)nwarps * 32) {
+      const int64_t k = base + lane;
+      int64_t beg = 0;
+      int len = 0;
+      if (k < ue) {
+        const int u = p.csc_users[k];
+        if (p.usplit) {
+          const int64_t* us = p.usplit + (int64_t)u * (p.P + 1) + pass;
+          beg = us[0];
+          len = (int)(us[1] - beg);
+        } else {
+          beg = p.indptr[u];
+          len = (int)(p.indptr[u + 1] - beg);
+        }
+      }
+      const int nvalid = (int)min((int64_t)32, ue - base);
+      for (int l = 0; l < nvalid; ++l) {
+        const int64_t b = __shfl_sync(0xffffffffu, beg, l);
+        const int n = __shfl_sync(0xffffffffu, len, l);
+        for (int e = lane; e < n; e += 32) atomicAdd(&cnt[p.indices[b + e] - r0], 1);
+      }
+    }
+    __syncthreads();
+    // ---- fused epilogue: similarity ordering, diagonal removal, top-K -- all on the shared-memory row
+    RowCountSrc src{p.sk, cnt, r0, ns, i};
+    const int m = block_select_topk(src, p.K, list, p.cap, p.direct_cap, hist, sh);
+    for (int t = tid; t < p.K; t += nt) {
+      o_idx[t] = t < m ? list[t].idx : -1;
+      o_cnt[t] = t < m ? list[t].aux : 0;
+    }
+    if (tid == 0) p.out_len[orow] = m;
+    __syncthreads();
+  }
+}
+
+// Merge the P per-range lists of a row (only when the item space does not fit one pass).
+struct MergeParams {
+  SimKey sk;
+  const int* part_idx;
+  const int* part_cnt;
+  int P, K, cap, direct_cap;
+  int* out_idx;
+  int* out_cnt;
+  int* out_len;
+};
+__global__ void __launch_bounds__(256) k_fit_merge(MergeParams p, int nrows) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Entry* list = reinterpret_cast<Entry*>(smem);
+  int* hist = reinterpret_cast<int*>(smem + (size_t)p.cap * sizeof(Entry));
+  SelShared* sh = reinterpret_cast<SelShared*>(hist + SEL_BINS);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    PairListSrc src{p.sk, p.part_idx + (int64_t)row * p.P * p.K, p.part_cnt + (int64_t)row * p.P * p.K, p.P * p.K};
+    const int m = block_select_topk(src, p.K, list, p.cap, p.direct_cap, hist, sh);
+    for (int t = tid; t < p.K; t += nt) {
+      p.out_idx[(int64_t)row * p.K + t] = t < m ? list[t].idx : -1;
+      p.out_cnt[(int64_t)row * p.K + t] = t < m ? list[t].aux : 0;
+    }
+    if (tid == 0) p.out_len[row] = m;
+    __syncthreads();
+  }
+}
+
+// Similarity values with the reference's floating-point operation order (see include/rpk.h).
+__global__ void k_fit_values(const int* __restrict__ idx, const int* __restrict__ cnt, const int* __restrict__ n,
+                             const double* __restrict__ pw, int mode, int64_t item_begin, int64_t nrows, int K,
+                             double* __restrict__ val) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrows * K) return;
+  const int j = idx[t];
+  double v = 0.0;
+  if (j >= 0) {
+    const int i = (int)(item_begin + t / K);
+    const int c = cnt[t];
+    if (mode == 0) {
+      // sklearn row-normalises X^T: a = 1/sqrt(n) (sparsefuncs_fast.pyx:578-604); scipy's csr_matmat then
+      // adds the c identical products one at a time
+      const double ai = __ddiv_rn(1.0, __dsqrt_rn((double)n[i]));
+      const double aj = __ddiv_rn(1.0, __dsqrt_rn((double)n[j]));
+      const double prod = __dmul_rn(ai, aj);
+      double s = 0.0;
+      for (int r = 0; r < c; ++r) s = __dadd_rn(s, prod);
+      v = s;
+    } else {
+      const double inv = __ddiv_rn(1.0, (double)n[i]);  // algorithms/util.py:132
+      v = __dmul_rn(inv, (double)c);                   // A @ co_mat
+      if (mode == 2) v = __dmul_rn(v, pw[j]);          // ... @ A.power(pop_discount)
+    }
+  }
+  val[t] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host driver
+// ------------------------------------------------------------------------------------------
+static int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr_u, const int32_t* indices_u,
+             int similarity, const double* item_pow_u, int K, int64_t item_begin, int64_t item_end, int32_t* out_idx_u,
+             int32_t* out_cnt_u, double* out_val_u, int32_t* out_len_u) {
+  RPK_REQUIRE(U >= 0 && I >= 0 && nnz >= 0, "negative dimension");
+  RPK_REQUIRE(I < (int64_t)1 << 24, "more than 2^24 items are not supported");
+  RPK_REQUIRE(U < (int64_t)1 << 31, "more than 2^31 users are not supported");
+  RPK_REQUIRE(K >= 1 && K <= 4096, "K must be in [1, 4096]");
+  RPK_REQUIRE(0 <= item_begin && item_begin <= item_end && item_end <= I, "bad item range");
+  RPK_REQUIRE(similarity == RPK_SIM_COSINE || similarity == RPK_SIM_CONDPROB, "unknown similarity");
+  RPK_REQUIRE(out_idx_u && out_len_u, "out_idx / out_len must not be null");
+  cudaStream_t st = c->stream;
+  const int64_t nrows = item_end - item_begin;
+  const int mode = similarity == RPK_SIM_COSINE ? 0 : (item_pow_u ? 2 : 1);
+
+  const int64_t* indptr = stage_in(c, indptr_u, (size_t)U + 1, "fit_indptr");
+  const int32_t* indices = stage_in(c, indices_u, (size_t)nnz, "fit_indices");
+  const double* pw = item_pow_u ? stage_in(c, item_pow_u, (size_t)I, "fit_pw") : nullptr;
+
+  // ---- preparation
+  int* n = c->buf<int>("fit_n", (size_t)I);
+  int* cursor = c->buf<int>("fit_cursor", (size_t)I);
+  u64* work = c->buf<u64>("fit_work", (size_t)I);
+  int64_t* cscptr = c->buf<int64_t>("fit_cscptr", (size_t)I + 1);
+  int* csc_users = c->buf<int>("fit_csc_users", (size_t)nnz);
+  float* rnf = c->buf<float>("fit_rnf", (size_t)I);
+  int* order = c->buf<int>("fit_order", (size_t)nrows);
+  int* bcnt = c->buf<int>("fit_bcnt", 65 * 2 + 2);
+  int* boff = bcnt + 65;
+  int* queue = boff + 65;
+  c->fit_I = I;
+  RPK_CUDA(cudaMemsetAsync(n, 0, sizeof(int) * (size_t)I, st));
+  RPK_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)I, st));
+  RPK_CUDA(cudaMemsetAsync(work, 0, sizeof(u64) * (size_t)I, st));
+  RPK_CUDA(cudaMemsetAsync(bcnt, 0, sizeof(int) * (65 * 2 + 2), st));
+  if (nnz > 0) {
+    int blocks = (int)std::min<int64_t>((nnz + 255) / 256, (int64_t)c->sm_count * 16);
+    k_item_counts<<<blocks, 256, 0, st>>>(indices, nnz, n);
+    RPK_LAUNCH_CHECK(c);
+  }
+  k_scan_i32_i64<<<1, 1024, 0, st>>>(n, cscptr, I);
+  RPK_LAUNCH_CHECK(c);
+  if (nnz > 0 && U > 0) {
+    int blocks = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
+    k_fill_csc<<<blocks, 256, 0, st>>>(indptr, indices, U, cscptr, cursor, csc_users, work);
+    RPK_LAUNCH_CHECK(c);
+  }
+  if (I > 0) {
+    k_recip_f32<<<ceil_div(I, 256), 256, 0, st>>>(n, rnf, I);
+    RPK_LAUNCH_CHECK(c);
+  }
+
+  Out<int32_t> o_idx, o_cnt, o_len;
+  Out<double> o_val;
+  o_idx.init(c, out_idx_u, (size_t)nrows * K, "fit_out_idx");
+  o_len.init(c, out_len_u, (size_t)nrows, "fit_out_len");
+  int32_t* cnt_dev;  // counts are always produced (values need them)
+  if (out_cnt_u) {
+    o_cnt.init(c, out_cnt_u, (size_t)nrows * K, "fit_out_cnt");
+    cnt_dev = o_cnt.dev;
+  } else {
+    cnt_dev = c->buf<int32_t>("fit_out_cnt", (size_t)nrows * K);
+  }
+  o_val.init(c, out_val_u, (size_t)nrows * K, "fit_out_val");
+
+  if (nrows > 0) {
+    k_bucket_count<<<ceil_div(nrows, 256), 256, 0, st>>>(work, item_begin, item_end, bcnt);
+    RPK_LAUNCH_CHECK(c);
+    k_bucket_offsets<<<1, 32, 0, st>>>(bcnt, boff);
+    RPK_LAUNCH_CHECK(c);
+    k_bucket_scatter<<<ceil_div(nrows, 256), 256, 0, st>>>(work, item_begin, item_end, boff, order);
+    RPK_LAUNCH_CHECK(c);
+
+    // ---- geometry: item-range passes so that the counters of one pass fit shared memory
+    const bool tiny = c->flags & DBG_TINY_LIST;
+    const int cap = std::max(tiny ? 64 : 2048, next_pow2(2 * K));
+    const int direct_cap = tiny ? K : cap;
+    const size_t fixed = (size_t)cap * sizeof(Entry) + SEL_BINS * sizeof(int) + ((sizeof(SelShared) + 15) / 16) * 16;
+    const size_t avail = (size_t)c->smem_max - fixed - 1024;  // 1 KB slack for static shared memory
+    RPK_REQUIRE((size_t)c->smem_max > fixed + 1024 + 4096, "K too large for shared memory");
+    int64_t Rmax = (int64_t)(avail / sizeof(int)) & ~(int64_t)3;
+    int P = (int)((I + Rmax - 1) / Rmax);
+    if (P < 1) P = 1;
+    if ((c->flags & DBG_MULTI_PASS) && P < 2 && I >= 2) P = 2;
+    int R = (int)(((I + P - 1) / P + 3) & ~(int64_t)3);
+    const size_t smem = fixed + (size_t)R * sizeof(int);
+    const int nt = R >= 16384 ? 1024 : (R >= 4096 ? 512 : 256);
+
+    const int64_t* usplit = nullptr;
+    if (P > 1) {
+      int64_t* us = c->buf<int64_t>("fit_usplit", (size_t)U * (P + 1));
+      if (U > 0) {
+        k_user_split<<<ceil_div(U * (P + 1), 256), 256, 0, st>>>(indptr, indices, U, P, R, us);
+        RPK_LAUNCH_CHECK(c);
+      }
+      usplit = us;
+    }
+    int* part_idx = o_idx.dev;
+    int* part_cnt = cnt_dev;
+    int* part_len = o_len.dev;
+    if (P > 1) {
+      part_idx = c->buf<int>("fit_part_idx", (size_t)nrows * P * K);
+      part_cnt = c->buf<int>("fit_part_cnt", (size_t)nrows * P * K);
+      part_len = c->buf<int>("fit_part_len", (size_t)nrows * P);
+    }
+    FitParams fp;
+    fp.indptr = indptr;
+    fp.indices = indices;
+    fp.usplit = usplit;
+    fp.cscptr = cscptr;
+    fp.csc_users = csc_users;
+    fp.sk = SimKey{n, rnf, pw, mode};
+    fp.order = order;
+    fp.nrows = (int)nrows;
+    fp.P = P;
+    fp.R = R;
+    fp.I = (int)I;
+    fp.K = K;
+    fp.item_begin = item_begin;
+    fp.cap = cap;
+    fp.direct_cap = direct_cap;
+    fp.queue = queue;
+    fp.out_idx = part_idx;
+    fp.out_cnt = part_cnt;
+    fp.out_len = part_len;
+    RPK_CUDA(cudaFuncSetAttribute(k_fit_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    RPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fit_rows, nt, smem));
+    RPK_REQUIRE(occ >= 1, "fit kernel does not fit on an SM");
+    const int64_t total = nrows * P;
+    const int grid = (int)std::min<int64_t>(total, (int64_t)c->sm_count * occ);
+    k_fit_rows<<<grid, nt, smem, st>>>(fp);
+    RPK_LAUNCH_CHECK(c);
+    if (P > 1) {
+      MergeParams mp;
+      mp.sk = fp.sk;
+      mp.part_idx = part_idx;
+      mp.part_cnt = part_cnt;
+      mp.P = P;
+      mp.K = K;
+      mp.cap = cap;
+      mp.direct_cap = direct_cap;
+      mp.out_idx = o_idx.dev;
+      mp.out_cnt = cnt_dev;
+      mp.out_len = o_len.dev;
+      RPK_CUDA(cudaFuncSetAttribute(k_fit_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fixed));
+      const int mgrid = (int)std::min<int64_t>(nrows, (int64_t)c->sm_count * 8);
+      k_fit_merge<<<mgrid, 256, fixed, st>>>(mp, (int)nrows);
+      RPK_LAUNCH_CHECK(c);
+    }
+    if (o_val.dev) {
+      k_fit_values<<<ceil_div(nrows * K, 256), 256, 0, st>>>(o_idx.dev, cnt_dev, n, pw, mode, item_begin, nrows, K, o_val.dev);
+      RPK_LAUNCH_CHECK(c);
+    }
+  }
+  o_idx.finish(c);
+  o_cnt.finish(c);
+  o_val.finish(c);
+  o_len.finish(c);
+  finish_call(c);
+}
+
+void run_fit_item_counts(rpk_ctx* c, int32_t* out_counts, int64_t I) {
+  RPK_REQUIRE(c->fit_I == I && I >= 0, "rpk_fit_item_counts: no fit with this item count on the context");
+  Out<int32_t> o;
+  o.init(c, out_counts, (size_t)I, "fit_n_out");
+  if (I > 0) RPK_CUDA(cudaMemcpyAsync(o.dev, c->get<int>("fit_n"), sizeof(int) * (size_t)I, cudaMemcpyDeviceToDevice, c->stream));
+  o.finish(c);
+  finish_call(c);
+}
+
+}  // namespace rpk

@@ -1,0 +1,31 @@
+// Host-side drivers implemented in the .cu files; called by the C ABI in api.cu.
+#pragma once
+#include <stdint.h>
+
+struct rpk_ctx;
+
+namespace rpk {
+
+void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices, int similarity,
+             const double* item_pow, int K, int64_t item_begin, int64_t item_end, int32_t* out_idx, int32_t* out_cnt,
+             double* out_val, int32_t* out_len);
+void run_fit_item_counts(rpk_ctx* c, int32_t* out_counts, int64_t I);
+
+void run_model_load_topk(rpk_ctx* c, int64_t I, int K, const int32_t* idx, const double* val, const int32_t* len);
+void run_model_load_csr(rpk_ctx* c, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                        const double* values);
+void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices, int N,
+                      int mask_history, int32_t* out_idx, double* out_val, int32_t* out_len);
+void run_predict_csr_count(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                           int mask_history, int64_t* out_row_nnz);
+void run_predict_csr_fill(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                          int mask_history, const int64_t* out_indptr, int32_t* out_indices, double* out_values);
+
+void run_topk_csr(rpk_ctx* c, int64_t rows, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                  const double* values, int K, int32_t* out_idx, int32_t* out_len);
+void run_metrics_topn(rpk_ctx* c, int64_t U, int N, const int32_t* top_idx, const int32_t* top_len,
+                      const int64_t* true_indptr, const int32_t* true_indices, int64_t true_nnz, int n_metrics,
+                      const int32_t* kinds, const int32_t* Ks, const double* discount, const double* idcg, int maxK,
+                      double* per_user, double* sums, int64_t* n_users);
+
+}  // namespace rpk

@@ -1,0 +1,412 @@
+// Block-wide exact top-K selection shared by the fit epilogue, the top-N of predict and the
+// CSR row ranking.  Replaces np.argpartition + the Python row loop of
+// recpack/util.py:50-77 (get_top_K_ranks) with a deterministic rule: best key first, ties by
+// ascending index.
+//
+// A "source" enumerates candidate slots.  For every candidate it yields
+//   - a 64-bit SORTABLE key `akey` (larger = better) that is allowed to be approximate: it may
+//     mis-order two candidates only if their akeys differ by at most Src::margin();
+//   - an Entry (16 B) carrying what the exact comparator needs.
+// Src::cmp3(a, b) is the exact three-way comparison of two entries' keys (index excluded).
+//
+// Algorithm (all control flow is block-uniform):
+//   A. one scan: count candidates, min/max akey, and copy them to `list` while they fit.
+//      If they all fit -> sort, done.
+//   B. radix refinement on akey: 4096-bin histogram over [lo, hi], descend into the bin that
+//      holds the K-th largest akey until the candidates with akey >= lo (minus margin) fit.
+//   C. if they never fit (a huge group of equal / near-equal akeys straddles the K-th place):
+//      exact quick-select inside that band with cmp3, and inside an exactly-tied class a second
+//      radix refinement on the index picks the smallest indices.
+//   D. bitonic sort of the (<= cap) survivors with the exact total order; the first K are the result.
+#pragma once
+#include <stdint.h>
+
+namespace rpk {
+
+typedef unsigned long long u64;
+
+struct __align__(16) Entry {
+  u64 key;
+  int idx;
+  int aux;
+};
+
+constexpr int SEL_BINS = 4096;
+constexpr int SENTINEL_IDX = 0x7fffffff;
+
+struct SelShared {
+  u64 kmin, kmax;
+  u64 lo, hi;
+  Entry piv;
+  int count;
+  int count2;
+  int bstar;
+  int g_new;
+  int n_in;
+  int piv_slot;
+  int warp_tot[33];
+};
+
+__device__ __forceinline__ u64 warp_min_u64(u64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    u64 t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t < v ? t : v;
+  }
+  return v;
+}
+__device__ __forceinline__ u64 warp_max_u64(u64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    u64 t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t > v ? t : v;
+  }
+  return v;
+}
+
+// Warp-aggregated append of `e` (when `take`) to list; returns nothing, counts every taker in
+// *counter even when the list is full (entries beyond `cap` are dropped, the count tells).
+__device__ __forceinline__ void append_entry(bool take, const Entry& e, Entry* list, int cap, int* counter) {
+  unsigned m = __ballot_sync(0xffffffffu, take);
+  if (m == 0) return;
+  int lane = threadIdx.x & 31;
+  int leader = __ffs(m) - 1;
+  int pos = 0;
+  if (lane == leader) pos = atomicAdd(counter, __popc(m));
+  pos = __shfl_sync(0xffffffffu, pos, leader);
+  if (take) {
+    int my = pos + __popc(m & ((1u << lane) - 1u));
+    if (my < cap) list[my] = e;
+  }
+}
+
+// Exact total order used by the final sort: true when a must precede b.
+template <class Src>
+__device__ __forceinline__ bool entry_before(const Src& src, const Entry& a, const Entry& b) {
+  if (a.idx == SENTINEL_IDX) return false;
+  if (b.idx == SENTINEL_IDX) return true;
+  int c = src.cmp3(a, b);
+  if (c != 0) return c > 0;
+  return a.idx < b.idx;
+}
+
+template <class Src>
+__device__ void bitonic_sort_entries(const Src& src, Entry* list, int n_pow2) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int k = 2; k <= n_pow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n_pow2; i += nt) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          Entry a = list[i], b = list[ixj];
+          bool up = (i & k) == 0;
+          if (entry_before(src, b, a) == up) {
+            list[i] = b;
+            list[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// One refinement run.  `f(slot, key)` returns true when the slot belongs to the group being
+// refined and sets its key.  On entry [lo, hi] bounds the group's keys, n_in = group size,
+// g = number of group members already known to be above hi (0 at the start).
+// Descends while  g + n_in > room  and  lo < hi.  Results in sh->lo / sh->hi / sh->g_new / sh->n_in.
+template <class F>
+__device__ void refine_keys(F f, int nslots, int need, int room, u64 lo, u64 hi, int g, int n_in, int* hist,
+                            SelShared* sh) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  while (g + n_in > room && lo < hi) {
+    const u64 range = hi - lo;
+    const int bits = 64 - __clzll((long long)range);
+    const int shift = bits > 12 ? bits - 12 : 0;
+    const int nb = (int)(range >> shift) + 1;
+    for (int b = tid; b < nb; b += nt) hist[b] = 0;
+    __syncthreads();
+    for (int base = 0; base < nslots; base += nt) {
+      int slot = base + tid;
+      u64 k;
+      if (slot < nslots && f(slot, k) && k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
+    }
+    __syncthreads();
+    // locate the bin holding the need-th largest key, scanning bins from the top
+    const int per = (nb + nt - 1) / nt;
+    const int b0 = tid * per;
+    const int b1 = min(nb, b0 + per);
+    int tsum = 0;
+    for (int b = b0; b < b1; ++b) tsum += hist[b];
+    int incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) sh->warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int v = lane < nwarps ? sh->warp_tot[lane] : 0;
+      int iv = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, iv, o);
+        if (lane >= o) iv += t;
+      }
+      sh->warp_tot[lane] = iv - v;  // exclusive prefix of warp totals
+      if (lane == 31) sh->warp_tot[32] = iv;
+    }
+    __syncthreads();
+    const int total = sh->warp_tot[32];
+    const int prefix_excl = sh->warp_tot[warp] + incl - tsum;
+    int above = g + (total - prefix_excl - tsum);  // group members in bins owned by higher threads
+    if (above < need && above + tsum >= need) {
+      for (int b = b1 - 1; b >= b0; --b) {
+        int h = hist[b];
+        if (above + h >= need) {
+          sh->bstar = b;
+          sh->g_new = above;
+          sh->n_in = h;
+          break;
+        }
+        above += h;
+      }
+    }
+    __syncthreads();
+    const int bstar = sh->bstar;
+    g = sh->g_new;
+    n_in = sh->n_in;
+    const u64 nlo = lo + ((u64)bstar << shift);
+    const u64 span = shift >= 64 ? ~0ull : (((u64)1 << shift) - 1);
+    u64 nhi = nlo + span;
+    if (nhi > hi || nhi < nlo) nhi = hi;
+    lo = nlo;
+    hi = nhi;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    sh->lo = lo;
+    sh->hi = hi;
+    sh->g_new = g;
+    sh->n_in = n_in;
+  }
+  __syncthreads();
+}
+
+// Returns m = number of selected entries (<= K); list[0..m) holds them best-first.
+// Requirements: blockDim.x multiple of 32; cap >= K, cap a power of two; direct_cap <= cap;
+// hist has SEL_BINS ints; list has cap entries.
+template <class Src>
+__device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, int direct_cap, int* hist,
+                                 SelShared* sh) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int nslots = src.nslots();
+  const u64 M = src.margin();
+  if (K > cap) K = cap;
+  if (direct_cap < K) direct_cap = K;  // the refinement needs at least K candidates
+  if (direct_cap > cap) direct_cap = cap;
+
+  // ---- A: count, bounds, optimistic copy
+  if (tid == 0) {
+    sh->count = 0;
+    sh->kmin = ~0ull;
+    sh->kmax = 0ull;
+  }
+  __syncthreads();
+  {
+    u64 lmin = ~0ull, lmax = 0ull;
+    for (int base = 0; base < nslots; base += nt) {
+      int slot = base + tid;
+      Entry e;
+      u64 k = 0;
+      bool c = slot < nslots && src.load(slot, e, k);
+      append_entry(c, e, list, direct_cap, &sh->count);
+      if (c) {
+        lmin = k < lmin ? k : lmin;
+        lmax = k > lmax ? k : lmax;
+      }
+    }
+    lmin = warp_min_u64(lmin);
+    lmax = warp_max_u64(lmax);
+    if (lane == 0) {
+      atomicMin(&sh->kmin, lmin);
+      atomicMax(&sh->kmax, lmax);
+    }
+  }
+  __syncthreads();
+  const int n_c = sh->count;
+  int m;
+  if (n_c <= direct_cap) {
+    m = n_c;
+  } else {
+    // ---- B: refine on the approximate key until the survivors fit
+    auto keyf = [&](int slot, u64& k) -> bool {
+      Entry e;
+      return src.load(slot, e, k);
+    };
+    const int room = cap / 2 > K ? cap / 2 : K;
+    refine_keys(keyf, nslots, K, room, sh->kmin, sh->kmax, 0, n_c, hist, sh);
+    u64 lo = sh->lo, hi = sh->hi;
+    int g = sh->g_new, n_in = sh->n_in;
+    u64 thr = lo > M ? lo - M : 0;
+    if (tid == 0) sh->count = 0;
+    __syncthreads();
+    for (int base = 0; base < nslots; base += nt) {
+      int slot = base + tid;
+      Entry e;
+      u64 k = 0;
+      bool c = slot < nslots && src.load(slot, e, k) && k >= thr;
+      append_entry(c, e, list, cap, &sh->count);
+    }
+    __syncthreads();
+    m = sh->count;
+    if (m > cap) {
+      // ---- C: a band of (near-)equal keys is too large.  Pin tau = the K-th largest akey.
+      __syncthreads();
+      refine_keys(keyf, nslots, K, -1, lo, hi, g, n_in, hist, sh);
+      const u64 tau = sh->lo;
+      const u64 band_lo = tau > M ? tau - M : 0;
+      const u64 band_hi = tau + M < tau ? ~0ull : tau + M;
+      // certain members: akey above the band (fewer than K of them)
+      if (tid == 0) sh->count = 0;
+      __syncthreads();
+      for (int base = 0; base < nslots; base += nt) {
+        int slot = base + tid;
+        Entry e;
+        u64 k = 0;
+        bool c = slot < nslots && src.load(slot, e, k) && k > band_hi;
+        append_entry(c, e, list, cap, &sh->count);
+      }
+      __syncthreads();
+      int have = sh->count;  // entries in list so far (all certain)
+      int need = K - have;   // still to take from the band, by exact order
+      bool has_lb = false, has_ub = false;
+      Entry lb = {0, 0, 0}, ub = {0, 0, 0};
+      // group = band members with exact key strictly between lb and ub
+      auto in_group = [&](int slot, Entry& e) -> bool {
+        u64 k;
+        if (!src.load(slot, e, k) || k < band_lo || k > band_hi) return false;
+        if (has_ub && src.cmp3(e, ub) >= 0) return false;
+        if (has_lb && src.cmp3(e, lb) <= 0) return false;
+        return true;
+      };
+      while (need > 0) {
+        // pivot: the group member in the lowest slot
+        if (tid == 0) sh->piv_slot = 0x7fffffff;
+        __syncthreads();
+        {
+          int best = 0x7fffffff;
+          for (int base = 0; base < nslots && best == 0x7fffffff; base += nt) {
+            int slot = base + tid;
+            Entry e;
+            if (slot < nslots && in_group(slot, e)) best = slot;
+          }
+          if (best != 0x7fffffff) atomicMin(&sh->piv_slot, best);
+        }
+        __syncthreads();
+        const int ps = sh->piv_slot;
+        if (ps == 0x7fffffff) break;  // group exhausted (cannot happen while need > 0)
+        if (tid == 0) {
+          Entry e;
+          u64 k;
+          src.load(ps, e, k);
+          sh->piv = e;
+          sh->count = 0;   // greater than pivot
+          sh->count2 = 0;  // equal to pivot
+        }
+        __syncthreads();
+        const Entry piv = sh->piv;
+        {
+          int gt = 0, eq = 0;
+          for (int base = 0; base < nslots; base += nt) {
+            int slot = base + tid;
+            Entry e;
+            if (slot < nslots && in_group(slot, e)) {
+              int c = src.cmp3(e, piv);
+              gt += c > 0;
+              eq += c == 0;
+            }
+          }
+          gt = __reduce_add_sync(0xffffffffu, gt);
+          eq = __reduce_add_sync(0xffffffffu, eq);
+          if (lane == 0) {
+            if (gt) atomicAdd(&sh->count, gt);
+            if (eq) atomicAdd(&sh->count2, eq);
+          }
+        }
+        __syncthreads();
+        const int gt = sh->count, eq = sh->count2;
+        __syncthreads();
+        if (gt >= need) {  // the need-th best is above the pivot
+          has_lb = true;
+          lb = piv;
+          continue;
+        }
+        // everything above the pivot is in
+        if (tid == 0) sh->count = have;
+        __syncthreads();
+        const bool take_eq = gt + eq <= need || eq <= cap - have - gt;
+        for (int base = 0; base < nslots; base += nt) {
+          int slot = base + tid;
+          Entry e;
+          bool c = false;
+          if (slot < nslots && in_group(slot, e)) {
+            int c3 = src.cmp3(e, piv);
+            c = c3 > 0 || (c3 == 0 && take_eq);
+          }
+          append_entry(c, e, list, cap, &sh->count);
+        }
+        __syncthreads();
+        have = sh->count;
+        if (gt + eq < need) {  // pivot class fully in, continue below the pivot
+          need -= gt + eq;
+          has_ub = true;
+          ub = piv;
+          continue;
+        }
+        if (take_eq) break;  // the class fitted as a whole; the final sort trims it
+        // ---- exact tie class larger than the list: take the (need - gt) smallest indices
+        const int need_idx = need - gt;
+        auto idxf = [&](int slot, u64& k) -> bool {
+          Entry e;
+          if (!in_group(slot, e) || src.cmp3(e, piv) != 0) return false;
+          k = (u64)(unsigned)(SENTINEL_IDX - e.idx);
+          return true;
+        };
+        refine_keys(idxf, nslots, need_idx, cap - have, 0ull, (u64)SENTINEL_IDX, 0, eq, hist, sh);
+        const u64 ilo = sh->lo;
+        if (tid == 0) sh->count = have;
+        __syncthreads();
+        for (int base = 0; base < nslots; base += nt) {
+          int slot = base + tid;
+          Entry e;
+          u64 k = 0;
+          bool c = slot < nslots && in_group(slot, e) && src.cmp3(e, piv) == 0 &&
+                   (u64)(unsigned)(SENTINEL_IDX - e.idx) >= ilo;
+          append_entry(c, e, list, cap, &sh->count);
+        }
+        __syncthreads();
+        have = sh->count;
+        break;
+      }
+      m = have < cap ? have : cap;
+    }
+  }
+  // ---- D: exact sort of the survivors
+  int n2 = 1;
+  while (n2 < m) n2 <<= 1;
+  if (n2 < 2) n2 = 2;
+  for (int i = m + tid; i < n2; i += nt) {
+    Entry s;
+    s.key = 0;
+    s.idx = SENTINEL_IDX;
+    s.aux = 0;
+    list[i] = s;
+  }
+  __syncthreads();
+  bitonic_sort_entries(src, list, n2);
+  return m < K ? m : K;
+}
+
+}  // namespace rpk

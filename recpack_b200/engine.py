@@ -1,0 +1,208 @@
+"""Thin Python driver over the C ABI: one Engine = one rpk context on one GPU.
+
+Arrays may be numpy arrays (host: the library copies them in / out inside the call) or torch
+CUDA tensors (device: passed by address, nothing is copied, the call is stream-ordered)."""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._lib import RpkError
+
+SIM_CODES = {"cosine": 0, "conditional_probability": 1}
+METRIC_CODES = {"ndcg": 0, "recall": 1, "dcg": 2, "calibrated_recall": 3}
+
+DBG_WIDE_ACC, DBG_TINY_LIST, DBG_MULTI_PASS = 1, 2, 4
+
+
+def _is_torch(x):
+    return hasattr(x, "data_ptr") and hasattr(x, "is_cuda")
+
+
+def _addr(x, dtype=None, allow_none=False):
+    """Address of a C-contiguous numpy array or torch tensor (None -> NULL)."""
+    if x is None:
+        if allow_none:
+            return None
+        raise ValueError("array argument must not be None")
+    if _is_torch(x):
+        if not x.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        if dtype is not None and str(x.dtype).replace("torch.", "") != np.dtype(dtype).name:
+            raise TypeError(f"tensor dtype {x.dtype}, expected {np.dtype(dtype).name}")
+        return x.data_ptr()
+    if not isinstance(x, np.ndarray):
+        raise TypeError(f"expected numpy array or torch tensor, got {type(x).__name__}")
+    if dtype is not None and x.dtype != np.dtype(dtype):
+        raise TypeError(f"array dtype {x.dtype}, expected {np.dtype(dtype).name}")
+    if not x.flags.c_contiguous:
+        raise ValueError("array must be C-contiguous")
+    return x.ctypes.data
+
+
+def _empty_like_kind(ref, shape, dtype):
+    """Allocate an output next to the inputs: torch CUDA tensor if ref is one, else numpy."""
+    if _is_torch(ref):
+        import torch
+
+        return torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), device=ref.device)
+    return np.empty(shape, dtype=dtype)
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        if self._lib.rpk_create(int(device), C.byref(h)) != 0:
+            raise RpkError("rpk_create failed: " + self._lib.rpk_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rpk_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RpkError(self._lib.rpk_last_error(self._h).decode())
+
+    # -- plumbing -------------------------------------------------------------------------
+    def set_stream(self, stream_ptr):
+        self._check(self._lib.rpk_set_stream(self._h, C.c_void_p(stream_ptr or 0)))
+
+    def use_torch_stream(self):
+        import torch
+
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        self._check(self._lib.rpk_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.rpk_launch_count(self._h))
+
+    def debug_flags(self, flags: int):
+        self._check(self._lib.rpk_debug_flags(self._h, int(flags)))
+
+    # -- fit ------------------------------------------------------------------------------
+    def fit_topk(self, U, I, indptr, indices, K, similarity="cosine", item_pow=None, item_begin=0, item_end=None,
+                 want_cnt=True, want_val=True, out=None):
+        """rpk_fit_topk.  Returns dict(idx, cnt, val, len); rows in rank order."""
+        item_end = I if item_end is None else item_end
+        rows = item_end - item_begin
+        nnz = int(indices.shape[0])
+        if out is None:
+            out = {
+                "idx": _empty_like_kind(indices, (rows, K), np.int32),
+                "cnt": _empty_like_kind(indices, (rows, K), np.int32) if want_cnt else None,
+                "val": _empty_like_kind(indices, (rows, K), np.float64) if want_val else None,
+                "len": _empty_like_kind(indices, (rows,), np.int32),
+            }
+        self._check(self._lib.rpk_fit_topk(
+            self._h, U, I, nnz, _addr(indptr, np.int64), _addr(indices, np.int32), SIM_CODES[similarity],
+            _addr(item_pow, np.float64, allow_none=True), int(K), int(item_begin), int(item_end),
+            _addr(out["idx"], np.int32), _addr(out.get("cnt"), np.int32, allow_none=True),
+            _addr(out.get("val"), np.float64, allow_none=True), _addr(out["len"], np.int32)))
+        return out
+
+    def fit_item_counts(self, I, like=None):
+        out = _empty_like_kind(like, (I,), np.int32)
+        self._check(self._lib.rpk_fit_item_counts(self._h, _addr(out, np.int32), int(I)))
+        return out
+
+    # -- model ----------------------------------------------------------------------------
+    def model_load_topk(self, I, K, idx, val, ln):
+        self._check(self._lib.rpk_model_load_topk(self._h, int(I), int(K), _addr(idx, np.int32), _addr(val, np.float64),
+                                                  _addr(ln, np.int32)))
+
+    def model_load_csr(self, I, indptr, indices, values):
+        self._check(self._lib.rpk_model_load_csr(self._h, int(I), int(indices.shape[0]), _addr(indptr, np.int64),
+                                                 _addr(indices, np.int32), _addr(values, np.float64)))
+
+    # -- predict --------------------------------------------------------------------------
+    def predict_topn(self, U, indptr, indices, N, mask_history=True, want_val=True, out=None):
+        if out is None:
+            out = {
+                "idx": _empty_like_kind(indices, (U, N), np.int32),
+                "val": _empty_like_kind(indices, (U, N), np.float64) if want_val else None,
+                "len": _empty_like_kind(indices, (U,), np.int32),
+            }
+        self._check(self._lib.rpk_predict_topn(
+            self._h, int(U), int(indices.shape[0]), _addr(indptr, np.int64), _addr(indices, np.int32), int(N),
+            int(bool(mask_history)), _addr(out["idx"], np.int32), _addr(out.get("val"), np.float64, allow_none=True),
+            _addr(out["len"], np.int32)))
+        return out
+
+    def predict_csr(self, U, indptr, indices, mask_history=False):
+        """Full score matrix as (indptr int64, indices int32, data float64) numpy arrays."""
+        nnz = int(indices.shape[0])
+        row_nnz = np.empty(U, dtype=np.int64)
+        self._check(self._lib.rpk_predict_csr_count(self._h, int(U), nnz, _addr(indptr, np.int64), _addr(indices, np.int32),
+                                                    int(bool(mask_history)), _addr(row_nnz, np.int64)))
+        out_indptr = np.zeros(U + 1, dtype=np.int64)
+        np.cumsum(row_nnz, out=out_indptr[1:])
+        total = int(out_indptr[-1])
+        out_indices = np.empty(total, dtype=np.int32)
+        out_values = np.empty(total, dtype=np.float64)
+        if U > 0:
+            self._check(self._lib.rpk_predict_csr_fill(
+                self._h, int(U), nnz, _addr(indptr, np.int64), _addr(indices, np.int32), int(bool(mask_history)),
+                _addr(out_indptr, np.int64), _addr(out_indices, np.int32), _addr(out_values, np.float64)))
+        return out_indptr, out_indices, out_values
+
+    # -- ranking / metrics ----------------------------------------------------------------
+    def topk_csr(self, rows, indptr, indices, values, K):
+        out_idx = _empty_like_kind(indices, (rows, K), np.int32)
+        out_len = _empty_like_kind(indices, (rows,), np.int32)
+        self._check(self._lib.rpk_topk_csr(self._h, int(rows), int(indices.shape[0]), _addr(indptr, np.int64),
+                                           _addr(indices, np.int32), _addr(values, np.float64), int(K),
+                                           _addr(out_idx, np.int32), _addr(out_len, np.int32)))
+        return out_idx, out_len
+
+    def metrics_topn(self, U, N, top_idx, top_len, true_indptr, true_indices, metrics, want_per_user=True):
+        """metrics: list of (kind, K).  Returns (sums float64[m], n_users int, per_user float64[m, U] or None).
+        The discount / IDCG tables are built here with numpy exactly as recpack/metrics/dcg.py:98-104 does."""
+        import itertools
+
+        kinds = np.array([METRIC_CODES[k] for k, _ in metrics], dtype=np.int32)
+        Ks = np.array([k for _, k in metrics], dtype=np.int32)
+        maxK = int(Ks.max())
+        disc = 1.0 / np.log2(np.arange(2, maxK + 2))
+        idcg = np.array([1] + list(itertools.accumulate(disc, lambda x, y: x + y)), dtype=np.float64)
+        m = len(metrics)
+        per_user = _empty_like_kind(top_idx, (m, U), np.float64) if want_per_user else None
+        sums = np.empty(m, dtype=np.float64)
+        n_users = np.zeros(1, dtype=np.int64)
+        self._check(self._lib.rpk_metrics_topn(
+            self._h, int(U), int(N), _addr(top_idx, np.int32), _addr(top_len, np.int32), _addr(true_indptr, np.int64),
+            _addr(true_indices, np.int32), int(true_indices.shape[0]), m, _addr(kinds), _addr(Ks),
+            _addr(np.ascontiguousarray(disc)), _addr(idcg), maxK, _addr(per_user, np.float64, allow_none=True),
+            _addr(sums), _addr(n_users)))
+        return sums, int(n_users[0]), per_user
+
+
+_engines = {}
+_lock = threading.Lock()
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """Process-wide engine of a device (default: LOCAL_RANK, else 0)."""
+    import os
+
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    with _lock:
+        eng = _engines.get(device)
+        if eng is None:
+            eng = _engines[device] = Engine(device)
+        return eng

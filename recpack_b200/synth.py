@@ -34,22 +34,36 @@ def synth_interactions(U: int, I: int, nnz: int, seed: int = 0, item_exp: float 
     ci = np.cumsum(pi / pi.sum())
     keys = np.empty(0, dtype=np.int64)
     while len(keys) < nnz:
-        want = int((nnz - len(keys)) * 1.3) + 1024
+        want = int((nnz - len(keys)) * 1.5) + 1024
         u = np.minimum(np.searchsorted(cu, rng.random(want)), U - 1).astype(np.int64)
         i = np.minimum(np.searchsorted(ci, rng.random(want)), I - 1).astype(np.int64)
-        keys = np.unique(np.concatenate([keys, u * I + i]))
+        fresh = u * I + i
+        fresh.sort()
+        fresh = fresh[np.r_[True, fresh[1:] != fresh[:-1]]]
+        if len(keys):
+            fresh = fresh[~np.isin(fresh, keys, assume_unique=True)]
+            keys = np.concatenate([keys, fresh])
+            keys.sort()
+        else:
+            keys = fresh
     if len(keys) > nnz:
-        keys = np.sort(rng.choice(keys, size=nnz, replace=False))
+        keep = np.zeros(len(keys), dtype=bool)
+        keep[rng.choice(len(keys), size=nnz, replace=False)] = True
+        keys = keys[keep]
     perm_u = rng.permutation(U).astype(np.int64)
     perm_i = rng.permutation(I).astype(np.int64)
-    u = perm_u[keys // I]
-    i = perm_i[keys % I]
-    order = np.lexsort((i, u))
-    u, i = u[order], i[order]
+    keys = perm_u[keys // I] * I + perm_i[keys % I]
+    keys.sort()
+    return _csr_from_sorted_keys(keys, U, I)
+
+
+def _csr_from_sorted_keys(keys: np.ndarray, U: int, I: int) -> csr_matrix:
+    """Binary CSR from sorted unique keys u * I + i."""
+    u = keys // I
     indptr = np.zeros(U + 1, dtype=np.int64)
-    np.add.at(indptr, u + 1, 1)
-    indptr = np.cumsum(indptr)
-    X = csr_matrix((np.ones(nnz, dtype=np.int32), i.astype(np.int32), indptr.astype(np.int32 if nnz < 2**31 else np.int64)), shape=(U, I))
+    np.cumsum(np.bincount(u, minlength=U), out=indptr[1:])
+    ptr_dtype = np.int32 if len(keys) < 2**31 else np.int64
+    X = csr_matrix((np.ones(len(keys), dtype=np.int32), (keys % I).astype(np.int32), indptr.astype(ptr_dtype)), shape=(U, I))
     X.has_sorted_indices = True
     return X
 
@@ -64,21 +78,12 @@ def weak_generalization_split(X: csr_matrix, frac_in: float = 0.8, seed: int = 4
     U, I = X.shape
     d = np.diff(X.indptr).astype(np.int64)
     rows = np.repeat(np.arange(U, dtype=np.int64), d)
-    order = np.lexsort((rng.random(X.nnz), rows))  # random order inside each user
+    order = np.argsort(rows + rng.random(X.nnz))  # random order inside each user, users stay grouped
     pos = np.arange(X.nnz, dtype=np.int64) - np.repeat(X.indptr[:-1].astype(np.int64), d)
-    n_in = np.ceil(frac_in * d).astype(np.int64)
-    to_in = pos < np.repeat(n_in, d)
-    cols = X.indices[order]
-
-    def build(mask):
-        r, c = rows[mask], cols[mask]
-        o = np.lexsort((c, r))
-        r, c = r[o], c[o]
-        ptr = np.zeros(U + 1, dtype=np.int64)
-        np.add.at(ptr, r + 1, 1)
-        ptr = np.cumsum(ptr)
-        M = csr_matrix((np.ones(len(c), dtype=np.int32), c.astype(np.int32), ptr.astype(X.indptr.dtype)), shape=(U, I))
-        M.has_sorted_indices = True
-        return M
-
-    return build(to_in), build(~to_in)
+    to_in = pos < np.repeat(np.ceil(frac_in * d).astype(np.int64), d)
+    keys = rows * I + X.indices[order].astype(np.int64)  # rows[order] == rows: users stay grouped
+    k_in = keys[to_in]
+    k_in.sort()
+    k_out = keys[~to_in]
+    k_out.sort()
+    return _csr_from_sorted_keys(k_in, U, I), _csr_from_sorted_keys(k_out, U, I)
