@@ -78,22 +78,20 @@ struct SimKey {
 
   __device__ __forceinline__ u64 margin() const { return mode == 0 ? 32ull : 0ull; }
 
-  // cosine: approximate fp32 key c^2/n_j (a few ulp of error, covered by margin()), exact order restored by cmp3
-  __device__ __forceinline__ void make(int c, int j, Entry& e, u64& k) const {
+  // cosine: approximate fp32 key c^2/n_j (a few ulp of error, covered by margin()); the exact order is
+  // restored by cmp3 on (c, n_j).  conditional probability: the exact float64 key itself.
+  __device__ __forceinline__ u64 akey(int c, int j) const {
+    if (mode == 0) {
+      const float a = (float)c;
+      return (u64)__float_as_uint(__fmul_rn(__fmul_rn(a, a), rnf[j]));
+    }
+    if (mode == 1) return (u64)__double_as_longlong((double)c);
+    return (u64)__double_as_longlong(__dmul_rn((double)c, pw[j]));
+  }
+  __device__ __forceinline__ void entry(int c, int j, Entry& e) const {
     e.idx = j;
     e.aux = c;
-    if (mode == 0) {
-      float a = (float)c;
-      float f = __fmul_rn(__fmul_rn(a, a), rnf[j]);
-      k = (u64)__float_as_uint(f);
-      e.key = (u64)(unsigned)n[j];
-    } else if (mode == 1) {
-      k = (u64)__double_as_longlong((double)c);
-      e.key = k;
-    } else {
-      k = (u64)__double_as_longlong(__dmul_rn((double)c, pw[j]));
-      e.key = k;
-    }
+    e.key = mode == 0 ? (u64)(unsigned)n[j] : akey(c, j);
   }
   __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const {
     if (mode == 0) {
@@ -111,19 +109,27 @@ struct SimKey {
   }
 };
 
-struct RowCountSrc {  // dense shared-memory counters of one (row, item range)
+// Dense shared-memory counters of one (row, item range).  PACK16: two 16-bit counters per word
+// (rows with fewer than 65536 users cannot overflow them), else one 32-bit counter per item.
+template <bool PACK16>
+struct RowCountSrc {
   SimKey sk;
-  const int* cnt;
+  const unsigned* cnt;
   int r0, ns, self;
+  __device__ __forceinline__ int count(int slot) const {
+    if (PACK16) return (int)((cnt[slot >> 1] >> ((slot & 1) * 16)) & 0xffffu);
+    return (int)cnt[slot];
+  }
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return sk.margin(); }
-  __device__ __forceinline__ bool load(int slot, Entry& e, u64& k) const {
-    int c = cnt[slot];
-    int j = r0 + slot;
+  __device__ __forceinline__ bool key(int slot, u64& k) const {
+    const int c = count(slot);
+    const int j = r0 + slot;
     if (c == 0 || j == self) return false;
-    sk.make(c, j, e, k);
+    k = sk.akey(c, j);
     return true;
   }
+  __device__ __forceinline__ void entry(int slot, Entry& e) const { sk.entry(count(slot), r0 + slot, e); }
   __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const { return sk.cmp3(a, b); }
 };
 
@@ -134,12 +140,13 @@ struct PairListSrc {  // (idx, cnt) pairs in global memory, idx < 0 = empty slot
   int ns;
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return sk.margin(); }
-  __device__ __forceinline__ bool load(int slot, Entry& e, u64& k) const {
-    int j = idx[slot];
+  __device__ __forceinline__ bool key(int slot, u64& k) const {
+    const int j = idx[slot];
     if (j < 0) return false;
-    sk.make(cnt[slot], j, e, k);
+    k = sk.akey(cnt[slot], j);
     return true;
   }
+  __device__ __forceinline__ void entry(int slot, Entry& e) const { sk.entry(cnt[slot], idx[slot], e); }
   __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const { return sk.cmp3(a, b); }
 };
 
@@ -153,42 +160,46 @@ struct FitParams {
   const int64_t* cscptr;
   const int* csc_users;
   SimKey sk;
-  const int* order;
-  int nrows, P, R, I, K;
+  const int* order;       // rows of this launch, heaviest first
+  const int* nrows_dev;   // number of rows in `order` (device side: no host round trip)
+  int P, R, I, K;
   int64_t item_begin;
   int cap, direct_cap;
+  int direct_out;         // 1: P == 1, write final rows; 0: write per-(list position, pass) partial lists
   int* queue;
   int* out_idx;
   int* out_cnt;
   int* out_len;
 };
 
-__device__ __forceinline__ size_t sel_smem_bytes(int cap) {
+__host__ __device__ __forceinline__ size_t sel_smem_bytes(int cap) {
   return (size_t)cap * sizeof(Entry) + SEL_BINS * sizeof(int) + ((sizeof(SelShared) + 15) / 16) * 16;
 }
 
+template <bool PACK16>
 __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   Entry* list = reinterpret_cast<Entry*>(smem);
   int* hist = reinterpret_cast<int*>(smem + (size_t)p.cap * sizeof(Entry));
   SelShared* sh = reinterpret_cast<SelShared*>(hist + SEL_BINS);
-  int* cnt = reinterpret_cast<int*>(smem + sel_smem_bytes(p.cap));
+  unsigned* cnt = reinterpret_cast<unsigned*>(smem + sel_smem_bytes(p.cap));
   __shared__ int s_work;
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  const int total = p.nrows * p.P;
+  const int total = p.nrows_dev[0] * p.P;
   for (;;) {
     if (tid == 0) s_work = atomicAdd(p.queue, 1);
     __syncthreads();
     const int w = s_work;
     __syncthreads();
     if (w >= total) break;
-    const int i = p.order[w / p.P];
+    const int pos = w / p.P;
+    const int i = p.order[pos];
     const int pass = w % p.P;
     const int r0 = pass * p.R;
     const int ns = min(p.R, p.I - r0);
     const int64_t ub = p.cscptr[i], ue = p.cscptr[i + 1];
-    const int64_t orow = ((int64_t)i - p.item_begin) * p.P + pass;
+    const int64_t orow = p.direct_out ? ((int64_t)i - p.item_begin) : ((int64_t)pos * p.P + pass);
     int* o_idx = p.out_idx + orow * p.K;
     int* o_cnt = p.out_cnt + orow * p.K;
     if (ue == ub) {  // item never seen: empty row (base.py:257-279 warns about these)
@@ -199,15 +210,20 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       if (tid == 0) p.out_len[orow] = 0;
       continue;
     }
-    for (int s = tid; s < ns; s += nt) cnt[s] = 0;
+    const int nwords = PACK16 ? (ns + 1) >> 1 : ns;
+    for (int s = tid; s < nwords; s += nt) cnt[s] = 0u;
     __syncthreads();
-    // ---- accumulate: each warp takes 32 users of the item at a time
-    for (int64_t base = ub + (int64_t)warp * 32; base < ue; base += (int64_t)nwarps * 32) {
-      const int64_t k = base + lane;
+    // ---- accumulate: the item's users are dealt to the warps in chunks (<= 32 users, one per lane, so
+    //      that their row pointers are fetched in parallel); every warp then walks its users' histories
+    const int64_t nu = ue - ub;
+    int chunk = (int)((nu + nwarps - 1) / nwarps);
+    chunk = chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk);
+    for (int64_t base = ub + (int64_t)warp * chunk; base < ue; base += (int64_t)nwarps * chunk) {
+      const int nvalid = (int)min((int64_t)chunk, ue - base);
       int64_t beg = 0;
       int len = 0;
-      if (k < ue) {
-        const int u = p.csc_users[k];
+      if (lane < nvalid) {
+        const int u = p.csc_users[base + lane];
         if (p.usplit) {
           const int64_t* us = p.usplit + (int64_t)u * (p.P + 1) + pass;
           beg = us[0];
@@ -217,16 +233,19 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
           len = (int)(p.indptr[u + 1] - beg);
         }
       }
-      const int nvalid = (int)min((int64_t)32, ue - base);
       for (int l = 0; l < nvalid; ++l) {
         const int64_t b = __shfl_sync(0xffffffffu, beg, l);
         const int n = __shfl_sync(0xffffffffu, len, l);
-        for (int e = lane; e < n; e += 32) atomicAdd(&cnt[p.indices[b + e] - r0], 1);
+        for (int e = lane; e < n; e += 32) {
+          const int j = p.indices[b + e] - r0;
+          if (PACK16) atomicAdd(&cnt[j >> 1], 1u << ((j & 1) * 16));
+          else atomicAdd(&cnt[j], 1u);
+        }
       }
     }
     __syncthreads();
     // ---- fused epilogue: similarity ordering, diagonal removal, top-K -- all on the shared-memory row
-    RowCountSrc src{p.sk, cnt, r0, ns, i};
+    RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i};
     const int m = block_select_topk(src, p.K, list, p.cap, p.direct_cap, hist, sh);
     for (int t = tid; t < p.K; t += nt) {
       o_idx[t] = t < m ? list[t].idx : -1;
@@ -237,31 +256,58 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
   }
 }
 
-// Merge the P per-range lists of a row (only when the item space does not fit one pass).
+// Merge the P per-range lists of the rows that needed several passes.
 struct MergeParams {
   SimKey sk;
   const int* part_idx;
   const int* part_cnt;
+  const int* order;
+  const int* nrows_dev;
+  int64_t item_begin;
   int P, K, cap, direct_cap;
   int* out_idx;
   int* out_cnt;
   int* out_len;
 };
-__global__ void __launch_bounds__(256) k_fit_merge(MergeParams p, int nrows) {
+__global__ void __launch_bounds__(256) k_fit_merge(MergeParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   Entry* list = reinterpret_cast<Entry*>(smem);
   int* hist = reinterpret_cast<int*>(smem + (size_t)p.cap * sizeof(Entry));
   SelShared* sh = reinterpret_cast<SelShared*>(hist + SEL_BINS);
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
-    PairListSrc src{p.sk, p.part_idx + (int64_t)row * p.P * p.K, p.part_cnt + (int64_t)row * p.P * p.K, p.P * p.K};
+  const int nrows = p.nrows_dev[0];
+  for (int pos = blockIdx.x; pos < nrows; pos += gridDim.x) {
+    const int64_t row = (int64_t)p.order[pos] - p.item_begin;
+    PairListSrc src{p.sk, p.part_idx + (int64_t)pos * p.P * p.K, p.part_cnt + (int64_t)pos * p.P * p.K, p.P * p.K};
     const int m = block_select_topk(src, p.K, list, p.cap, p.direct_cap, hist, sh);
     for (int t = tid; t < p.K; t += nt) {
-      p.out_idx[(int64_t)row * p.K + t] = t < m ? list[t].idx : -1;
-      p.out_cnt[(int64_t)row * p.K + t] = t < m ? list[t].aux : 0;
+      p.out_idx[row * p.K + t] = t < m ? list[t].idx : -1;
+      p.out_cnt[row * p.K + t] = t < m ? list[t].aux : 0;
     }
     if (tid == 0) p.out_len[row] = m;
     __syncthreads();
+  }
+}
+
+// Stable split of the heaviest-first row order into rows whose counts fit 16 bits and the rest.
+__global__ void k_split_rows(const int* __restrict__ order, int nrows, const int* __restrict__ n, int limit,
+                             int* __restrict__ light, int* __restrict__ heavy, int* __restrict__ counts) {
+  const int lane = threadIdx.x;
+  int nl = 0, nh = 0;
+  for (int base = 0; base < nrows; base += 32) {
+    const int k = base + lane;
+    const int row = k < nrows ? order[k] : -1;
+    const bool is_l = row >= 0 && n[row] < limit;
+    const bool is_h = row >= 0 && !is_l;
+    const unsigned ml = __ballot_sync(0xffffffffu, is_l), mh = __ballot_sync(0xffffffffu, is_h);
+    if (is_l) light[nl + __popc(ml & ((1u << lane) - 1u))] = row;
+    if (is_h) heavy[nh + __popc(mh & ((1u << lane) - 1u))] = row;
+    nl += __popc(ml);
+    nh += __popc(mh);
+  }
+  if (lane == 0) {
+    counts[0] = nl;
+    counts[1] = nh;
   }
 }
 
@@ -331,7 +377,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
   int* order = c->buf<int>("fit_order", (size_t)nrows);
   int* bcnt = c->buf<int>("fit_bcnt", 65 * 2 + 2);
   int* boff = bcnt + 65;
-  int* queue = boff + 65;
+  (void)boff;
   c->fit_I = I;
   RPK_CUDA(cudaMemsetAsync(n, 0, sizeof(int) * (size_t)I, st));
   RPK_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)I, st));
@@ -374,83 +420,102 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     RPK_LAUNCH_CHECK(c);
     k_bucket_scatter<<<ceil_div(nrows, 256), 256, 0, st>>>(work, item_begin, item_end, boff, order);
     RPK_LAUNCH_CHECK(c);
+    // rows with fewer than 65536 users -> 16-bit packed counters; the few heavier rows -> 32-bit counters
+    int* order_l = c->buf<int>("fit_order_l", (size_t)nrows);
+    int* order_h = c->buf<int>("fit_order_h", (size_t)nrows);
+    int* split_cnt = c->buf<int>("fit_split_cnt", 4);
+    int* queues = c->buf<int>("fit_queues", 4);
+    RPK_CUDA(cudaMemsetAsync(queues, 0, sizeof(int) * 4, st));
+    const bool force_wide = (c->flags & DBG_WIDE_ACC) != 0;  // test hook: every row through the 32-bit path
+    k_split_rows<<<1, 32, 0, st>>>(order, (int)nrows, n, force_wide ? 0 : 65536, order_l, order_h, split_cnt);
+    RPK_LAUNCH_CHECK(c);
 
-    // ---- geometry: item-range passes so that the counters of one pass fit shared memory
     const bool tiny = c->flags & DBG_TINY_LIST;
-    const int cap = std::max(tiny ? 64 : 2048, next_pow2(2 * K));
-    const int direct_cap = tiny ? K : cap;
-    const size_t fixed = (size_t)cap * sizeof(Entry) + SEL_BINS * sizeof(int) + ((sizeof(SelShared) + 15) / 16) * 16;
-    const size_t avail = (size_t)c->smem_max - fixed - 1024;  // 1 KB slack for static shared memory
+    const int cap = std::max(tiny ? 64 : 512, next_pow2(2 * K));
+    const int direct_cap = tiny ? K : std::min(cap, std::max(2 * K, 64));
+    const size_t fixed = sel_smem_bytes(cap);
     RPK_REQUIRE((size_t)c->smem_max > fixed + 1024 + 4096, "K too large for shared memory");
-    int64_t Rmax = (int64_t)(avail / sizeof(int)) & ~(int64_t)3;
-    int P = (int)((I + Rmax - 1) / Rmax);
-    if (P < 1) P = 1;
-    if ((c->flags & DBG_MULTI_PASS) && P < 2 && I >= 2) P = 2;
-    int R = (int)(((I + P - 1) / P + 3) & ~(int64_t)3);
-    const size_t smem = fixed + (size_t)R * sizeof(int);
-    const int nt = R >= 16384 ? 1024 : (R >= 4096 ? 512 : 256);
+    const size_t avail = (size_t)c->smem_max - fixed - 1024;  // 1 KB slack for static shared memory
+    const SimKey sk{n, rnf, pw, mode};
 
-    const int64_t* usplit = nullptr;
-    if (P > 1) {
-      int64_t* us = c->buf<int64_t>("fit_usplit", (size_t)U * (P + 1));
-      if (U > 0) {
-        k_user_split<<<ceil_div(U * (P + 1), 256), 256, 0, st>>>(indptr, indices, U, P, R, us);
+    for (int wide = 0; wide < 2; ++wide) {
+      // geometry: item-range passes so that the counters of one pass fit shared memory
+      const int bytes_per_item = wide ? 4 : 2;
+      int64_t Rmax = (int64_t)(avail / bytes_per_item) & ~(int64_t)7;
+      int P = (int)((I + Rmax - 1) / Rmax);
+      if (P < 1) P = 1;
+      if ((c->flags & DBG_MULTI_PASS) && P < 2 && I >= 16) P = 2;
+      const int R = (int)(((I + P - 1) / P + 7) & ~(int64_t)7);
+      const size_t smem = fixed + (size_t)R * bytes_per_item;
+      const int nt = R >= 16384 ? 1024 : (R >= 4096 ? 512 : 256);
+      const int64_t* usplit = nullptr;
+      if (P > 1) {
+        int64_t* us = c->buf<int64_t>(wide ? "fit_usplit32" : "fit_usplit16", (size_t)U * (P + 1));
+        if (U > 0) {
+          k_user_split<<<ceil_div(U * (P + 1), 256), 256, 0, st>>>(indptr, indices, U, P, R, us);
+          RPK_LAUNCH_CHECK(c);
+        }
+        usplit = us;
+      }
+      int* part_idx = o_idx.dev;
+      int* part_cnt = cnt_dev;
+      int* part_len = o_len.dev;
+      if (P > 1) {
+        part_idx = c->buf<int>(wide ? "fit_part_idx32" : "fit_part_idx16", (size_t)nrows * P * K);
+        part_cnt = c->buf<int>(wide ? "fit_part_cnt32" : "fit_part_cnt16", (size_t)nrows * P * K);
+        part_len = c->buf<int>(wide ? "fit_part_len32" : "fit_part_len16", (size_t)nrows * P);
+      }
+      FitParams fp;
+      fp.indptr = indptr;
+      fp.indices = indices;
+      fp.usplit = usplit;
+      fp.cscptr = cscptr;
+      fp.csc_users = csc_users;
+      fp.sk = sk;
+      fp.order = wide ? order_h : order_l;
+      fp.nrows_dev = split_cnt + wide;
+      fp.P = P;
+      fp.R = R;
+      fp.I = (int)I;
+      fp.K = K;
+      fp.item_begin = item_begin;
+      fp.cap = cap;
+      fp.direct_cap = direct_cap;
+      fp.direct_out = P == 1;
+      fp.queue = queues + wide;
+      fp.out_idx = part_idx;
+      fp.out_cnt = part_cnt;
+      fp.out_len = part_len;
+      auto kern = wide ? k_fit_rows<false> : k_fit_rows<true>;
+      RPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int occ = 0;
+      RPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem));
+      RPK_REQUIRE(occ >= 1, "fit kernel does not fit on an SM");
+      // the heavy list is short (items seen by >= 65536 users): a small grid is enough for it
+      const int64_t max_items = wide && !force_wide ? std::min<int64_t>(nrows * P, 64) : nrows * P;
+      const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(max_items, (int64_t)c->sm_count * occ));
+      kern<<<grid, nt, smem, st>>>(fp);
+      RPK_LAUNCH_CHECK(c);
+      if (P > 1) {
+        MergeParams mp;
+        mp.sk = sk;
+        mp.part_idx = part_idx;
+        mp.part_cnt = part_cnt;
+        mp.order = fp.order;
+        mp.nrows_dev = fp.nrows_dev;
+        mp.item_begin = item_begin;
+        mp.P = P;
+        mp.K = K;
+        mp.cap = cap;
+        mp.direct_cap = direct_cap;
+        mp.out_idx = o_idx.dev;
+        mp.out_cnt = cnt_dev;
+        mp.out_len = o_len.dev;
+        RPK_CUDA(cudaFuncSetAttribute(k_fit_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fixed));
+        const int mgrid = (int)std::min<int64_t>(max_items, (int64_t)c->sm_count * 8);
+        k_fit_merge<<<std::max(1, mgrid), 256, fixed, st>>>(mp);
         RPK_LAUNCH_CHECK(c);
       }
-      usplit = us;
-    }
-    int* part_idx = o_idx.dev;
-    int* part_cnt = cnt_dev;
-    int* part_len = o_len.dev;
-    if (P > 1) {
-      part_idx = c->buf<int>("fit_part_idx", (size_t)nrows * P * K);
-      part_cnt = c->buf<int>("fit_part_cnt", (size_t)nrows * P * K);
-      part_len = c->buf<int>("fit_part_len", (size_t)nrows * P);
-    }
-    FitParams fp;
-    fp.indptr = indptr;
-    fp.indices = indices;
-    fp.usplit = usplit;
-    fp.cscptr = cscptr;
-    fp.csc_users = csc_users;
-    fp.sk = SimKey{n, rnf, pw, mode};
-    fp.order = order;
-    fp.nrows = (int)nrows;
-    fp.P = P;
-    fp.R = R;
-    fp.I = (int)I;
-    fp.K = K;
-    fp.item_begin = item_begin;
-    fp.cap = cap;
-    fp.direct_cap = direct_cap;
-    fp.queue = queue;
-    fp.out_idx = part_idx;
-    fp.out_cnt = part_cnt;
-    fp.out_len = part_len;
-    RPK_CUDA(cudaFuncSetAttribute(k_fit_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    RPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fit_rows, nt, smem));
-    RPK_REQUIRE(occ >= 1, "fit kernel does not fit on an SM");
-    const int64_t total = nrows * P;
-    const int grid = (int)std::min<int64_t>(total, (int64_t)c->sm_count * occ);
-    k_fit_rows<<<grid, nt, smem, st>>>(fp);
-    RPK_LAUNCH_CHECK(c);
-    if (P > 1) {
-      MergeParams mp;
-      mp.sk = fp.sk;
-      mp.part_idx = part_idx;
-      mp.part_cnt = part_cnt;
-      mp.P = P;
-      mp.K = K;
-      mp.cap = cap;
-      mp.direct_cap = direct_cap;
-      mp.out_idx = o_idx.dev;
-      mp.out_cnt = cnt_dev;
-      mp.out_len = o_len.dev;
-      RPK_CUDA(cudaFuncSetAttribute(k_fit_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fixed));
-      const int mgrid = (int)std::min<int64_t>(nrows, (int64_t)c->sm_count * 8);
-      k_fit_merge<<<mgrid, 256, fixed, st>>>(mp, (int)nrows);
-      RPK_LAUNCH_CHECK(c);
     }
     if (o_val.dev) {
       k_fit_values<<<ceil_div(nrows * K, 256), 256, 0, st>>>(o_idx.dev, cnt_dev, n, pw, mode, item_begin, nrows, K, o_val.dev);

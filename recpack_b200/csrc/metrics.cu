@@ -25,14 +25,18 @@ struct CsrRowSrc {
   int ns;
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return 0ull; }
-  __device__ __forceinline__ bool load(int slot, Entry& e, u64& k) const {
+  __device__ __forceinline__ bool key(int slot, u64& k) const {
     double v = val[slot];
     if (v == 0.0) v = 0.0;  // -0.0 and +0.0 are the same score
     k = ordered_bits(v);
+    return true;  // every stored entry is ranked, explicit zeros included (util.py:63-73)
+  }
+  __device__ __forceinline__ void entry(int slot, Entry& e) const {
+    u64 k;
+    key(slot, k);
     e.key = k;
     e.idx = idx[slot];
     e.aux = 0;
-    return true;  // every stored entry is ranked, explicit zeros included (util.py:63-73)
   }
   __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const {
     if (a.key != b.key) return a.key > b.key ? 1 : -1;

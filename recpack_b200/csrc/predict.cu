@@ -222,24 +222,28 @@ void run_model_load_csr(rpk_ctx* c, int64_t I, int64_t nnz, const int64_t* indpt
 // ------------------------------------------------------------------------------------------
 // Scoring kernel
 // ------------------------------------------------------------------------------------------
+// Candidate sources: the dense accumulator range, or the list of slots touched by this user.
 struct ScoreSrc {
   const unsigned* lo;
   const unsigned* hi;
-  const u64* wide;  // non-null: 64-bit accumulators
+  const u64* wide;     // non-null: 64-bit accumulators
+  const int* touched;  // non-null: slot list (sparse mode)
   int r0, ns;
-  __device__ __forceinline__ u64 score(int slot) const {
-    return wide ? wide[slot] : (((u64)hi[slot] << LIMB_BITS) + (u64)lo[slot]);
+  __device__ __forceinline__ u64 score_at(int j) const {
+    return wide ? wide[j] : (((u64)hi[j] << LIMB_BITS) + (u64)lo[j]);
   }
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return 0ull; }
-  __device__ __forceinline__ bool load(int slot, Entry& e, u64& k) const {
-    u64 s = score(slot);
-    if (s == 0) return false;
-    k = s;
-    e.key = s;
-    e.idx = r0 + slot;
+  __device__ __forceinline__ bool key(int slot, u64& k) const {
+    const int j = touched ? touched[slot] : slot;
+    k = score_at(j);
+    return k != 0;
+  }
+  __device__ __forceinline__ void entry(int slot, Entry& e) const {
+    const int j = touched ? touched[slot] : slot;
+    e.key = score_at(j);
+    e.idx = r0 + j;
     e.aux = 0;
-    return true;
   }
   __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const {
     if (a.key != b.key) return a.key > b.key ? 1 : -1;
@@ -258,7 +262,7 @@ struct PredParams {
   const unsigned* m_rowmax;
   const int* order;
   int U, P, R, I, N, mask, mode, force_wide;
-  int cap, direct_cap;
+  int cap, direct_cap, tcap;
   int* queue;
   int* part_idx;
   u64* part_sq;
@@ -269,6 +273,10 @@ struct PredParams {
   double* out_values;
 };
 
+// Invariant: the accumulators of a CTA are all zero between work items.  A light user touches few of
+// the R slots of a range, so its slots are recorded on first touch (the low limb of a touched slot can
+// never be zero again: every q is odd) and only those are ranked and cleared; heavy users, and the
+// full-CSR modes, sweep the whole range instead.
 __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   Entry* list = reinterpret_cast<Entry*>(smem);
@@ -278,17 +286,21 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
                                       ((sizeof(SelShared) + 15) / 16) * 16);
   unsigned* acc_lo = reinterpret_cast<unsigned*>(acc64);
   unsigned* acc_hi = acc_lo + p.R;
+  int* touched = reinterpret_cast<int*>(acc64 + p.R);
   __shared__ int s_work;
   __shared__ u64 s_bound;
   __shared__ int s_cnt;
+  __shared__ int s_ntouched;
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int total = p.U * p.P;
+  for (int s = tid; s < p.R; s += nt) acc64[s] = 0ull;
   for (;;) {
     if (tid == 0) {
       s_work = atomicAdd(p.queue, 1);
       s_bound = 0;
       s_cnt = 0;
+      s_ntouched = 0;
     }
     __syncthreads();
     const int w = s_work;
@@ -324,38 +336,57 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       __syncthreads();
       wide = s_bound >= (((u64)1) << 32);
     }
-    for (int s = tid; s < ns; s += nt) acc64[s] = 0ull;  // clears both limb arrays when ns == R ...
-    if (ns < p.R)
-      for (int s = tid; s < ns; s += nt) acc_hi[s] = 0u;  // ... and the high limbs of a short last range
-    __syncthreads();
-    // ---- accumulate: each warp takes 32 history rows at a time; rows are added in chunks so that the
-    //      low limb (20 bits per term) cannot overflow 32 bits between normalisations
+    // sparse mode: track first touches (needs the limb accumulators and a single chunk)
+    const bool track = !wide && d <= LIMB_CHUNK && p.mode == PRED_TOPN && p.tcap > 0;
+    // ---- accumulate: history rows are dealt to the warps in chunks (<= 32 rows, one per lane, so that the
+    //      segment bounds are fetched in parallel); rows are added in groups of LIMB_CHUNK so that the low
+    //      limb (20 bits per term) cannot overflow 32 bits between normalisations
     for (int c0 = 0; c0 < d; c0 += LIMB_CHUNK) {
       const int c1 = min(d, c0 + LIMB_CHUNK);
-      for (int base = c0 + warp * 32; base < c1; base += nwarps * 32) {
-        const int r = base + lane;
+      int chunk = (c1 - c0 + nwarps - 1) / nwarps;
+      chunk = chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk);
+      for (int base = c0 + warp * chunk; base < c1; base += nwarps * chunk) {
+        const int nvalid = min(chunk, c1 - base);
         int64_t beg = 0;
         int len = 0;
-        if (r < c1) {
-          const int i = p.indices[xb + r];
+        if (lane < nvalid) {
+          const int i = p.indices[xb + base + lane];
           const int* sg = p.m_seg + (int64_t)i * (p.P + 1) + pass;
           const int s0 = sg[0];
           beg = p.m_ptr[i] + s0;
           len = sg[1] - s0;
         }
-        const int nvalid = min(32, c1 - base);
         for (int l = 0; l < nvalid; ++l) {
           const int64_t b = __shfl_sync(0xffffffffu, beg, l);
           const int n = __shfl_sync(0xffffffffu, len, l);
-          for (int e = lane; e < n; e += 32) {
-            const u64 ent = p.m_ent[b + e];
-            const int j = (int)(ent >> 40) - r0;
-            const u64 q = ent & Q_MASK40;
-            if (wide) {
-              atomicAdd(&acc64[j], q);
-            } else {
-              atomicAdd(&acc_lo[j], (unsigned)q & LIMB_MASK);
-              atomicAdd(&acc_hi[j], (unsigned)(q >> LIMB_BITS));
+          for (int e0 = 0; e0 < n; e0 += 32) {
+            const int e = e0 + lane;
+            bool first = false;
+            int j = 0;
+            if (e < n) {
+              const u64 ent = p.m_ent[b + e];
+              j = (int)(ent >> 40) - r0;
+              const u64 q = ent & Q_MASK40;
+              if (wide) {
+                atomicAdd(&acc64[j], q);
+              } else {
+                const unsigned old = atomicAdd(&acc_lo[j], (unsigned)q & LIMB_MASK);
+                atomicAdd(&acc_hi[j], (unsigned)(q >> LIMB_BITS));
+                first = old == 0u;
+              }
+            }
+            if (track) {
+              const unsigned m = __ballot_sync(0xffffffffu, first);
+              if (m) {
+                const int leader = __ffs(m) - 1;
+                int pos = 0;
+                if (lane == leader) pos = atomicAdd(&s_ntouched, __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, leader);
+                if (first) {
+                  const int my = pos + __popc(m & ((1u << lane) - 1u));
+                  if (my < p.tcap) touched[my] = j;
+                }
+              }
             }
           }
         }
@@ -370,6 +401,8 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
         __syncthreads();
       }
     }
+    const int n_touched = s_ntouched;
+    const bool sparse = track && n_touched <= p.tcap;
     if (p.mask) {  // pipelines/pipeline.py:174-175 -- before the truncation to N
       for (int r = tid; r < d; r += nt) {
         const int j = p.indices[xb + r] - r0;
@@ -383,7 +416,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       }
       __syncthreads();
     }
-    ScoreSrc src{acc_lo, acc_hi, wide ? acc64 : nullptr, r0, ns};
+    ScoreSrc src{acc_lo, acc_hi, wide ? acc64 : nullptr, sparse ? touched : nullptr, r0, sparse ? n_touched : ns};
     if (p.mode == PRED_TOPN) {
       const int m = block_select_topk(src, p.N, list, p.cap, p.direct_cap, hist, sh);
       for (int t = tid; t < p.N; t += nt) {
@@ -393,7 +426,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       if (tid == 0) p.part_len[slot_out] = m;
     } else if (p.mode == PRED_COUNT) {
       int cnt = 0;
-      for (int s = tid; s < ns; s += nt) cnt += src.score(s) != 0;
+      for (int s = tid; s < ns; s += nt) cnt += src.score_at(s) != 0;
       cnt = __reduce_add_sync(0xffffffffu, cnt);
       if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
       __syncthreads();
@@ -404,7 +437,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       int running = 0;
       for (int base = 0; base < ns; base += nt) {
         const int s = base + tid;
-        const u64 sc = s < ns ? src.score(s) : 0ull;
+        const u64 sc = s < ns ? src.score_at(s) : 0ull;
         const unsigned bal = __ballot_sync(0xffffffffu, sc != 0);
         if (lane == 0) sh->warp_tot[warp] = __popc(bal);
         __syncthreads();
@@ -422,6 +455,19 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
         running += tot;
         __syncthreads();
       }
+    }
+    __syncthreads();
+    // ---- restore the all-zero invariant
+    if (sparse) {
+      for (int t = tid; t < n_touched; t += nt) {
+        const int j = touched[t];
+        acc_lo[j] = 0u;
+        acc_hi[j] = 0u;
+      }
+    } else {
+      for (int s = tid; s < ns; s += nt) acc64[s] = 0ull;
+      if (ns < p.R)
+        for (int s = tid; s < ns; s += nt) acc_hi[s] = 0u;
     }
     __syncthreads();
   }
@@ -489,27 +535,37 @@ static int next_pow2(int v) {
 }
 
 struct PredGeom {
-  int cap, direct_cap, P, R, nt;
+  int cap, direct_cap, P, R, nt, tcap;
   size_t fixed, smem;
 };
 
 static PredGeom predict_geometry(rpk_ctx* c, int N) {
   PredGeom g;
   const bool tiny = c->flags & DBG_TINY_LIST;
-  g.cap = std::max(tiny ? 64 : 1024, next_pow2(2 * std::max(N, 1)));
-  g.direct_cap = tiny ? std::max(N, 1) : std::min(g.cap, std::max(256, 2 * N));
+  g.cap = std::max(tiny ? 64 : 256, next_pow2(2 * std::max(N, 1)));
+  g.direct_cap = tiny ? std::max(N, 1) : std::min(g.cap, std::max(64, 2 * N));
   g.fixed = (size_t)g.cap * sizeof(Entry) + SEL_BINS * sizeof(int) + ((sizeof(SelShared) + 15) / 16) * 16;
   RPK_REQUIRE((size_t)c->smem_max > g.fixed + 1024 + 8192, "N too large for shared memory");
   const size_t avail = (size_t)c->smem_max - g.fixed - 1024;
-  const int64_t Rmax = (int64_t)(avail / sizeof(u64)) & ~(int64_t)3;
   const int64_t I = c->m_I;
-  int P = (int)((I + Rmax - 1) / Rmax);
-  if (P < 1) P = 1;
-  if ((c->flags & DBG_MULTI_PASS) && P < 2 && I >= 2) P = 2;
+  // 8 B of accumulator per item of a range + a list of touched slots (4 B each, up to 8192 of them)
+  int P = 1;
+  int64_t R = 0, T = 0;
+  for (;; ++P) {
+    R = ((I + P - 1) / P + 3) & ~(int64_t)3;
+    if (R < 4) R = 4;
+    T = std::min<int64_t>(R, tiny ? 48 : 8192);
+    if ((size_t)(R * 8 + T * 4) <= avail) break;
+  }
+  if ((c->flags & DBG_MULTI_PASS) && P < 2 && I >= 8) {
+    P = 2;
+    R = ((I + P - 1) / P + 3) & ~(int64_t)3;
+    T = std::min<int64_t>(R, tiny ? 48 : 8192);
+  }
   g.P = P;
-  g.R = (int)(((I + P - 1) / P + 3) & ~(int64_t)3);
-  if (g.R < 4) g.R = 4;
-  g.smem = g.fixed + (size_t)g.R * sizeof(u64);
+  g.R = (int)R;
+  g.tcap = (int)T;
+  g.smem = g.fixed + (size_t)R * sizeof(u64) + (size_t)T * sizeof(int);
   g.nt = g.R >= 8192 ? 1024 : (g.R >= 2048 ? 512 : 256);
   return g;
 }
@@ -574,6 +630,7 @@ static void fill_common(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_t U
   pp.force_wide = (c->flags & DBG_WIDE_ACC) ? 1 : 0;
   pp.cap = g.cap;
   pp.direct_cap = g.direct_cap;
+  pp.tcap = g.tcap;
   pp.part_idx = nullptr;
   pp.part_sq = nullptr;
   pp.part_len = nullptr;

@@ -3,11 +3,13 @@
 // recpack/util.py:50-77 (get_top_K_ranks) with a deterministic rule: best key first, ties by
 // ascending index.
 //
-// A "source" enumerates candidate slots.  For every candidate it yields
-//   - a 64-bit SORTABLE key `akey` (larger = better) that is allowed to be approximate: it may
-//     mis-order two candidates only if their akeys differ by at most Src::margin();
-//   - an Entry (16 B) carrying what the exact comparator needs.
-// Src::cmp3(a, b) is the exact three-way comparison of two entries' keys (index excluded).
+// A "source" enumerates candidate slots:
+//   bool key(slot, akey)   false when the slot holds no candidate; otherwise a 64-bit SORTABLE key
+//                          (larger = better) that is allowed to be approximate: it may mis-order two
+//                          candidates only if their akeys differ by at most Src::margin();
+//   void entry(slot, e)    the Entry (16 B) of a candidate slot, carrying what the exact comparator needs;
+//   int cmp3(a, b)         exact three-way comparison of two entries' keys (index excluded).
+// Scans that only need the key (histograms, counts) never build entries.
 //
 // Algorithm (all control flow is block-uniform):
 //   A. one scan: count candidates, min/max akey, and copy them to `list` while they fit.
@@ -220,12 +222,13 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
       int slot = base + tid;
       Entry e;
       u64 k = 0;
-      bool c = slot < nslots && src.load(slot, e, k);
-      append_entry(c, e, list, direct_cap, &sh->count);
+      bool c = slot < nslots && src.key(slot, k);
       if (c) {
+        src.entry(slot, e);
         lmin = k < lmin ? k : lmin;
         lmax = k > lmax ? k : lmax;
       }
+      append_entry(c, e, list, direct_cap, &sh->count);
     }
     lmin = warp_min_u64(lmin);
     lmax = warp_max_u64(lmax);
@@ -241,11 +244,10 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
     m = n_c;
   } else {
     // ---- B: refine on the approximate key until the survivors fit
-    auto keyf = [&](int slot, u64& k) -> bool {
-      Entry e;
-      return src.load(slot, e, k);
-    };
-    const int room = cap / 2 > K ? cap / 2 : K;
+    auto keyf = [&](int slot, u64& k) -> bool { return src.key(slot, k); };
+    // keep the survivor list (and the final sort) close to K
+    int room = K + (K / 4 > 32 ? K / 4 : 32);
+    if (room > cap) room = cap;
     refine_keys(keyf, nslots, K, room, sh->kmin, sh->kmax, 0, n_c, hist, sh);
     u64 lo = sh->lo, hi = sh->hi;
     int g = sh->g_new, n_in = sh->n_in;
@@ -256,7 +258,8 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
       int slot = base + tid;
       Entry e;
       u64 k = 0;
-      bool c = slot < nslots && src.load(slot, e, k) && k >= thr;
+      bool c = slot < nslots && src.key(slot, k) && k >= thr;
+      if (c) src.entry(slot, e);
       append_entry(c, e, list, cap, &sh->count);
     }
     __syncthreads();
@@ -275,7 +278,8 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
         int slot = base + tid;
         Entry e;
         u64 k = 0;
-        bool c = slot < nslots && src.load(slot, e, k) && k > band_hi;
+        bool c = slot < nslots && src.key(slot, k) && k > band_hi;
+        if (c) src.entry(slot, e);
         append_entry(c, e, list, cap, &sh->count);
       }
       __syncthreads();
@@ -286,7 +290,8 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
       // group = band members with exact key strictly between lb and ub
       auto in_group = [&](int slot, Entry& e) -> bool {
         u64 k;
-        if (!src.load(slot, e, k) || k < band_lo || k > band_hi) return false;
+        if (!src.key(slot, k) || k < band_lo || k > band_hi) return false;
+        src.entry(slot, e);
         if (has_ub && src.cmp3(e, ub) >= 0) return false;
         if (has_lb && src.cmp3(e, lb) <= 0) return false;
         return true;
@@ -309,8 +314,7 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
         if (ps == 0x7fffffff) break;  // group exhausted (cannot happen while need > 0)
         if (tid == 0) {
           Entry e;
-          u64 k;
-          src.load(ps, e, k);
+          src.entry(ps, e);
           sh->piv = e;
           sh->count = 0;   // greater than pivot
           sh->count2 = 0;  // equal to pivot
@@ -381,7 +385,6 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
         for (int base = 0; base < nslots; base += nt) {
           int slot = base + tid;
           Entry e;
-          u64 k = 0;
           bool c = slot < nslots && in_group(slot, e) && src.cmp3(e, piv) == 0 &&
                    (u64)(unsigned)(SENTINEL_IDX - e.idx) >= ilo;
           append_entry(c, e, list, cap, &sh->count);

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 UNIT = ["unit_cosine", "unit_empty_col", "unit_condprob", "unit_condprob_pd1", "unit_condprob_pd0.2", "unit_condprob_pd0.5"]
 SMALL = ["small_cosine", "small_condprob", "small_condprob_pd"]
-FLAG_SETS = [0, 2, 4, 6]  # tiny candidate list / multi-pass / both
+FLAG_SETS = [0, 1, 2, 4, 5, 6]  # bit0: 32-bit counters (fit) / wide accumulators (predict); bit1: tiny lists; bit2: multi-pass
 
 
 @pytest.fixture(scope="module")
