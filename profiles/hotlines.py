@@ -26,7 +26,7 @@ for l in dis:
 rows = list(csv.reader(open(src_csv)))
 hdr = rows[1]
 i_s, i_n, i_x = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Source")
-inst = rows[2:]
+inst = [r for r in rows[2:] if len(r) == len(hdr)][: len(lines)]
 print(f"# {len(inst)} SASS rows in csv, {len(lines)} instructions with line info")
 agg = defaultdict(lambda: [0, 0])
 tot = 0

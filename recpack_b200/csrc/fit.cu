@@ -41,6 +41,35 @@ __global__ void k_fill_csc(const int64_t* __restrict__ indptr, const int* __rest
   }
 }
 
+// pref[k] = sum of the history lengths of the users listed before position k of the same item
+// (exclusive, in CSC order): lets the fit kernel cut a row's work into equal pieces per warp.
+__global__ void k_csc_prefix(const int64_t* __restrict__ cscptr, const int* __restrict__ csc_users,
+                             const int64_t* __restrict__ indptr, int64_t I, unsigned* __restrict__ pref) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < I; i += nwarps) {
+    const int64_t b = cscptr[i], e = cscptr[i + 1];
+    unsigned carry = 0;
+    for (int64_t base = b; base < e; base += 32) {
+      const int64_t k = base + lane;
+      unsigned v = 0;
+      if (k < e) {
+        const int u = csc_users[k];
+        v = (unsigned)(indptr[u + 1] - indptr[u]);
+      }
+      unsigned incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (k < e) pref[k] = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+}
+
 __global__ void k_recip_f32(const int* __restrict__ n, float* __restrict__ rnf, int64_t I) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < I) rnf[j] = n[j] > 0 ? __frcp_rn((float)n[j]) : 0.f;
@@ -159,6 +188,8 @@ struct FitParams {
   const int64_t* usplit;  // null when P == 1
   const int64_t* cscptr;
   const int* csc_users;
+  const unsigned* pref;   // per-item exclusive prefix of history lengths (CSC order)
+  const u64* work;        // per-item total of history lengths
   SimKey sk;
   const int* order;       // rows of this launch, heaviest first
   const int* nrows_dev;   // number of rows in `order` (device side: no host round trip)
@@ -172,15 +203,11 @@ struct FitParams {
   int* out_len;
 };
 
-__host__ __device__ __forceinline__ size_t sel_smem_bytes(int cap) {
-  return (size_t)cap * sizeof(Entry) + SEL_BINS * sizeof(int) + ((sizeof(SelShared) + 15) / 16) * 16;
-}
-
 template <bool PACK16>
 __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   Entry* list = reinterpret_cast<Entry*>(smem);
-  int* hist = reinterpret_cast<int*>(smem + (size_t)p.cap * sizeof(Entry));
+  int* hist = reinterpret_cast<int*>(smem + sel_list_bytes(p.cap));
   SelShared* sh = reinterpret_cast<SelShared*>(hist + SEL_BINS);
   unsigned* cnt = reinterpret_cast<unsigned*>(smem + sel_smem_bytes(p.cap));
   __shared__ int s_work;
@@ -213,33 +240,79 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
     const int nwords = PACK16 ? (ns + 1) >> 1 : ns;
     for (int s = tid; s < nwords; s += nt) cnt[s] = 0u;
     __syncthreads();
-    // ---- accumulate: the item's users are dealt to the warps in chunks (<= 32 users, one per lane, so
-    //      that their row pointers are fetched in parallel); every warp then walks its users' histories
-    const int64_t nu = ue - ub;
-    int chunk = (int)((nu + nwarps - 1) / nwarps);
-    chunk = chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk);
-    for (int64_t base = ub + (int64_t)warp * chunk; base < ue; base += (int64_t)nwarps * chunk) {
-      const int nvalid = (int)min((int64_t)chunk, ue - base);
-      int64_t beg = 0;
-      int len = 0;
-      if (lane < nvalid) {
-        const int u = p.csc_users[base + lane];
-        if (p.usplit) {
+    const int64_t nu64 = ue - ub;
+    if (!p.usplit) {
+      // ---- accumulate, single pass: the row's work (sum of its users' history lengths) is cut into equal
+      //      pieces, one per warp, so that a single long history cannot stall the row on one warp
+      const int nu = (int)nu64;
+      const unsigned T = (unsigned)p.work[i];
+      unsigned share = (T + nwarps - 1) / nwarps;
+      share = (share + 31u) & ~31u;
+      const unsigned lo = (unsigned)warp * share;
+      const unsigned hi = min(T, lo + share);
+      if (lo < hi) {
+        const unsigned* pf_row = p.pref + ub;
+        int a = 0, b = nu;  // 32-ary search: last user whose prefix is <= lo
+        while (b - a > 1) {
+          const int step = (b - a + 31) / 32;
+          const int k = a + lane * step;
+          const bool ok = k < b && pf_row[k] <= lo;
+          const unsigned mk = __ballot_sync(0xffffffffu, ok) | 1u;
+          const int last = 31 - __clz(mk);
+          const int na = a + last * step;
+          b = min(b, na + step);
+          a = na;
+        }
+        for (int kbase = a; kbase < nu; kbase += 32) {
+          const int kk = kbase + lane;
+          unsigned pf = 0xffffffffu;
+          int64_t beg = 0;
+          int len = 0;
+          if (kk < nu) {
+            const int u = p.csc_users[ub + kk];
+            pf = pf_row[kk];
+            beg = p.indptr[u];
+            len = (int)(p.indptr[u + 1] - beg);
+          }
+          if (__shfl_sync(0xffffffffu, pf, 0) >= hi) break;
+          for (int l = 0; l < 32; ++l) {
+            const unsigned pfl = __shfl_sync(0xffffffffu, pf, l);
+            if (pfl >= hi) break;
+            const int n = __shfl_sync(0xffffffffu, len, l);
+            const int64_t bb = __shfl_sync(0xffffffffu, beg, l);
+            const int s0 = lo > pfl ? (int)(lo - pfl) : 0;
+            const int e1 = (int)min((unsigned)n, hi - pfl);
+            for (int e = s0 + lane; e < e1; e += 32) {
+              const int j = p.indices[bb + e] - r0;
+              if (PACK16) atomicAdd(&cnt[j >> 1], 1u << ((j & 1) * 16));
+              else atomicAdd(&cnt[j], 1u);
+            }
+          }
+        }
+      }
+    } else {
+      // ---- accumulate, several item ranges: users are dealt to the warps in chunks (<= 32 users, one per
+      //      lane, so that their row pointers are fetched in parallel)
+      int chunk = (int)((nu64 + nwarps - 1) / nwarps);
+      chunk = chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk);
+      for (int64_t base = ub + (int64_t)warp * chunk; base < ue; base += (int64_t)nwarps * chunk) {
+        const int nvalid = (int)min((int64_t)chunk, ue - base);
+        int64_t beg = 0;
+        int len = 0;
+        if (lane < nvalid) {
+          const int u = p.csc_users[base + lane];
           const int64_t* us = p.usplit + (int64_t)u * (p.P + 1) + pass;
           beg = us[0];
           len = (int)(us[1] - beg);
-        } else {
-          beg = p.indptr[u];
-          len = (int)(p.indptr[u + 1] - beg);
         }
-      }
-      for (int l = 0; l < nvalid; ++l) {
-        const int64_t b = __shfl_sync(0xffffffffu, beg, l);
-        const int n = __shfl_sync(0xffffffffu, len, l);
-        for (int e = lane; e < n; e += 32) {
-          const int j = p.indices[b + e] - r0;
-          if (PACK16) atomicAdd(&cnt[j >> 1], 1u << ((j & 1) * 16));
-          else atomicAdd(&cnt[j], 1u);
+        for (int l = 0; l < nvalid; ++l) {
+          const int64_t b = __shfl_sync(0xffffffffu, beg, l);
+          const int n = __shfl_sync(0xffffffffu, len, l);
+          for (int e = lane; e < n; e += 32) {
+            const int j = p.indices[b + e] - r0;
+            if (PACK16) atomicAdd(&cnt[j >> 1], 1u << ((j & 1) * 16));
+            else atomicAdd(&cnt[j], 1u);
+          }
         }
       }
     }
@@ -272,7 +345,7 @@ struct MergeParams {
 __global__ void __launch_bounds__(256) k_fit_merge(MergeParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   Entry* list = reinterpret_cast<Entry*>(smem);
-  int* hist = reinterpret_cast<int*>(smem + (size_t)p.cap * sizeof(Entry));
+  int* hist = reinterpret_cast<int*>(smem + sel_list_bytes(p.cap));
   SelShared* sh = reinterpret_cast<SelShared*>(hist + SEL_BINS);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int nrows = p.nrows_dev[0];
@@ -289,23 +362,40 @@ __global__ void __launch_bounds__(256) k_fit_merge(MergeParams p) {
   }
 }
 
-// Stable split of the heaviest-first row order into rows whose counts fit 16 bits and the rest.
-__global__ void k_split_rows(const int* __restrict__ order, int nrows, const int* __restrict__ n, int limit,
-                             int* __restrict__ light, int* __restrict__ heavy, int* __restrict__ counts) {
-  const int lane = threadIdx.x;
+// Stable split of the heaviest-first row order into rows whose counts fit 16 bits and the rest (one block).
+__global__ void __launch_bounds__(1024) k_split_rows(const int* __restrict__ order, int nrows, const int* __restrict__ n,
+                                                     int limit, int* __restrict__ light, int* __restrict__ heavy,
+                                                     int* __restrict__ counts) {
+  __shared__ int wl[32], wh[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   int nl = 0, nh = 0;
-  for (int base = 0; base < nrows; base += 32) {
-    const int k = base + lane;
+  for (int base = 0; base < nrows; base += blockDim.x) {
+    const int k = base + tid;
     const int row = k < nrows ? order[k] : -1;
     const bool is_l = row >= 0 && n[row] < limit;
     const bool is_h = row >= 0 && !is_l;
     const unsigned ml = __ballot_sync(0xffffffffu, is_l), mh = __ballot_sync(0xffffffffu, is_h);
-    if (is_l) light[nl + __popc(ml & ((1u << lane) - 1u))] = row;
-    if (is_h) heavy[nh + __popc(mh & ((1u << lane) - 1u))] = row;
-    nl += __popc(ml);
-    nh += __popc(mh);
+    if (lane == 0) {
+      wl[warp] = __popc(ml);
+      wh[warp] = __popc(mh);
+    }
+    __syncthreads();
+    int ol = 0, oh = 0, tl = 0, th = 0;
+    for (int q = 0; q < nw; ++q) {
+      if (q < warp) {
+        ol += wl[q];
+        oh += wh[q];
+      }
+      tl += wl[q];
+      th += wh[q];
+    }
+    if (is_l) light[nl + ol + __popc(ml & ((1u << lane) - 1u))] = row;
+    if (is_h) heavy[nh + oh + __popc(mh & ((1u << lane) - 1u))] = row;
+    nl += tl;
+    nh += th;
+    __syncthreads();
   }
-  if (lane == 0) {
+  if (tid == 0) {
     counts[0] = nl;
     counts[1] = nh;
   }
@@ -395,6 +485,12 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     k_fill_csc<<<blocks, 256, 0, st>>>(indptr, indices, U, cscptr, cursor, csc_users, work);
     RPK_LAUNCH_CHECK(c);
   }
+  unsigned* pref = c->buf<unsigned>("fit_pref", (size_t)nnz);
+  if (nnz > 0 && I > 0) {
+    int blocks = (int)std::min<int64_t>((I * 32 + 255) / 256, (int64_t)c->sm_count * 32);
+    k_csc_prefix<<<blocks, 256, 0, st>>>(cscptr, csc_users, indptr, I, pref);
+    RPK_LAUNCH_CHECK(c);
+  }
   if (I > 0) {
     k_recip_f32<<<ceil_div(I, 256), 256, 0, st>>>(n, rnf, I);
     RPK_LAUNCH_CHECK(c);
@@ -427,11 +523,11 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     int* queues = c->buf<int>("fit_queues", 4);
     RPK_CUDA(cudaMemsetAsync(queues, 0, sizeof(int) * 4, st));
     const bool force_wide = (c->flags & DBG_WIDE_ACC) != 0;  // test hook: every row through the 32-bit path
-    k_split_rows<<<1, 32, 0, st>>>(order, (int)nrows, n, force_wide ? 0 : 65536, order_l, order_h, split_cnt);
+    k_split_rows<<<1, 1024, 0, st>>>(order, (int)nrows, n, force_wide ? 0 : 65536, order_l, order_h, split_cnt);
     RPK_LAUNCH_CHECK(c);
 
     const bool tiny = c->flags & DBG_TINY_LIST;
-    const int cap = std::max(tiny ? 64 : 512, next_pow2(2 * K));
+    const int cap = std::max(tiny ? 64 : 1024, next_pow2(2 * K));
     const int direct_cap = tiny ? K : std::min(cap, std::max(2 * K, 64));
     const size_t fixed = sel_smem_bytes(cap);
     RPK_REQUIRE((size_t)c->smem_max > fixed + 1024 + 4096, "K too large for shared memory");
@@ -471,6 +567,8 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
       fp.usplit = usplit;
       fp.cscptr = cscptr;
       fp.csc_users = csc_users;
+      fp.pref = pref;
+      fp.work = work;
       fp.sk = sk;
       fp.order = wide ? order_h : order_l;
       fp.nrows_dev = split_cnt + wide;

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_topk_csr(const int64_t* __restrict__ in
                                                   int direct_cap, int* __restrict__ out_idx, int* __restrict__ out_len) {
   extern __shared__ __align__(16) unsigned char smem[];
   Entry* list = reinterpret_cast<Entry*>(smem);
-  int* hist = reinterpret_cast<int*>(smem + (size_t)cap * sizeof(Entry));
+  int* hist = reinterpret_cast<int*>(smem + sel_list_bytes(cap));
   SelShared* sh = reinterpret_cast<SelShared*>(hist + SEL_BINS);
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
@@ -88,7 +88,7 @@ void run_topk_csr(rpk_ctx* c, int64_t rows, int64_t nnz, const int64_t* indptr_u
     const bool tiny = c->flags & DBG_TINY_LIST;
     const int cap = std::max(tiny ? 64 : 1024, next_pow2(2 * K));
     const int direct_cap = tiny ? K : cap;
-    const size_t smem = (size_t)cap * sizeof(Entry) + SEL_BINS * sizeof(int) + ((sizeof(SelShared) + 15) / 16) * 16;
+    const size_t smem = sel_smem_bytes(cap);
     RPK_CUDA(cudaFuncSetAttribute(k_topk_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = (int)std::min<int64_t>(rows, (int64_t)c->sm_count * 8);
     k_topk_csr<<<grid, 256, smem, st>>>(indptr, indices, values, rows, K, cap, direct_cap, o_idx.dev, o_len.dev);

@@ -280,10 +280,9 @@ struct PredParams {
 __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   Entry* list = reinterpret_cast<Entry*>(smem);
-  int* hist = reinterpret_cast<int*>(smem + (size_t)p.cap * sizeof(Entry));
+  int* hist = reinterpret_cast<int*>(smem + sel_list_bytes(p.cap));
   SelShared* sh = reinterpret_cast<SelShared*>(hist + SEL_BINS);
-  u64* acc64 = reinterpret_cast<u64*>(smem + (size_t)p.cap * sizeof(Entry) + SEL_BINS * sizeof(int) +
-                                      ((sizeof(SelShared) + 15) / 16) * 16);
+  u64* acc64 = reinterpret_cast<u64*>(smem + sel_smem_bytes(p.cap));
   unsigned* acc_lo = reinterpret_cast<unsigned*>(acc64);
   unsigned* acc_hi = acc_lo + p.R;
   int* touched = reinterpret_cast<int*>(acc64 + p.R);
@@ -544,7 +543,7 @@ static PredGeom predict_geometry(rpk_ctx* c, int N) {
   const bool tiny = c->flags & DBG_TINY_LIST;
   g.cap = std::max(tiny ? 64 : 256, next_pow2(2 * std::max(N, 1)));
   g.direct_cap = tiny ? std::max(N, 1) : std::min(g.cap, std::max(64, 2 * N));
-  g.fixed = (size_t)g.cap * sizeof(Entry) + SEL_BINS * sizeof(int) + ((sizeof(SelShared) + 15) / 16) * 16;
+  g.fixed = sel_smem_bytes(g.cap);
   RPK_REQUIRE((size_t)c->smem_max > g.fixed + 1024 + 8192, "N too large for shared memory");
   const size_t avail = (size_t)c->smem_max - g.fixed - 1024;
   const int64_t I = c->m_I;

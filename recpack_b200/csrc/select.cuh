@@ -35,6 +35,7 @@ struct __align__(16) Entry {
 
 constexpr int SEL_BINS = 4096;
 constexpr int SENTINEL_IDX = 0x7fffffff;
+constexpr int SEL_RANK_MAX = 64;  // up to this many survivors: rank by counting instead of bitonic
 
 struct SelShared {
   u64 kmin, kmax;
@@ -48,6 +49,12 @@ struct SelShared {
   int piv_slot;
   int warp_tot[33];
 };
+
+// Shared-memory layout of the selection workspace: [list: cap + SEL_RANK_MAX entries][hist][SelShared]
+__host__ __device__ __forceinline__ size_t sel_list_bytes(int cap) { return (size_t)(cap + SEL_RANK_MAX) * sizeof(Entry); }
+__host__ __device__ __forceinline__ size_t sel_smem_bytes(int cap) {
+  return sel_list_bytes(cap) + SEL_BINS * sizeof(int) + ((sizeof(SelShared) + 15) / 16) * 16;
+}
 
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
 #pragma unroll
@@ -92,6 +99,8 @@ __device__ __forceinline__ bool entry_before(const Src& src, const Entry& a, con
   return a.idx < b.idx;
 }
 
+// Bitonic sort, best first.  Stages whose partner distance is below 32 only touch elements owned by
+// one warp (element i belongs to thread i % blockDim.x), so they need a warp barrier, not a block barrier.
 template <class Src>
 __device__ void bitonic_sort_entries(const Src& src, Entry* list, int n_pow2) {
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -108,9 +117,81 @@ __device__ void bitonic_sort_entries(const Src& src, Entry* list, int n_pow2) {
           }
         }
       }
-      __syncthreads();
+      const bool next_is_wide = j > 1 ? (j >> 1) >= 32 : k >= 32;
+      if (j >= 32 || next_is_wide || (j == 1 && k == n_pow2)) __syncthreads();
+      else __syncwarp();
     }
   }
+}
+
+// Small lists: rank every element by counting the elements that precede it (one pass, two barriers).
+// `tmp` must hold m entries and may not alias `list`.
+template <class Src>
+__device__ void rank_sort_entries(const Src& src, Entry* list, Entry* tmp, int m) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < m; i += nt) {
+    const Entry a = list[i];
+    int rank = 0;
+    for (int f = 0; f < m; ++f) rank += (f != i) && entry_before(src, list[f], a);
+    tmp[rank] = a;
+  }
+  __syncthreads();
+  for (int i = tid; i < m; i += nt) list[i] = tmp[i];
+  __syncthreads();
+}
+
+// Finds the bin holding the need-th largest key of a histogram, scanning bins from the top:
+// sh->bstar = that bin, sh->g_new = g + members of higher bins, sh->n_in = members of the bin.
+// When fewer than `need` members exist in total, bstar = 0 and n_in / g_new describe bin 0.
+__device__ __forceinline__ void find_boundary_bin(const int* hist, int nb, int g, int need, SelShared* sh) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const int per = (nb + nt - 1) / nt;
+  const int b0 = tid * per;
+  const int b1 = min(nb, b0 + per);
+  int tsum = 0;
+  for (int b = b0; b < b1; ++b) tsum += hist[b];
+  int incl = tsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) sh->warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = lane < nwarps ? sh->warp_tot[lane] : 0;
+    int iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, iv, o);
+      if (lane >= o) iv += t;
+    }
+    sh->warp_tot[lane] = iv - v;  // exclusive prefix of warp totals
+    if (lane == 31) sh->warp_tot[32] = iv;
+  }
+  __syncthreads();
+  const int total = sh->warp_tot[32];
+  const int prefix_excl = sh->warp_tot[warp] + incl - tsum;
+  int above = g + (total - prefix_excl - tsum);  // members in bins owned by higher threads
+  if (g + total < need) {
+    if (tid == 0) {
+      sh->bstar = 0;
+      sh->g_new = g + total - hist[0];
+      sh->n_in = hist[0];
+    }
+  } else if (above < need && above + tsum >= need) {
+    for (int b = b1 - 1; b >= b0; --b) {
+      int h = hist[b];
+      if (above + h >= need) {
+        sh->bstar = b;
+        sh->g_new = above;
+        sh->n_in = h;
+        break;
+      }
+      above += h;
+    }
+  }
+  __syncthreads();
 }
 
 // One refinement run.  `f(slot, key)` returns true when the slot belongs to the group being
@@ -120,7 +201,7 @@ __device__ void bitonic_sort_entries(const Src& src, Entry* list, int n_pow2) {
 template <class F>
 __device__ void refine_keys(F f, int nslots, int need, int room, u64 lo, u64 hi, int g, int n_in, int* hist,
                             SelShared* sh) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const int tid = threadIdx.x, nt = blockDim.x;
   while (g + n_in > room && lo < hi) {
     const u64 range = hi - lo;
     const int bits = 64 - __clzll((long long)range);
@@ -128,59 +209,25 @@ __device__ void refine_keys(F f, int nslots, int need, int room, u64 lo, u64 hi,
     const int nb = (int)(range >> shift) + 1;
     for (int b = tid; b < nb; b += nt) hist[b] = 0;
     __syncthreads();
-    for (int base = 0; base < nslots; base += nt) {
-      int slot = base + tid;
-      u64 k;
-      if (slot < nslots && f(slot, k) && k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
-    }
-    __syncthreads();
-    // locate the bin holding the need-th largest key, scanning bins from the top
-    const int per = (nb + nt - 1) / nt;
-    const int b0 = tid * per;
-    const int b1 = min(nb, b0 + per);
-    int tsum = 0;
-    for (int b = b0; b < b1; ++b) tsum += hist[b];
-    int incl = tsum;
+    for (int base = 0; base < nslots; base += 4 * nt) {
+      u64 k[4];
+      bool c[4];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    if (lane == 31) sh->warp_tot[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      int v = lane < nwarps ? sh->warp_tot[lane] : 0;
-      int iv = v;
+      for (int q = 0; q < 4; ++q) {
+        const int slot = base + q * nt + tid;
+        c[q] = slot < nslots && f(slot, k[q]) && k[q] >= lo && k[q] <= hi;
+      }
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, iv, o);
-        if (lane >= o) iv += t;
-      }
-      sh->warp_tot[lane] = iv - v;  // exclusive prefix of warp totals
-      if (lane == 31) sh->warp_tot[32] = iv;
+      for (int q = 0; q < 4; ++q)
+        if (c[q]) atomicAdd(&hist[(int)((k[q] - lo) >> shift)], 1);
     }
     __syncthreads();
-    const int total = sh->warp_tot[32];
-    const int prefix_excl = sh->warp_tot[warp] + incl - tsum;
-    int above = g + (total - prefix_excl - tsum);  // group members in bins owned by higher threads
-    if (above < need && above + tsum >= need) {
-      for (int b = b1 - 1; b >= b0; --b) {
-        int h = hist[b];
-        if (above + h >= need) {
-          sh->bstar = b;
-          sh->g_new = above;
-          sh->n_in = h;
-          break;
-        }
-        above += h;
-      }
-    }
-    __syncthreads();
+    find_boundary_bin(hist, nb, g, need, sh);
     const int bstar = sh->bstar;
     g = sh->g_new;
     n_in = sh->n_in;
     const u64 nlo = lo + ((u64)bstar << shift);
-    const u64 span = shift >= 64 ? ~0ull : (((u64)1 << shift) - 1);
+    const u64 span = (((u64)1) << shift) - 1;
     u64 nhi = nlo + span;
     if (nhi > hi || nhi < nlo) nhi = hi;
     lo = nlo;
@@ -196,9 +243,38 @@ __device__ void refine_keys(F f, int nslots, int need, int room, u64 lo, u64 hi,
   __syncthreads();
 }
 
+// Appends every candidate with key >= thr to list (4 slots per thread in flight); returns the count.
+template <class Src>
+__device__ int compact_above(const Src& src, u64 thr, Entry* list, int cap, SelShared* sh) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int nslots = src.nslots();
+  if (tid == 0) sh->count = 0;
+  __syncthreads();
+  for (int base = 0; base < nslots; base += 4 * nt) {
+    u64 k[4];
+    bool c[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int slot = base + q * nt + tid;
+      c[q] = slot < nslots && src.key(slot, k[q]) && k[q] >= thr;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      Entry e;
+      if (c[q]) src.entry(base + q * nt + tid, e);
+      append_entry(c[q], e, list, cap, &sh->count);
+    }
+  }
+  __syncthreads();
+  return sh->count;
+}
+
+constexpr int SEL_SAMPLE = 16;        // the threshold guess looks at one slot in 16
+constexpr int SEL_GUESS_MIN = 4096;   // below this many candidates the exact histogram is cheap enough
+
 // Returns m = number of selected entries (<= K); list[0..m) holds them best-first.
 // Requirements: blockDim.x multiple of 32; cap >= K, cap a power of two; direct_cap <= cap;
-// hist has SEL_BINS ints; list has cap entries.
+// hist has SEL_BINS ints; list has cap entries (+ SEL_RANK_MAX spare entries behind them).
 template <class Src>
 __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, int direct_cap, int* hist,
                                  SelShared* sh) {
@@ -209,7 +285,7 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
   if (direct_cap < K) direct_cap = K;  // the refinement needs at least K candidates
   if (direct_cap > cap) direct_cap = cap;
 
-  // ---- A: count, bounds, optimistic copy
+  // ---- A: count candidates and bound their keys (register accumulation, one atomic per warp)
   if (tid == 0) {
     sh->count = 0;
     sh->kmin = ~0ull;
@@ -218,197 +294,227 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
   __syncthreads();
   {
     u64 lmin = ~0ull, lmax = 0ull;
-    for (int base = 0; base < nslots; base += nt) {
-      int slot = base + tid;
-      Entry e;
-      u64 k = 0;
-      bool c = slot < nslots && src.key(slot, k);
-      if (c) {
-        src.entry(slot, e);
-        lmin = k < lmin ? k : lmin;
-        lmax = k > lmax ? k : lmax;
+    int cnt = 0;
+    for (int base = 0; base < nslots; base += 4 * nt) {
+      u64 k[4];
+      bool c[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int slot = base + q * nt + tid;
+        c[q] = slot < nslots && src.key(slot, k[q]);
       }
-      append_entry(c, e, list, direct_cap, &sh->count);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (c[q]) {
+          cnt++;
+          lmin = k[q] < lmin ? k[q] : lmin;
+          lmax = k[q] > lmax ? k[q] : lmax;
+        }
     }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
     lmin = warp_min_u64(lmin);
     lmax = warp_max_u64(lmax);
-    if (lane == 0) {
+    if (lane == 0 && cnt) {
+      atomicAdd(&sh->count, cnt);
       atomicMin(&sh->kmin, lmin);
       atomicMax(&sh->kmax, lmax);
     }
   }
   __syncthreads();
   const int n_c = sh->count;
-  int m;
+  const u64 kmin = sh->kmin, kmax = sh->kmax;
+  __syncthreads();
+  int m = -1;
   if (n_c <= direct_cap) {
-    m = n_c;
+    m = compact_above(src, 0ull, list, cap, sh);
   } else {
-    // ---- B: refine on the approximate key until the survivors fit
     auto keyf = [&](int slot, u64& k) -> bool { return src.key(slot, k); };
     // keep the survivor list (and the final sort) close to K
     int room = K + (K / 4 > 32 ? K / 4 : 32);
     if (room > cap) room = cap;
-    refine_keys(keyf, nslots, K, room, sh->kmin, sh->kmax, 0, n_c, hist, sh);
-    u64 lo = sh->lo, hi = sh->hi;
-    int g = sh->g_new, n_in = sh->n_in;
-    u64 thr = lo > M ? lo - M : 0;
-    if (tid == 0) sh->count = 0;
-    __syncthreads();
-    for (int base = 0; base < nslots; base += nt) {
-      int slot = base + tid;
-      Entry e;
-      u64 k = 0;
-      bool c = slot < nslots && src.key(slot, k) && k >= thr;
-      if (c) src.entry(slot, e);
-      append_entry(c, e, list, cap, &sh->count);
-    }
-    __syncthreads();
-    m = sh->count;
-    if (m > cap) {
-      // ---- C: a band of (near-)equal keys is too large.  Pin tau = the K-th largest akey.
+    // ---- B0: cheap threshold guess from a 1-in-16 sample of the slots; accepted when it leaves
+    //          between K and cap candidates, which is then verified by the compaction itself
+    if (n_c >= SEL_GUESS_MIN && kmax > kmin) {
+      const u64 range = kmax - kmin;
+      const int bits = 64 - __clzll((long long)range);
+      const int shift = bits > 12 ? bits - 12 : 0;
+      const int nb = (int)(range >> shift) + 1;
+      for (int b = tid; b < nb; b += nt) hist[b] = 0;
       __syncthreads();
-      refine_keys(keyf, nslots, K, -1, lo, hi, g, n_in, hist, sh);
-      const u64 tau = sh->lo;
-      const u64 band_lo = tau > M ? tau - M : 0;
-      const u64 band_hi = tau + M < tau ? ~0ull : tau + M;
-      // certain members: akey above the band (fewer than K of them)
-      if (tid == 0) sh->count = 0;
-      __syncthreads();
-      for (int base = 0; base < nslots; base += nt) {
-        int slot = base + tid;
-        Entry e;
-        u64 k = 0;
-        bool c = slot < nslots && src.key(slot, k) && k > band_hi;
-        if (c) src.entry(slot, e);
-        append_entry(c, e, list, cap, &sh->count);
+      for (int t = tid; t * SEL_SAMPLE < nslots; t += nt) {
+        const int slot = t * SEL_SAMPLE + (SEL_SAMPLE / 2 < nslots - t * SEL_SAMPLE ? SEL_SAMPLE / 2 : 0);
+        u64 k;
+        if (src.key(slot, k)) atomicAdd(&hist[(int)((k - kmin) >> shift)], 1);
       }
       __syncthreads();
-      int have = sh->count;  // entries in list so far (all certain)
-      int need = K - have;   // still to take from the band, by exact order
-      bool has_lb = false, has_ub = false;
-      Entry lb = {0, 0, 0}, ub = {0, 0, 0};
-      // group = band members with exact key strictly between lb and ub
-      auto in_group = [&](int slot, Entry& e) -> bool {
-        u64 k;
-        if (!src.key(slot, k) || k < band_lo || k > band_hi) return false;
-        src.entry(slot, e);
-        if (has_ub && src.cmp3(e, ub) >= 0) return false;
-        if (has_lb && src.cmp3(e, lb) <= 0) return false;
-        return true;
-      };
-      while (need > 0) {
-        // pivot: the group member in the lowest slot
-        if (tid == 0) sh->piv_slot = 0x7fffffff;
+      const int ks = (K + SEL_SAMPLE - 1) / SEL_SAMPLE;
+      int sd = 1;
+      while (sd * sd < ks) ++sd;
+      find_boundary_bin(hist, nb, 0, ks + 3 * sd + 3, sh);
+      const u64 edge = kmin + ((u64)sh->bstar << shift);
+      const u64 thr = edge > M ? edge - M : 0;
+      __syncthreads();
+      const int got = compact_above(src, thr, list, cap, sh);
+      if (got >= K && got <= cap) m = got;
+    }
+    if (m < 0) {
+      // ---- B: exact radix refinement on the (approximate) key until the survivors fit
+      refine_keys(keyf, nslots, K, room, kmin, kmax, 0, n_c, hist, sh);
+      u64 lo = sh->lo, hi = sh->hi;
+      int g = sh->g_new, n_in = sh->n_in;
+      u64 thr = lo > M ? lo - M : 0;
+      __syncthreads();
+      m = compact_above(src, thr, list, cap, sh);
+      if (m > cap) {
+        // ---- C: a band of (near-)equal keys is too large.  Pin tau = the K-th largest akey.
         __syncthreads();
-        {
-          int best = 0x7fffffff;
-          for (int base = 0; base < nslots && best == 0x7fffffff; base += nt) {
-            int slot = base + tid;
-            Entry e;
-            if (slot < nslots && in_group(slot, e)) best = slot;
-          }
-          if (best != 0x7fffffff) atomicMin(&sh->piv_slot, best);
-        }
+        refine_keys(keyf, nslots, K, -1, lo, hi, g, n_in, hist, sh);
+        const u64 tau = sh->lo;
+        const u64 band_lo = tau > M ? tau - M : 0;
+        const u64 band_hi = tau + M < tau ? ~0ull : tau + M;
+        // certain members: akey above the band (fewer than K of them)
+        if (tid == 0) sh->count = 0;
         __syncthreads();
-        const int ps = sh->piv_slot;
-        if (ps == 0x7fffffff) break;  // group exhausted (cannot happen while need > 0)
-        if (tid == 0) {
+        for (int base = 0; base < nslots; base += nt) {
+          int slot = base + tid;
           Entry e;
-          src.entry(ps, e);
-          sh->piv = e;
-          sh->count = 0;   // greater than pivot
-          sh->count2 = 0;  // equal to pivot
+          u64 k = 0;
+          bool c = slot < nslots && src.key(slot, k) && k > band_hi;
+          if (c) src.entry(slot, e);
+          append_entry(c, e, list, cap, &sh->count);
         }
         __syncthreads();
-        const Entry piv = sh->piv;
-        {
-          int gt = 0, eq = 0;
+        int have = sh->count;  // entries in list so far (all certain)
+        int need = K - have;   // still to take from the band, by exact order
+        bool has_lb = false, has_ub = false;
+        Entry lb = {0, 0, 0}, ub = {0, 0, 0};
+        // group = band members with exact key strictly between lb and ub
+        auto in_group = [&](int slot, Entry& e) -> bool {
+          u64 k;
+          if (!src.key(slot, k) || k < band_lo || k > band_hi) return false;
+          src.entry(slot, e);
+          if (has_ub && src.cmp3(e, ub) >= 0) return false;
+          if (has_lb && src.cmp3(e, lb) <= 0) return false;
+          return true;
+        };
+        while (need > 0) {
+          // pivot: the group member in the lowest slot
+          if (tid == 0) sh->piv_slot = 0x7fffffff;
+          __syncthreads();
+          {
+            int best = 0x7fffffff;
+            for (int base = 0; base < nslots && best == 0x7fffffff; base += nt) {
+              int slot = base + tid;
+              Entry e;
+              if (slot < nslots && in_group(slot, e)) best = slot;
+            }
+            if (best != 0x7fffffff) atomicMin(&sh->piv_slot, best);
+          }
+          __syncthreads();
+          const int ps = sh->piv_slot;
+          if (ps == 0x7fffffff) break;  // group exhausted (cannot happen while need > 0)
+          if (tid == 0) {
+            Entry e;
+            src.entry(ps, e);
+            sh->piv = e;
+            sh->count = 0;   // greater than pivot
+            sh->count2 = 0;  // equal to pivot
+          }
+          __syncthreads();
+          const Entry piv = sh->piv;
+          {
+            int gt = 0, eq = 0;
+            for (int base = 0; base < nslots; base += nt) {
+              int slot = base + tid;
+              Entry e;
+              if (slot < nslots && in_group(slot, e)) {
+                int c = src.cmp3(e, piv);
+                gt += c > 0;
+                eq += c == 0;
+              }
+            }
+            gt = __reduce_add_sync(0xffffffffu, gt);
+            eq = __reduce_add_sync(0xffffffffu, eq);
+            if (lane == 0) {
+              if (gt) atomicAdd(&sh->count, gt);
+              if (eq) atomicAdd(&sh->count2, eq);
+            }
+          }
+          __syncthreads();
+          const int gt = sh->count, eq = sh->count2;
+          __syncthreads();
+          if (gt >= need) {  // the need-th best is above the pivot
+            has_lb = true;
+            lb = piv;
+            continue;
+          }
+          // everything above the pivot is in
+          if (tid == 0) sh->count = have;
+          __syncthreads();
+          const bool take_eq = gt + eq <= need || eq <= cap - have - gt;
           for (int base = 0; base < nslots; base += nt) {
             int slot = base + tid;
             Entry e;
+            bool c = false;
             if (slot < nslots && in_group(slot, e)) {
-              int c = src.cmp3(e, piv);
-              gt += c > 0;
-              eq += c == 0;
+              int c3 = src.cmp3(e, piv);
+              c = c3 > 0 || (c3 == 0 && take_eq);
             }
+            append_entry(c, e, list, cap, &sh->count);
           }
-          gt = __reduce_add_sync(0xffffffffu, gt);
-          eq = __reduce_add_sync(0xffffffffu, eq);
-          if (lane == 0) {
-            if (gt) atomicAdd(&sh->count, gt);
-            if (eq) atomicAdd(&sh->count2, eq);
+          __syncthreads();
+          have = sh->count;
+          if (gt + eq < need) {  // pivot class fully in, continue below the pivot
+            need -= gt + eq;
+            has_ub = true;
+            ub = piv;
+            continue;
           }
-        }
-        __syncthreads();
-        const int gt = sh->count, eq = sh->count2;
-        __syncthreads();
-        if (gt >= need) {  // the need-th best is above the pivot
-          has_lb = true;
-          lb = piv;
-          continue;
-        }
-        // everything above the pivot is in
-        if (tid == 0) sh->count = have;
-        __syncthreads();
-        const bool take_eq = gt + eq <= need || eq <= cap - have - gt;
-        for (int base = 0; base < nslots; base += nt) {
-          int slot = base + tid;
-          Entry e;
-          bool c = false;
-          if (slot < nslots && in_group(slot, e)) {
-            int c3 = src.cmp3(e, piv);
-            c = c3 > 0 || (c3 == 0 && take_eq);
+          if (take_eq) break;  // the class fitted as a whole; the final sort trims it
+          // ---- exact tie class larger than the list: take the (need - gt) smallest indices
+          const int need_idx = need - gt;
+          auto idxf = [&](int slot, u64& k) -> bool {
+            Entry e;
+            if (!in_group(slot, e) || src.cmp3(e, piv) != 0) return false;
+            k = (u64)(unsigned)(SENTINEL_IDX - e.idx);
+            return true;
+          };
+          refine_keys(idxf, nslots, need_idx, cap - have, 0ull, (u64)SENTINEL_IDX, 0, eq, hist, sh);
+          const u64 ilo = sh->lo;
+          if (tid == 0) sh->count = have;
+          __syncthreads();
+          for (int base = 0; base < nslots; base += nt) {
+            int slot = base + tid;
+            Entry e;
+            bool c = slot < nslots && in_group(slot, e) && src.cmp3(e, piv) == 0 &&
+                     (u64)(unsigned)(SENTINEL_IDX - e.idx) >= ilo;
+            append_entry(c, e, list, cap, &sh->count);
           }
-          append_entry(c, e, list, cap, &sh->count);
+          __syncthreads();
+          have = sh->count;
+          break;
         }
-        __syncthreads();
-        have = sh->count;
-        if (gt + eq < need) {  // pivot class fully in, continue below the pivot
-          need -= gt + eq;
-          has_ub = true;
-          ub = piv;
-          continue;
-        }
-        if (take_eq) break;  // the class fitted as a whole; the final sort trims it
-        // ---- exact tie class larger than the list: take the (need - gt) smallest indices
-        const int need_idx = need - gt;
-        auto idxf = [&](int slot, u64& k) -> bool {
-          Entry e;
-          if (!in_group(slot, e) || src.cmp3(e, piv) != 0) return false;
-          k = (u64)(unsigned)(SENTINEL_IDX - e.idx);
-          return true;
-        };
-        refine_keys(idxf, nslots, need_idx, cap - have, 0ull, (u64)SENTINEL_IDX, 0, eq, hist, sh);
-        const u64 ilo = sh->lo;
-        if (tid == 0) sh->count = have;
-        __syncthreads();
-        for (int base = 0; base < nslots; base += nt) {
-          int slot = base + tid;
-          Entry e;
-          bool c = slot < nslots && in_group(slot, e) && src.cmp3(e, piv) == 0 &&
-                   (u64)(unsigned)(SENTINEL_IDX - e.idx) >= ilo;
-          append_entry(c, e, list, cap, &sh->count);
-        }
-        __syncthreads();
-        have = sh->count;
-        break;
+        m = have < cap ? have : cap;
       }
-      m = have < cap ? have : cap;
     }
   }
   // ---- D: exact sort of the survivors
-  int n2 = 1;
-  while (n2 < m) n2 <<= 1;
-  if (n2 < 2) n2 = 2;
-  for (int i = m + tid; i < n2; i += nt) {
-    Entry s;
-    s.key = 0;
-    s.idx = SENTINEL_IDX;
-    s.aux = 0;
-    list[i] = s;
+  if (m > cap) m = cap;
+  if (m <= SEL_RANK_MAX) {
+    rank_sort_entries(src, list, list + cap, m);
+  } else {
+    int n2 = 1;
+    while (n2 < m) n2 <<= 1;
+    for (int i = m + tid; i < n2; i += nt) {
+      Entry s;
+      s.key = 0;
+      s.idx = SENTINEL_IDX;
+      s.aux = 0;
+      list[i] = s;
+    }
+    __syncthreads();
+    bitonic_sort_entries(src, list, n2);
   }
-  __syncthreads();
-  bitonic_sort_entries(src, list, n2);
   return m < K ? m : K;
 }
 
