@@ -70,6 +70,20 @@ __global__ void k_csc_prefix(const int64_t* __restrict__ cscptr, const int* __re
   }
 }
 
+// Largest popularity and (with pop_discount) the smallest item_pow among seen items: key bounds.
+__global__ void k_item_extremes(const int* __restrict__ n, const double* __restrict__ pw, int64_t I, int* __restrict__ nmax,
+                                u64* __restrict__ pwmin_bits) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int v = j < I ? n[j] : 0;
+  v = __reduce_max_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(nmax, v);
+  if (pw) {
+    u64 b = (j < I && n[j] > 0) ? (u64)__double_as_longlong(pw[j]) : ~0ull;  // positive doubles order like integers
+    b = warp_min_u64(b);
+    if ((threadIdx.x & 31) == 0) atomicMin(pwmin_bits, b);
+  }
+}
+
 __global__ void k_recip_f32(const int* __restrict__ n, float* __restrict__ rnf, int64_t I) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < I) rnf[j] = n[j] > 0 ? __frcp_rn((float)n[j]) : 0.f;
@@ -103,6 +117,8 @@ struct SimKey {
   const int* n;
   const float* rnf;
   const double* pw;
+  const int* nmax;      // largest item popularity (device scalar)
+  const double* pwmin;  // smallest item_pow among seen items (device scalar, mode 2)
   int mode;  // 0 cosine, 1 conditional probability, 2 conditional probability with pop_discount
 
   __device__ __forceinline__ u64 margin() const { return mode == 0 ? 32ull : 0ull; }
@@ -116,6 +132,32 @@ struct SimKey {
     }
     if (mode == 1) return (u64)__double_as_longlong((double)c);
     return (u64)__double_as_longlong(__dmul_rn((double)c, pw[j]));
+  }
+  // Every key of a row whose largest count is cmax lies in [lo, hi]  (rnf <= 1, item_pow <= 1).
+  __device__ __forceinline__ void bounds(int cmax, u64& lo, u64& hi) const {
+    if (mode == 0) {
+      const float a = (float)cmax;
+      hi = (u64)__float_as_uint(__fmul_rn(a, a));
+      lo = (u64)__float_as_uint(__frcp_rn((float)nmax[0]));
+    } else if (mode == 1) {
+      hi = (u64)__double_as_longlong((double)cmax);
+      lo = (u64)__double_as_longlong(1.0);
+    } else {
+      hi = (u64)__double_as_longlong((double)cmax);
+      lo = (u64)__double_as_longlong(pwmin[0]);
+    }
+  }
+  // Smallest count that can reach key thr (conservative): key <= c^2 (cosine) or key <= c.
+  __device__ __forceinline__ int min_count(u64 thr) const {
+    if (thr == 0) return 1;
+    if (mode == 0) {
+      const float t = __uint_as_float((unsigned)thr);
+      const int c = (int)sqrtf(t) - 1;
+      return c < 1 ? 1 : c;
+    }
+    const double t = __longlong_as_double((long long)thr);
+    const int c = t > 2.0e9 ? 2000000000 : (int)t - 1;
+    return c < 1 ? 1 : c;
   }
   __device__ __forceinline__ void entry(int c, int j, Entry& e) const {
     e.idx = j;
@@ -151,12 +193,58 @@ struct RowCountSrc {
   }
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return sk.margin(); }
+  int cmin;  // set_floor(): counts below this cannot reach the requested key
+  __device__ __forceinline__ void set_floor(u64 thr) { cmin = sk.min_count(thr); }
   __device__ __forceinline__ bool key(int slot, u64& k) const {
     const int c = count(slot);
     const int j = r0 + slot;
-    if (c == 0 || j == self) return false;
+    if (c < cmin || j == self) return false;
     k = sk.akey(c, j);
     return true;
+  }
+  // Integer-only pass over the packed counters: candidate count and the largest count; the key bounds
+  // follow from that (no popularity loads, no float math).
+  __device__ void stats(SelShared* sh) const {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    if (tid == 0) {
+      sh->count = 0;
+      sh->bstar = 0;
+    }
+    __syncthreads();
+    int cntc = 0, cmax = 0;
+    const int sslot = self - r0;
+    if (PACK16) {
+      const int nwords = (ns + 1) >> 1;
+      for (int w = tid; w < nwords; w += nt) {
+        const unsigned v = cnt[w];
+        int c0 = (int)(v & 0xffffu), c1 = (int)(v >> 16);
+        if (2 * w == sslot) c0 = 0;
+        if (2 * w + 1 == sslot) c1 = 0;
+        cntc += (c0 != 0) + (c1 != 0);
+        cmax = max(cmax, max(c0, c1));
+      }
+    } else {
+      for (int w = tid; w < ns; w += nt) {
+        int c0 = (int)cnt[w];
+        if (w == sslot) c0 = 0;
+        cntc += c0 != 0;
+        cmax = max(cmax, c0);
+      }
+    }
+    cntc = __reduce_add_sync(0xffffffffu, cntc);
+    cmax = __reduce_max_sync(0xffffffffu, cmax);
+    if (lane == 0 && cntc) {
+      atomicAdd(&sh->count, cntc);
+      atomicMax(&sh->bstar, cmax);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      u64 lo = 0, hi = 0;
+      if (sh->count) sk.bounds(sh->bstar, lo, hi);
+      sh->kmin = lo;
+      sh->kmax = hi;
+    }
+    __syncthreads();
   }
   __device__ __forceinline__ void entry(int slot, Entry& e) const { sk.entry(count(slot), r0 + slot, e); }
   __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const { return sk.cmp3(a, b); }
@@ -169,6 +257,8 @@ struct PairListSrc {  // (idx, cnt) pairs in global memory, idx < 0 = empty slot
   int ns;
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return sk.margin(); }
+  __device__ __forceinline__ void set_floor(u64) {}
+  __device__ __forceinline__ void stats(SelShared* sh) const { generic_stats(*this, sh); }
   __device__ __forceinline__ bool key(int slot, u64& k) const {
     const int j = idx[slot];
     if (j < 0) return false;
@@ -318,7 +408,7 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
     }
     __syncthreads();
     // ---- fused epilogue: similarity ordering, diagonal removal, top-K -- all on the shared-memory row
-    RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i};
+    RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i, 1};
     const int m = block_select_topk(src, p.K, list, p.cap, p.direct_cap, hist, sh);
     for (int t = tid; t < p.K; t += nt) {
       o_idx[t] = t < m ? list[t].idx : -1;
@@ -491,7 +581,13 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     k_csc_prefix<<<blocks, 256, 0, st>>>(cscptr, csc_users, indptr, I, pref);
     RPK_LAUNCH_CHECK(c);
   }
+  int* nmax = c->buf<int>("fit_nmax", 4);
+  u64* pwmin = reinterpret_cast<u64*>(c->buf<double>("fit_pwmin", 2));
+  RPK_CUDA(cudaMemsetAsync(nmax, 0, sizeof(int) * 4, st));
+  RPK_CUDA(cudaMemsetAsync(pwmin, 0xff, sizeof(u64), st));
   if (I > 0) {
+    k_item_extremes<<<ceil_div(I, 256), 256, 0, st>>>(n, pw, I, nmax, pwmin);
+    RPK_LAUNCH_CHECK(c);
     k_recip_f32<<<ceil_div(I, 256), 256, 0, st>>>(n, rnf, I);
     RPK_LAUNCH_CHECK(c);
   }
@@ -532,7 +628,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     const size_t fixed = sel_smem_bytes(cap);
     RPK_REQUIRE((size_t)c->smem_max > fixed + 1024 + 4096, "K too large for shared memory");
     const size_t avail = (size_t)c->smem_max - fixed - 1024;  // 1 KB slack for static shared memory
-    const SimKey sk{n, rnf, pw, mode};
+    const SimKey sk{n, rnf, pw, nmax, reinterpret_cast<const double*>(pwmin), mode};
 
     for (int wide = 0; wide < 2; ++wide) {
       // geometry: item-range passes so that the counters of one pass fit shared memory

@@ -25,6 +25,8 @@ struct CsrRowSrc {
   int ns;
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return 0ull; }
+  __device__ __forceinline__ void set_floor(u64) {}
+  __device__ __forceinline__ void stats(SelShared* sh) const { generic_stats(*this, sh); }
   __device__ __forceinline__ bool key(int slot, u64& k) const {
     double v = val[slot];
     if (v == 0.0) v = 0.0;  // -0.0 and +0.0 are the same score

@@ -11,6 +11,8 @@
 // (q & 0xFFFFF, q >> 20) with native shared-memory integer atomics (ATOMS.ADD); a 64-bit
 // compare-and-swap accumulator is the fallback when a limb could overflow.  Integer sums make the
 // result independent of the order in which the atomics land, so the top-N lists are deterministic.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 #include "prims.cuh"
@@ -234,6 +236,8 @@ struct ScoreSrc {
   }
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return 0ull; }
+  __device__ __forceinline__ void set_floor(u64) {}
+  __device__ __forceinline__ void stats(SelShared* sh) const { generic_stats(*this, sh); }
   __device__ __forceinline__ bool key(int slot, u64& k) const {
     const int j = touched ? touched[slot] : slot;
     k = score_at(j);
@@ -566,6 +570,10 @@ static PredGeom predict_geometry(rpk_ctx* c, int N) {
   g.tcap = (int)T;
   g.smem = g.fixed + (size_t)R * sizeof(u64) + (size_t)T * sizeof(int);
   g.nt = g.R >= 8192 ? 1024 : (g.R >= 2048 ? 512 : 256);
+  if (const char* e = getenv("RPK_PRED_NT")) {  // tuning hook
+    int v = atoi(e);
+    if (v >= 64 && v <= 1024 && v % 32 == 0) g.nt = v;
+  }
   return g;
 }
 

@@ -8,7 +8,9 @@
 //                          (larger = better) that is allowed to be approximate: it may mis-order two
 //                          candidates only if their akeys differ by at most Src::margin();
 //   void entry(slot, e)    the Entry (16 B) of a candidate slot, carrying what the exact comparator needs;
-//   int cmp3(a, b)         exact three-way comparison of two entries' keys (index excluded).
+//   int cmp3(a, b)         exact three-way comparison of two entries' keys (index excluded);
+//   void stats(sh)         candidate count and key bounds into sh (generic_stats, or something cheaper);
+//   void set_floor(thr)    hint: until the next call, key() may report slots whose key is below thr as empty.
 // Scans that only need the key (histograms, counts) never build entries.
 //
 // Algorithm (all control flow is block-uniform):
@@ -269,6 +271,47 @@ __device__ int compact_above(const Src& src, u64 thr, Entry* list, int cap, SelS
   return sh->count;
 }
 
+// Step A of the selection for sources without a cheaper way: count the candidates and find the
+// smallest / largest key.  Results in sh->count, sh->kmin, sh->kmax (block-wide, after a barrier).
+template <class Src>
+__device__ void generic_stats(const Src& src, SelShared* sh) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int nslots = src.nslots();
+  if (tid == 0) {
+    sh->count = 0;
+    sh->kmin = ~0ull;
+    sh->kmax = 0ull;
+  }
+  __syncthreads();
+  u64 lmin = ~0ull, lmax = 0ull;
+  int cnt = 0;
+  for (int base = 0; base < nslots; base += 4 * nt) {
+    u64 k[4];
+    bool c[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int slot = base + q * nt + tid;
+      c[q] = slot < nslots && src.key(slot, k[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (c[q]) {
+        cnt++;
+        lmin = k[q] < lmin ? k[q] : lmin;
+        lmax = k[q] > lmax ? k[q] : lmax;
+      }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  lmin = warp_min_u64(lmin);
+  lmax = warp_max_u64(lmax);
+  if (lane == 0 && cnt) {
+    atomicAdd(&sh->count, cnt);
+    atomicMin(&sh->kmin, lmin);
+    atomicMax(&sh->kmax, lmax);
+  }
+  __syncthreads();
+}
+
 constexpr int SEL_SAMPLE = 16;        // the threshold guess looks at one slot in 16
 constexpr int SEL_GUESS_MIN = 4096;   // below this many candidates the exact histogram is cheap enough
 
@@ -276,7 +319,7 @@ constexpr int SEL_GUESS_MIN = 4096;   // below this many candidates the exact hi
 // Requirements: blockDim.x multiple of 32; cap >= K, cap a power of two; direct_cap <= cap;
 // hist has SEL_BINS ints; list has cap entries (+ SEL_RANK_MAX spare entries behind them).
 template <class Src>
-__device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, int direct_cap, int* hist,
+__device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int direct_cap, int* hist,
                                  SelShared* sh) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   const int nslots = src.nslots();
@@ -285,42 +328,9 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
   if (direct_cap < K) direct_cap = K;  // the refinement needs at least K candidates
   if (direct_cap > cap) direct_cap = cap;
 
-  // ---- A: count candidates and bound their keys (register accumulation, one atomic per warp)
-  if (tid == 0) {
-    sh->count = 0;
-    sh->kmin = ~0ull;
-    sh->kmax = 0ull;
-  }
-  __syncthreads();
-  {
-    u64 lmin = ~0ull, lmax = 0ull;
-    int cnt = 0;
-    for (int base = 0; base < nslots; base += 4 * nt) {
-      u64 k[4];
-      bool c[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int slot = base + q * nt + tid;
-        c[q] = slot < nslots && src.key(slot, k[q]);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (c[q]) {
-          cnt++;
-          lmin = k[q] < lmin ? k[q] : lmin;
-          lmax = k[q] > lmax ? k[q] : lmax;
-        }
-    }
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
-    lmin = warp_min_u64(lmin);
-    lmax = warp_max_u64(lmax);
-    if (lane == 0 && cnt) {
-      atomicAdd(&sh->count, cnt);
-      atomicMin(&sh->kmin, lmin);
-      atomicMax(&sh->kmax, lmax);
-    }
-  }
-  __syncthreads();
+  // ---- A: count candidates and bound their keys
+  src.set_floor(0ull);
+  src.stats(sh);
   const int n_c = sh->count;
   const u64 kmin = sh->kmin, kmax = sh->kmax;
   __syncthreads();
@@ -354,7 +364,9 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
       const u64 edge = kmin + ((u64)sh->bstar << shift);
       const u64 thr = edge > M ? edge - M : 0;
       __syncthreads();
+      src.set_floor(thr);
       const int got = compact_above(src, thr, list, cap, sh);
+      src.set_floor(0ull);
       if (got >= K && got <= cap) m = got;
     }
     if (m < 0) {
@@ -364,6 +376,7 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
       int g = sh->g_new, n_in = sh->n_in;
       u64 thr = lo > M ? lo - M : 0;
       __syncthreads();
+      src.set_floor(thr);
       m = compact_above(src, thr, list, cap, sh);
       if (m > cap) {
         // ---- C: a band of (near-)equal keys is too large.  Pin tau = the K-th largest akey.
@@ -372,6 +385,7 @@ __device__ int block_select_topk(const Src& src, int K, Entry* list, int cap, in
         const u64 tau = sh->lo;
         const u64 band_lo = tau > M ? tau - M : 0;
         const u64 band_hi = tau + M < tau ? ~0ull : tau + M;
+        src.set_floor(band_lo);
         // certain members: akey above the band (fewer than K of them)
         if (tid == 0) sh->count = 0;
         __syncthreads();
