@@ -372,10 +372,17 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
             const int64_t bb = __shfl_sync(0xffffffffu, beg, l);
             const int s0 = lo > pfl ? (int)(lo - pfl) : 0;
             const int e1 = (int)min((unsigned)n, hi - pfl);
-            for (int e = s0 + lane; e < e1; e += 32) {
-              const int j = p.indices[bb + e] - r0;
-              if (PACK16) atomicAdd(&cnt[j >> 1], 1u << ((j & 1) * 16));
-              else atomicAdd(&cnt[j], 1u);
+            // four index loads in flight per lane, then the four counter updates
+            for (int e = s0 + lane; e < e1; e += 128) {
+              int jj[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) jj[q] = e + 32 * q < e1 ? p.indices[bb + e + 32 * q] - r0 : -1;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (jj[q] >= 0) {
+                  if (PACK16) atomicAdd(&cnt[jj[q] >> 1], 1u << ((jj[q] & 1) * 16));
+                  else atomicAdd(&cnt[jj[q]], 1u);
+                }
             }
           }
         }

@@ -359,37 +359,60 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
           beg = p.m_ptr[i] + s0;
           len = sg[1] - s0;
         }
-        for (int l = 0; l < nvalid; ++l) {
-          const int64_t b = __shfl_sync(0xffffffffu, beg, l);
-          const int n = __shfl_sync(0xffffffffu, len, l);
-          for (int e0 = 0; e0 < n; e0 += 32) {
-            const int e = e0 + lane;
-            bool first = false;
-            int j = 0;
-            if (e < n) {
-              const u64 ent = p.m_ent[b + e];
-              j = (int)(ent >> 40) - r0;
-              const u64 q = ent & Q_MASK40;
-              if (wide) {
-                atomicAdd(&acc64[j], q);
-              } else {
-                const unsigned old = atomicAdd(&acc_lo[j], (unsigned)q & LIMB_MASK);
-                atomicAdd(&acc_hi[j], (unsigned)(q >> LIMB_BITS));
-                first = old == 0u;
+        // add one entry to the accumulators; in sparse mode record the slot on its first touch
+        auto add_entry = [&](u64 ent) {
+          bool first = false;
+          int j = 0;
+          if (ent != 0ull) {
+            j = (int)(ent >> 40) - r0;
+            const u64 q = ent & Q_MASK40;
+            if (wide) {
+              atomicAdd(&acc64[j], q);
+            } else {
+              const unsigned old = atomicAdd(&acc_lo[j], (unsigned)q & LIMB_MASK);
+              atomicAdd(&acc_hi[j], (unsigned)(q >> LIMB_BITS));
+              first = old == 0u;
+            }
+          }
+          if (track) {
+            const unsigned m = __ballot_sync(0xffffffffu, first);
+            if (m) {
+              const int leader = __ffs(m) - 1;
+              int pos = 0;
+              if (lane == leader) pos = atomicAdd(&s_ntouched, __popc(m));
+              pos = __shfl_sync(0xffffffffu, pos, leader);
+              if (first) {
+                const int my = pos + __popc(m & ((1u << lane) - 1u));
+                if (my < p.tcap) touched[my] = j;
               }
             }
-            if (track) {
-              const unsigned m = __ballot_sync(0xffffffffu, first);
-              if (m) {
-                const int leader = __ffs(m) - 1;
-                int pos = 0;
-                if (lane == leader) pos = atomicAdd(&s_ntouched, __popc(m));
-                pos = __shfl_sync(0xffffffffu, pos, leader);
-                if (first) {
-                  const int my = pos + __popc(m & ((1u << lane) - 1u));
-                  if (my < p.tcap) touched[my] = j;
-                }
-              }
+          }
+        };
+        // rows are taken four at a time: the first 96 entries of each (a row segment rarely has more) are
+        // loaded up front -- 12 independent loads in flight per lane -- and only then added
+        for (int l0 = 0; l0 < nvalid; l0 += 4) {
+          u64 ent[4][3];
+          int64_t bq[4];
+          int nq[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int l = l0 + q;  // lanes >= nvalid hold len = 0
+            bq[q] = __shfl_sync(0xffffffffu, beg, l & 31);
+            nq[q] = l < nvalid ? __shfl_sync(0xffffffffu, len, l & 31) : 0;
+#pragma unroll
+            for (int it = 0; it < 3; ++it) {
+              const int e = it * 32 + lane;
+              ent[q][it] = e < nq[q] ? p.m_ent[bq[q] + e] : 0ull;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int it = 0; it < 3; ++it)
+              if (it * 32 < nq[q]) add_entry(ent[q][it]);
+            for (int e0 = 96; e0 < nq[q]; e0 += 32) {
+              const int e = e0 + lane;
+              add_entry(e < nq[q] ? p.m_ent[bq[q] + e] : 0ull);
             }
           }
         }

@@ -126,16 +126,32 @@ __device__ void bitonic_sort_entries(const Src& src, Entry* list, int n_pow2) {
   }
 }
 
-// Small lists: rank every element by counting the elements that precede it (one pass, two barriers).
-// `tmp` must hold m entries and may not alias `list`.
+// Small lists (m <= SEL_RANK_MAX = 64): rank every element by counting the elements that precede it.
+// 16 threads share one element (4 comparisons each, combined by shuffles), so the whole list is ranked
+// in one short step by the first 16*m threads.  `tmp` must hold m entries and may not alias `list`.
 template <class Src>
 __device__ void rank_sort_entries(const Src& src, Entry* list, Entry* tmp, int m) {
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < m; i += nt) {
-    const Entry a = list[i];
+  if (nt >= 16 * SEL_RANK_MAX) {
+    const int i = tid >> 4, part = tid & 15;
     int rank = 0;
-    for (int f = 0; f < m; ++f) rank += (f != i) && entry_before(src, list[f], a);
-    tmp[rank] = a;
+    Entry a;
+    if (i < m) {
+      a = list[i];
+      for (int f = part; f < m; f += 16) rank += (f != i) && entry_before(src, list[f], a);
+    }
+    rank += __shfl_xor_sync(0xffffffffu, rank, 8);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+    rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+    if (i < m && part == 0) tmp[rank] = a;
+  } else {
+    for (int i = tid; i < m; i += nt) {
+      const Entry a = list[i];
+      int rank = 0;
+      for (int f = 0; f < m; ++f) rank += (f != i) && entry_before(src, list[f], a);
+      tmp[rank] = a;
+    }
   }
   __syncthreads();
   for (int i = tid; i < m; i += nt) list[i] = tmp[i];
