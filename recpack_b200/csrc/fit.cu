@@ -195,12 +195,34 @@ struct RowCountSrc {
   __device__ __forceinline__ u64 margin() const { return sk.margin(); }
   int cmin;  // set_floor(): counts below this cannot reach the requested key
   __device__ __forceinline__ void set_floor(u64 thr) { cmin = sk.min_count(thr); }
-  __device__ __forceinline__ bool key(int slot, u64& k) const {
-    const int c = count(slot);
-    const int j = r0 + slot;
-    if (c < cmin || j == self) return false;
-    k = sk.akey(c, j);
-    return true;
+  // Visit every candidate whose count reaches the floor.  Words of two packed counters are skipped as a
+  // whole when empty, which is what makes sparse rows cheap.
+  template <class F>
+  __device__ __forceinline__ void visit(F f, int wstride, bool low_half_only) const {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (PACK16) {
+      const int nwords = (ns + 1) >> 1;
+      for (int w = tid * wstride; w < nwords; w += nt * wstride) {
+        const unsigned v = cnt[w];
+        if (v == 0u) continue;
+        const int c0 = (int)(v & 0xffffu), c1 = (int)(v >> 16);
+        const int j0 = r0 + 2 * w;
+        if (c0 >= cmin && j0 != self) f(2 * w, sk.akey(c0, j0));
+        if (!low_half_only && c1 >= cmin && j0 + 1 != self) f(2 * w + 1, sk.akey(c1, j0 + 1));
+      }
+    } else {
+      for (int w = tid * wstride; w < ns; w += nt * wstride) {
+        const int c0 = (int)cnt[w];
+        if (c0 >= cmin && r0 + w != self) f(w, sk.akey(c0, r0 + w));
+      }
+    }
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each(F f) const { visit(f, 1, false); }
+  template <class F>
+  __device__ __forceinline__ void for_each_sampled(F f) const {
+    if (PACK16) visit(f, SEL_SAMPLE / 2, true);  // the low counter of every 8th word = 1 slot in 16
+    else visit(f, SEL_SAMPLE, false);
   }
   // Integer-only pass over the packed counters: candidate count and the largest count; the key bounds
   // follow from that (no popularity loads, no float math).
@@ -259,12 +281,17 @@ struct PairListSrc {  // (idx, cnt) pairs in global memory, idx < 0 = empty slot
   __device__ __forceinline__ u64 margin() const { return sk.margin(); }
   __device__ __forceinline__ void set_floor(u64) {}
   __device__ __forceinline__ void stats(SelShared* sh) const { generic_stats(*this, sh); }
-  __device__ __forceinline__ bool key(int slot, u64& k) const {
-    const int j = idx[slot];
-    if (j < 0) return false;
-    k = sk.akey(cnt[slot], j);
-    return true;
+  template <class F>
+  __device__ __forceinline__ void visit(F f, int stride) const {
+    for (int slot = threadIdx.x * stride; slot < ns; slot += blockDim.x * stride) {
+      const int j = idx[slot];
+      if (j >= 0) f(slot, sk.akey(cnt[slot], j));
+    }
   }
+  template <class F>
+  __device__ __forceinline__ void for_each(F f) const { visit(f, 1); }
+  template <class F>
+  __device__ __forceinline__ void for_each_sampled(F f) const { visit(f, SEL_SAMPLE); }
   __device__ __forceinline__ void entry(int slot, Entry& e) const { sk.entry(cnt[slot], idx[slot], e); }
   __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const { return sk.cmp3(a, b); }
 };

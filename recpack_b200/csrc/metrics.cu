@@ -27,16 +27,22 @@ struct CsrRowSrc {
   __device__ __forceinline__ u64 margin() const { return 0ull; }
   __device__ __forceinline__ void set_floor(u64) {}
   __device__ __forceinline__ void stats(SelShared* sh) const { generic_stats(*this, sh); }
-  __device__ __forceinline__ bool key(int slot, u64& k) const {
+  __device__ __forceinline__ u64 key_at(int slot) const {
     double v = val[slot];
     if (v == 0.0) v = 0.0;  // -0.0 and +0.0 are the same score
-    k = ordered_bits(v);
-    return true;  // every stored entry is ranked, explicit zeros included (util.py:63-73)
+    return ordered_bits(v);
   }
+  // every stored entry is ranked, explicit zeros included (util.py:63-73)
+  template <class F>
+  __device__ __forceinline__ void visit(F f, int stride) const {
+    for (int slot = threadIdx.x * stride; slot < ns; slot += blockDim.x * stride) f(slot, key_at(slot));
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each(F f) const { visit(f, 1); }
+  template <class F>
+  __device__ __forceinline__ void for_each_sampled(F f) const { visit(f, SEL_SAMPLE); }
   __device__ __forceinline__ void entry(int slot, Entry& e) const {
-    u64 k;
-    key(slot, k);
-    e.key = k;
+    e.key = key_at(slot);
     e.idx = idx[slot];
     e.aux = 0;
   }

@@ -231,18 +231,26 @@ struct ScoreSrc {
   const u64* wide;     // non-null: 64-bit accumulators
   const int* touched;  // non-null: slot list (sparse mode)
   int r0, ns;
+  u64 floor_;
   __device__ __forceinline__ u64 score_at(int j) const {
     return wide ? wide[j] : (((u64)hi[j] << LIMB_BITS) + (u64)lo[j]);
   }
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return 0ull; }
-  __device__ __forceinline__ void set_floor(u64) {}
+  __device__ __forceinline__ void set_floor(u64 thr) { floor_ = thr; }
   __device__ __forceinline__ void stats(SelShared* sh) const { generic_stats(*this, sh); }
-  __device__ __forceinline__ bool key(int slot, u64& k) const {
-    const int j = touched ? touched[slot] : slot;
-    k = score_at(j);
-    return k != 0;
+  template <class F>
+  __device__ __forceinline__ void visit(F f, int stride) const {
+    for (int slot = threadIdx.x * stride; slot < ns; slot += blockDim.x * stride) {
+      const int j = touched ? touched[slot] : slot;
+      const u64 k = score_at(j);
+      if (k != 0 && k >= floor_) f(slot, k);
+    }
   }
+  template <class F>
+  __device__ __forceinline__ void for_each(F f) const { visit(f, 1); }
+  template <class F>
+  __device__ __forceinline__ void for_each_sampled(F f) const { visit(f, SEL_SAMPLE); }
   __device__ __forceinline__ void entry(int slot, Entry& e) const {
     const int j = touched ? touched[slot] : slot;
     e.key = score_at(j);
@@ -442,7 +450,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       }
       __syncthreads();
     }
-    ScoreSrc src{acc_lo, acc_hi, wide ? acc64 : nullptr, sparse ? touched : nullptr, r0, sparse ? n_touched : ns};
+    ScoreSrc src{acc_lo, acc_hi, wide ? acc64 : nullptr, sparse ? touched : nullptr, r0, sparse ? n_touched : ns, 0ull};
     if (p.mode == PRED_TOPN) {
       const int m = block_select_topk(src, p.N, list, p.cap, p.direct_cap, hist, sh);
       for (int t = tid; t < p.N; t += nt) {

@@ -3,25 +3,27 @@
 // recpack/util.py:50-77 (get_top_K_ranks) with a deterministic rule: best key first, ties by
 // ascending index.
 //
-// A "source" enumerates candidate slots:
-//   bool key(slot, akey)   false when the slot holds no candidate; otherwise a 64-bit SORTABLE key
-//                          (larger = better) that is allowed to be approximate: it may mis-order two
-//                          candidates only if their akeys differ by at most Src::margin();
-//   void entry(slot, e)    the Entry (16 B) of a candidate slot, carrying what the exact comparator needs;
-//   int cmp3(a, b)         exact three-way comparison of two entries' keys (index excluded);
-//   void stats(sh)         candidate count and key bounds into sh (generic_stats, or something cheaper);
-//   void set_floor(thr)    hint: until the next call, key() may report slots whose key is below thr as empty.
-// Scans that only need the key (histograms, counts) never build entries.
+// A "source" owns the candidate slots and drives the iteration over them:
+//   for_each(f)            calls f(slot, akey) for every candidate slot (any thread, any order; each
+//                          candidate exactly once per block).  akey is a 64-bit SORTABLE key (larger =
+//                          better) that may be approximate: it may mis-order two candidates only if
+//                          their akeys differ by at most margin();
+//   for_each_sampled(f)    the same for roughly one candidate in SEL_SAMPLE (a fixed subset);
+//   set_floor(thr)         hint: until the next call the iteration may skip candidates with akey < thr;
+//   stats(sh)              candidate count and key bounds into sh->count / kmin / kmax;
+//   void entry(slot, e)    the Entry (16 B) of a candidate slot, carrying what cmp3 needs;
+//   int cmp3(a, b)         exact three-way comparison of two entries' keys (index excluded).
 //
 // Algorithm (all control flow is block-uniform):
-//   A. one scan: count candidates, min/max akey, and copy them to `list` while they fit.
-//      If they all fit -> sort, done.
-//   B. radix refinement on akey: 4096-bin histogram over [lo, hi], descend into the bin that
-//      holds the K-th largest akey until the candidates with akey >= lo (minus margin) fit.
-//   C. if they never fit (a huge group of equal / near-equal akeys straddles the K-th place):
-//      exact quick-select inside that band with cmp3, and inside an exactly-tied class a second
-//      radix refinement on the index picks the smallest indices.
-//   D. bitonic sort of the (<= cap) survivors with the exact total order; the first K are the result.
+//   A. stats.  Few candidates -> copy them all, sort, done.
+//   B0. many candidates: guess a threshold from a 1-in-16 sample; accept it when it leaves between
+//       K and cap survivors (verified by the copy itself).
+//   B. otherwise radix refinement on akey: 4096-bin histograms over [lo, hi], descending into the bin
+//      that holds the K-th largest akey until the candidates with akey >= lo (minus margin) fit.
+//   C. if they never fit (a huge group of equal / near-equal akeys straddles the K-th place): exact
+//      quick-select inside that band with cmp3, and inside an exactly-tied class a second radix
+//      refinement on the index picks the smallest indices.
+//   D. exact sort of the (<= cap) survivors; the first K are the result.
 #pragma once
 #include <stdint.h>
 
@@ -37,7 +39,9 @@ struct __align__(16) Entry {
 
 constexpr int SEL_BINS = 4096;
 constexpr int SENTINEL_IDX = 0x7fffffff;
-constexpr int SEL_RANK_MAX = 64;  // up to this many survivors: rank by counting instead of bitonic
+constexpr int SEL_RANK_MAX = 64;     // up to this many survivors: rank by counting instead of bitonic
+constexpr int SEL_SAMPLE = 16;       // the threshold guess looks at one slot in 16
+constexpr int SEL_GUESS_MIN = 4096;  // below this many candidates the exact histogram is cheap enough
 
 struct SelShared {
   u64 kmin, kmax;
@@ -75,20 +79,11 @@ __device__ __forceinline__ u64 warp_max_u64(u64 v) {
   return v;
 }
 
-// Warp-aggregated append of `e` (when `take`) to list; returns nothing, counts every taker in
-// *counter even when the list is full (entries beyond `cap` are dropped, the count tells).
-__device__ __forceinline__ void append_entry(bool take, const Entry& e, Entry* list, int cap, int* counter) {
-  unsigned m = __ballot_sync(0xffffffffu, take);
-  if (m == 0) return;
-  int lane = threadIdx.x & 31;
-  int leader = __ffs(m) - 1;
-  int pos = 0;
-  if (lane == leader) pos = atomicAdd(counter, __popc(m));
-  pos = __shfl_sync(0xffffffffu, pos, leader);
-  if (take) {
-    int my = pos + __popc(m & ((1u << lane) - 1u));
-    if (my < cap) list[my] = e;
-  }
+// Append one survivor (callable from divergent code; survivors are few, so one atomic each is fine).
+// Every caller is counted, entries beyond `cap` are dropped -- the count tells.
+__device__ __forceinline__ void append_one(const Entry& e, Entry* list, int cap, int* counter) {
+  const int pos = atomicAdd(counter, 1);
+  if (pos < cap) list[pos] = e;
 }
 
 // Exact total order used by the final sort: true when a must precede b.
@@ -212,33 +207,58 @@ __device__ __forceinline__ void find_boundary_bin(const int* hist, int nb, int g
   __syncthreads();
 }
 
-// One refinement run.  `f(slot, key)` returns true when the slot belongs to the group being
-// refined and sets its key.  On entry [lo, hi] bounds the group's keys, n_in = group size,
-// g = number of group members already known to be above hi (0 at the start).
-// Descends while  g + n_in > room  and  lo < hi.  Results in sh->lo / sh->hi / sh->g_new / sh->n_in.
-template <class F>
-__device__ void refine_keys(F f, int nslots, int need, int room, u64 lo, u64 hi, int g, int n_in, int* hist,
-                            SelShared* sh) {
+// Histogram geometry for keys in [lo, hi]: at most SEL_BINS bins of 2^shift consecutive keys.
+__device__ __forceinline__ void bin_geometry(u64 lo, u64 hi, int& shift, int& nb) {
+  const u64 range = hi - lo;
+  const int bits = range ? 64 - __clzll((long long)range) : 0;
+  shift = bits > 12 ? bits - 12 : 0;
+  nb = (int)(range >> shift) + 1;
+}
+
+// Step A for sources without a cheaper way: candidate count and smallest / largest key.
+template <class Src>
+__device__ void generic_stats(const Src& src, SelShared* sh) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (tid == 0) {
+    sh->count = 0;
+    sh->kmin = ~0ull;
+    sh->kmax = 0ull;
+  }
+  __syncthreads();
+  u64 lmin = ~0ull, lmax = 0ull;
+  int cnt = 0;
+  src.for_each([&](int, u64 k) {
+    cnt++;
+    lmin = k < lmin ? k : lmin;
+    lmax = k > lmax ? k : lmax;
+  });
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  lmin = warp_min_u64(lmin);
+  lmax = warp_max_u64(lmax);
+  if (lane == 0 && cnt) {
+    atomicAdd(&sh->count, cnt);
+    atomicMin(&sh->kmin, lmin);
+    atomicMax(&sh->kmax, lmax);
+  }
+  __syncthreads();
+}
+
+// One refinement run over the candidates of `src`.  On entry [lo, hi] bounds the keys of interest,
+// n_in = candidates inside, g = candidates known to be above hi.  Descends while g + n_in > room and
+// lo < hi.  Results in sh->lo / sh->hi / sh->g_new / sh->n_in.
+template <class Src>
+__device__ void refine_keys(Src& src, int need, int room, u64 lo, u64 hi, int g, int n_in, int* hist, SelShared* sh) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  const u64 M = src.margin();
   while (g + n_in > room && lo < hi) {
-    const u64 range = hi - lo;
-    const int bits = 64 - __clzll((long long)range);
-    const int shift = bits > 12 ? bits - 12 : 0;
-    const int nb = (int)(range >> shift) + 1;
+    int shift, nb;
+    bin_geometry(lo, hi, shift, nb);
     for (int b = tid; b < nb; b += nt) hist[b] = 0;
+    src.set_floor(lo > M ? lo - M : 0ull);
     __syncthreads();
-    for (int base = 0; base < nslots; base += 4 * nt) {
-      u64 k[4];
-      bool c[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int slot = base + q * nt + tid;
-        c[q] = slot < nslots && f(slot, k[q]) && k[q] >= lo && k[q] <= hi;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (c[q]) atomicAdd(&hist[(int)((k[q] - lo) >> shift)], 1);
-    }
+    src.for_each([&](int, u64 k) {
+      if (k >= lo && k <= hi) atomicAdd(&hist[(int)((k - lo) >> shift)], 1);
+    });
     __syncthreads();
     find_boundary_bin(hist, nb, g, need, sh);
     const int bstar = sh->bstar;
@@ -261,84 +281,29 @@ __device__ void refine_keys(F f, int nslots, int need, int room, u64 lo, u64 hi,
   __syncthreads();
 }
 
-// Appends every candidate with key >= thr to list (4 slots per thread in flight); returns the count.
+// Copies every candidate with key >= thr to list; returns how many there were (may exceed cap).
 template <class Src>
-__device__ int compact_above(const Src& src, u64 thr, Entry* list, int cap, SelShared* sh) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int nslots = src.nslots();
-  if (tid == 0) sh->count = 0;
+__device__ int compact_above(Src& src, u64 thr, Entry* list, int cap, SelShared* sh) {
+  if (threadIdx.x == 0) sh->count = 0;
+  src.set_floor(thr);
   __syncthreads();
-  for (int base = 0; base < nslots; base += 4 * nt) {
-    u64 k[4];
-    bool c[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int slot = base + q * nt + tid;
-      c[q] = slot < nslots && src.key(slot, k[q]) && k[q] >= thr;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
+  src.for_each([&](int slot, u64 k) {
+    if (k >= thr) {
       Entry e;
-      if (c[q]) src.entry(base + q * nt + tid, e);
-      append_entry(c[q], e, list, cap, &sh->count);
+      src.entry(slot, e);
+      append_one(e, list, cap, &sh->count);
     }
-  }
+  });
   __syncthreads();
   return sh->count;
 }
 
-// Step A of the selection for sources without a cheaper way: count the candidates and find the
-// smallest / largest key.  Results in sh->count, sh->kmin, sh->kmax (block-wide, after a barrier).
-template <class Src>
-__device__ void generic_stats(const Src& src, SelShared* sh) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-  const int nslots = src.nslots();
-  if (tid == 0) {
-    sh->count = 0;
-    sh->kmin = ~0ull;
-    sh->kmax = 0ull;
-  }
-  __syncthreads();
-  u64 lmin = ~0ull, lmax = 0ull;
-  int cnt = 0;
-  for (int base = 0; base < nslots; base += 4 * nt) {
-    u64 k[4];
-    bool c[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int slot = base + q * nt + tid;
-      c[q] = slot < nslots && src.key(slot, k[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (c[q]) {
-        cnt++;
-        lmin = k[q] < lmin ? k[q] : lmin;
-        lmax = k[q] > lmax ? k[q] : lmax;
-      }
-  }
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
-  lmin = warp_min_u64(lmin);
-  lmax = warp_max_u64(lmax);
-  if (lane == 0 && cnt) {
-    atomicAdd(&sh->count, cnt);
-    atomicMin(&sh->kmin, lmin);
-    atomicMax(&sh->kmax, lmax);
-  }
-  __syncthreads();
-}
-
-constexpr int SEL_SAMPLE = 16;        // the threshold guess looks at one slot in 16
-constexpr int SEL_GUESS_MIN = 4096;   // below this many candidates the exact histogram is cheap enough
-
 // Returns m = number of selected entries (<= K); list[0..m) holds them best-first.
 // Requirements: blockDim.x multiple of 32; cap >= K, cap a power of two; direct_cap <= cap;
-// hist has SEL_BINS ints; list has cap entries (+ SEL_RANK_MAX spare entries behind them).
+// hist has SEL_BINS ints; list has cap + SEL_RANK_MAX entries.
 template <class Src>
-__device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int direct_cap, int* hist,
-                                 SelShared* sh) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
-  const int nslots = src.nslots();
+__device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int direct_cap, int* hist, SelShared* sh) {
+  const int tid = threadIdx.x, nt = blockDim.x;
   const u64 M = src.margin();
   if (K > cap) K = cap;
   if (direct_cap < K) direct_cap = K;  // the refinement needs at least K candidates
@@ -354,24 +319,19 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
   if (n_c <= direct_cap) {
     m = compact_above(src, 0ull, list, cap, sh);
   } else {
-    auto keyf = [&](int slot, u64& k) -> bool { return src.key(slot, k); };
     // keep the survivor list (and the final sort) close to K
     int room = K + (K / 4 > 32 ? K / 4 : 32);
     if (room > cap) room = cap;
-    // ---- B0: cheap threshold guess from a 1-in-16 sample of the slots; accepted when it leaves
-    //          between K and cap candidates, which is then verified by the compaction itself
+    // ---- B0: cheap threshold guess from a 1-in-16 sample; accepted when it leaves between K and cap
+    //          candidates, which the copy itself verifies
     if (n_c >= SEL_GUESS_MIN && kmax > kmin) {
-      const u64 range = kmax - kmin;
-      const int bits = 64 - __clzll((long long)range);
-      const int shift = bits > 12 ? bits - 12 : 0;
-      const int nb = (int)(range >> shift) + 1;
+      int shift, nb;
+      bin_geometry(kmin, kmax, shift, nb);
       for (int b = tid; b < nb; b += nt) hist[b] = 0;
       __syncthreads();
-      for (int t = tid; t * SEL_SAMPLE < nslots; t += nt) {
-        const int slot = t * SEL_SAMPLE + (SEL_SAMPLE / 2 < nslots - t * SEL_SAMPLE ? SEL_SAMPLE / 2 : 0);
-        u64 k;
-        if (src.key(slot, k)) atomicAdd(&hist[(int)((k - kmin) >> shift)], 1);
-      }
+      src.for_each_sampled([&](int, u64 k) {
+        if (k >= kmin && k <= kmax) atomicAdd(&hist[(int)((k - kmin) >> shift)], 1);
+      });
       __syncthreads();
       const int ks = (K + SEL_SAMPLE - 1) / SEL_SAMPLE;
       int sd = 1;
@@ -380,24 +340,21 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
       const u64 edge = kmin + ((u64)sh->bstar << shift);
       const u64 thr = edge > M ? edge - M : 0;
       __syncthreads();
-      src.set_floor(thr);
       const int got = compact_above(src, thr, list, cap, sh);
-      src.set_floor(0ull);
       if (got >= K && got <= cap) m = got;
     }
     if (m < 0) {
       // ---- B: exact radix refinement on the (approximate) key until the survivors fit
-      refine_keys(keyf, nslots, K, room, kmin, kmax, 0, n_c, hist, sh);
+      refine_keys(src, K, room, kmin, kmax, 0, n_c, hist, sh);
       u64 lo = sh->lo, hi = sh->hi;
       int g = sh->g_new, n_in = sh->n_in;
       u64 thr = lo > M ? lo - M : 0;
       __syncthreads();
-      src.set_floor(thr);
       m = compact_above(src, thr, list, cap, sh);
       if (m > cap) {
         // ---- C: a band of (near-)equal keys is too large.  Pin tau = the K-th largest akey.
         __syncthreads();
-        refine_keys(keyf, nslots, K, -1, lo, hi, g, n_in, hist, sh);
+        refine_keys(src, K, -1, lo, hi, g, n_in, hist, sh);
         const u64 tau = sh->lo;
         const u64 band_lo = tau > M ? tau - M : 0;
         const u64 band_hi = tau + M < tau ? ~0ull : tau + M;
@@ -405,23 +362,21 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
         // certain members: akey above the band (fewer than K of them)
         if (tid == 0) sh->count = 0;
         __syncthreads();
-        for (int base = 0; base < nslots; base += nt) {
-          int slot = base + tid;
-          Entry e;
-          u64 k = 0;
-          bool c = slot < nslots && src.key(slot, k) && k > band_hi;
-          if (c) src.entry(slot, e);
-          append_entry(c, e, list, cap, &sh->count);
-        }
+        src.for_each([&](int slot, u64 k) {
+          if (k > band_hi) {
+            Entry e;
+            src.entry(slot, e);
+            append_one(e, list, cap, &sh->count);
+          }
+        });
         __syncthreads();
         int have = sh->count;  // entries in list so far (all certain)
         int need = K - have;   // still to take from the band, by exact order
         bool has_lb = false, has_ub = false;
         Entry lb = {0, 0, 0}, ub = {0, 0, 0};
         // group = band members with exact key strictly between lb and ub
-        auto in_group = [&](int slot, Entry& e) -> bool {
-          u64 k;
-          if (!src.key(slot, k) || k < band_lo || k > band_hi) return false;
+        auto in_group = [&](int slot, u64 k, Entry& e) -> bool {
+          if (k < band_lo || k > band_hi) return false;
           src.entry(slot, e);
           if (has_ub && src.cmp3(e, ub) >= 0) return false;
           if (has_lb && src.cmp3(e, lb) <= 0) return false;
@@ -433,11 +388,10 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
           __syncthreads();
           {
             int best = 0x7fffffff;
-            for (int base = 0; base < nslots && best == 0x7fffffff; base += nt) {
-              int slot = base + tid;
+            src.for_each([&](int slot, u64 k) {
               Entry e;
-              if (slot < nslots && in_group(slot, e)) best = slot;
-            }
+              if (slot < best && in_group(slot, k, e)) best = slot;
+            });
             if (best != 0x7fffffff) atomicMin(&sh->piv_slot, best);
           }
           __syncthreads();
@@ -454,18 +408,17 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
           const Entry piv = sh->piv;
           {
             int gt = 0, eq = 0;
-            for (int base = 0; base < nslots; base += nt) {
-              int slot = base + tid;
+            src.for_each([&](int slot, u64 k) {
               Entry e;
-              if (slot < nslots && in_group(slot, e)) {
+              if (in_group(slot, k, e)) {
                 int c = src.cmp3(e, piv);
                 gt += c > 0;
                 eq += c == 0;
               }
-            }
+            });
             gt = __reduce_add_sync(0xffffffffu, gt);
             eq = __reduce_add_sync(0xffffffffu, eq);
-            if (lane == 0) {
+            if ((tid & 31) == 0) {
               if (gt) atomicAdd(&sh->count, gt);
               if (eq) atomicAdd(&sh->count2, eq);
             }
@@ -482,16 +435,13 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
           if (tid == 0) sh->count = have;
           __syncthreads();
           const bool take_eq = gt + eq <= need || eq <= cap - have - gt;
-          for (int base = 0; base < nslots; base += nt) {
-            int slot = base + tid;
+          src.for_each([&](int slot, u64 k) {
             Entry e;
-            bool c = false;
-            if (slot < nslots && in_group(slot, e)) {
+            if (in_group(slot, k, e)) {
               int c3 = src.cmp3(e, piv);
-              c = c3 > 0 || (c3 == 0 && take_eq);
+              if (c3 > 0 || (c3 == 0 && take_eq)) append_one(e, list, cap, &sh->count);
             }
-            append_entry(c, e, list, cap, &sh->count);
-          }
+          });
           __syncthreads();
           have = sh->count;
           if (gt + eq < need) {  // pivot class fully in, continue below the pivot
@@ -501,25 +451,43 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
             continue;
           }
           if (take_eq) break;  // the class fitted as a whole; the final sort trims it
-          // ---- exact tie class larger than the list: take the (need - gt) smallest indices
+          // ---- exact tie class larger than the list: take the (need - gt) smallest indices by a radix
+          //      refinement on the index
           const int need_idx = need - gt;
-          auto idxf = [&](int slot, u64& k) -> bool {
-            Entry e;
-            if (!in_group(slot, e) || src.cmp3(e, piv) != 0) return false;
-            k = (u64)(unsigned)(SENTINEL_IDX - e.idx);
-            return true;
-          };
-          refine_keys(idxf, nslots, need_idx, cap - have, 0ull, (u64)SENTINEL_IDX, 0, eq, hist, sh);
-          const u64 ilo = sh->lo;
+          u64 ilo = 0, ihi = (u64)SENTINEL_IDX;
+          int ig = 0, iin = eq;
+          const int iroom = cap - have;
+          while (ig + iin > iroom && ilo < ihi) {
+            int shift, nb;
+            bin_geometry(ilo, ihi, shift, nb);
+            for (int b = tid; b < nb; b += nt) hist[b] = 0;
+            __syncthreads();
+            src.for_each([&](int slot, u64 k) {
+              Entry e;
+              if (in_group(slot, k, e) && src.cmp3(e, piv) == 0) {
+                const u64 ik = (u64)(unsigned)(SENTINEL_IDX - e.idx);
+                if (ik >= ilo && ik <= ihi) atomicAdd(&hist[(int)((ik - ilo) >> shift)], 1);
+              }
+            });
+            __syncthreads();
+            find_boundary_bin(hist, nb, ig, need_idx, sh);
+            const int bstar = sh->bstar;
+            ig = sh->g_new;
+            iin = sh->n_in;
+            const u64 nlo = ilo + ((u64)bstar << shift);
+            u64 nhi = nlo + ((((u64)1) << shift) - 1);
+            if (nhi > ihi || nhi < nlo) nhi = ihi;
+            ilo = nlo;
+            ihi = nhi;
+            __syncthreads();
+          }
           if (tid == 0) sh->count = have;
           __syncthreads();
-          for (int base = 0; base < nslots; base += nt) {
-            int slot = base + tid;
+          src.for_each([&](int slot, u64 k) {
             Entry e;
-            bool c = slot < nslots && in_group(slot, e) && src.cmp3(e, piv) == 0 &&
-                     (u64)(unsigned)(SENTINEL_IDX - e.idx) >= ilo;
-            append_entry(c, e, list, cap, &sh->count);
-          }
+            if (in_group(slot, k, e) && src.cmp3(e, piv) == 0 && (u64)(unsigned)(SENTINEL_IDX - e.idx) >= ilo)
+              append_one(e, list, cap, &sh->count);
+          });
           __syncthreads();
           have = sh->count;
           break;
@@ -529,6 +497,7 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
     }
   }
   // ---- D: exact sort of the survivors
+  src.set_floor(0ull);
   if (m > cap) m = cap;
   if (m <= SEL_RANK_MAX) {
     rank_sort_entries(src, list, list + cap, m);
