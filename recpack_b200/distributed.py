@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing of the hot path: one process per GPU (torchrun), item rows sharded for fit,
+users sharded for scoring.  The only data-path exchange is one all-gather of the pruned similarity
+lists (I x K x 12 B in total) and one all-reduce of the metric sums; both go through
+torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(weights, parts: int):
+    """Cut points of `parts` contiguous shards with balanced total weight: cuts[r]..cuts[r+1]."""
+    w = np.asarray(weights, dtype=np.float64)
+    c = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [int(np.searchsorted(c, c[-1] * p / parts)) for p in range(parts + 1)]
+    cuts[0], cuts[-1] = 0, len(w)
+    for p in range(1, parts + 1):  # monotone even with zero weights
+        cuts[p] = max(cuts[p], cuts[p - 1])
+    return cuts
+
+
+def fit_work_per_item(X):
+    """Work of item row i in the sparse Gram: sum of the history lengths of its users (+ a constant
+    for the row's fixed cost)."""
+    d = np.diff(X.indptr).astype(np.float64)
+    return np.bincount(X.indices, weights=np.repeat(d, np.diff(X.indptr)), minlength=X.shape[1]) + 2000.0
+
+
+def score_work_per_user(X, K: int):
+    return np.diff(X.indptr).astype(np.float64) * K + 3.0 * X.shape[1] / 64
+
+
+class ShardExchange:
+    """Pre-allocated buffers for the all-gather of per-rank top-K lists into full [I, K] arrays."""
+
+    def __init__(self, cuts, K, device, dist):
+        import torch
+
+        self.cuts, self.K, self.dist = list(cuts), int(K), dist
+        self.world = len(cuts) - 1
+        self.rank = dist.get_rank()
+        self.maxrows = max(cuts[r + 1] - cuts[r] for r in range(self.world))
+        I = cuts[-1]
+        mk = lambda shape, dt, fill: torch.full(shape, fill, dtype=dt, device=device)
+        self.p_idx = mk((self.maxrows, K), torch.int32, -1)
+        self.p_val = mk((self.maxrows, K), torch.float64, 0)
+        self.p_len = mk((self.maxrows,), torch.int32, 0)
+        self.g_idx = mk((self.world, self.maxrows, K), torch.int32, -1)
+        self.g_val = mk((self.world, self.maxrows, K), torch.float64, 0)
+        self.g_len = mk((self.world, self.maxrows), torch.int32, 0)
+        self.all_idx = mk((I, K), torch.int32, -1)
+        self.all_val = mk((I, K), torch.float64, 0)
+        self.all_len = mk((I,), torch.int32, 0)
+
+    def gather(self, idx, val, ln):
+        """idx/val/ln: this rank's rows (cuts[rank]..cuts[rank+1]).  Returns the full arrays."""
+        rows = self.cuts[self.rank + 1] - self.cuts[self.rank]
+        self.p_idx[:rows].copy_(idx)
+        self.p_val[:rows].copy_(val)
+        self.p_len[:rows].copy_(ln)
+        # concatenated (2-D / 1-D) views: the layout both NCCL and gloo accept
+        self.dist.all_gather_into_tensor(self.g_idx.view(-1, self.K), self.p_idx)
+        self.dist.all_gather_into_tensor(self.g_val.view(-1, self.K), self.p_val)
+        self.dist.all_gather_into_tensor(self.g_len.view(-1), self.p_len)
+        for r in range(self.world):
+            b, e = self.cuts[r], self.cuts[r + 1]
+            self.all_idx[b:e].copy_(self.g_idx[r, : e - b])
+            self.all_val[b:e].copy_(self.g_val[r, : e - b])
+            self.all_len[b:e].copy_(self.g_len[r, : e - b])
+        return self.all_idx, self.all_val, self.all_len

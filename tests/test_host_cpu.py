@@ -1,0 +1,153 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, input coercion, constructor validation, the synthetic generator, and the multi-GPU
+plumbing on the gloo backend (world size 2)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "rpk.h")).read()
+    return sorted(set(re.findall(r"RPK_EXPORT\s+[\w\s\*]+?\b(rpk_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    from recpack_b200 import _lib
+
+    assert _header_symbols() == sorted(_lib.EXPORTED_SYMBOLS)
+
+
+def test_library_loads_and_exports_every_symbol():
+    from recpack_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+
+        __graft_entry__.build()
+    lib = _lib.load()
+    assert lib.rpk_abi_version() == 1
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _header_symbols():
+        assert hasattr(raw, name), name
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from recpack_b200 import ItemKNN
+    from recpack_b200._lib import RpkError
+
+    with pytest.raises(RpkError):
+        ItemKNN(K=2).fit(csr_matrix(np.eye(3)))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "recpack_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_constructor_contract():
+    """recpack/algorithms/nearest_neighbour.py:170-202 and base.py:50-61."""
+    from recpack_b200 import ItemKNN, NDCGK, RecallK
+
+    a = ItemKNN(K=7, similarity="conditional_probability", pop_discount=0.5, normalize_sim=True)
+    p = a.get_params()
+    assert p["K"] == 7 and p["similarity"] == "conditional_probability" and p["pop_discount"] == 0.5
+    assert a.identifier.startswith("ItemKNN(K=7,") and a.name == "ItemKNN" and str(a) == "ItemKNN"
+    with pytest.raises(ValueError):
+        ItemKNN(similarity="nope")
+    with pytest.raises(ValueError):
+        ItemKNN(similarity="conditional_probability", pop_discount=-0.1)
+    with pytest.warns(UserWarning):
+        ItemKNN(similarity="cosine", pop_discount=0.3)
+    assert NDCGK(10).name == "NDCGK_10" and RecallK(20).name == "RecallK_20"
+    from sklearn.exceptions import NotFittedError
+
+    with pytest.raises(NotFittedError):
+        ItemKNN().predict(csr_matrix((2, 2)))
+
+
+def test_binary_structure_coercion():
+    from recpack_b200.matrix import UnsupportedTypeError, binary_structure, to_csr_matrix
+
+    X = csr_matrix((np.array([3, 1, 1, 0, 2]), np.array([2, 0, 0, 1, 1]), np.array([0, 4, 5])), shape=(2, 3))
+    Xc, indptr, indices = binary_structure(X)
+    assert indptr.dtype == np.int64 and indices.dtype == np.int32
+    assert indptr.tolist() == [0, 2, 3] and indices.tolist() == [0, 2, 1]
+    canon = csr_matrix(np.array([[1, 0, 1], [0, 1, 0]]))
+    _, p2, i2 = binary_structure(canon)
+    assert np.shares_memory(i2, canon.indices) or i2.tolist() == canon.indices.tolist()
+    with pytest.raises(UnsupportedTypeError):
+        to_csr_matrix([[1, 0]] and np.ones((2, 2)))
+
+
+def test_synthetic_generator_is_exact_and_deterministic():
+    from recpack_b200.synth import synth_interactions, weak_generalization_split
+
+    X = synth_interactions(500, 200, 7000, seed=3)
+    Y = synth_interactions(500, 200, 7000, seed=3)
+    assert X.nnz == 7000 and X.shape == (500, 200) and X.has_canonical_format
+    assert (X != Y).nnz == 0
+    tr, te = weak_generalization_split(X, 0.8, seed=1)
+    assert (tr + te != X).nnz == 0 and tr.multiply(te).nnz == 0
+    d, dt = np.diff(X.indptr), np.diff(tr.indptr)
+    assert np.array_equal(dt, np.ceil(0.8 * d).astype(dt.dtype))
+
+
+def test_shard_bounds():
+    from recpack_b200.distributed import shard_bounds
+
+    cuts = shard_bounds(np.ones(10), 3)
+    assert cuts[0] == 0 and cuts[-1] == 10 and all(b >= a for a, b in zip(cuts, cuts[1:]))
+    cuts = shard_bounds([100, 1, 1, 1, 1, 1], 2)
+    assert cuts == [0, 1, 6]
+    assert shard_bounds(np.zeros(4), 2)[-1] == 4
+
+
+def _gloo_worker(rank, world, port, tmpdir):
+    import torch
+    import torch.distributed as dist
+
+    from recpack_b200.distributed import ShardExchange
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        I, K = 11, 3
+        cuts = [0, 7, 11]
+        rng = np.random.default_rng(5)
+        full_idx = rng.integers(0, I, size=(I, K)).astype(np.int32)
+        full_val = rng.random((I, K))
+        full_len = rng.integers(0, K + 1, size=I).astype(np.int32)
+        ex = ShardExchange(cuts, K, "cpu", dist)
+        b, e = cuts[rank], cuts[rank + 1]
+        a_idx, a_val, a_len = ex.gather(torch.from_numpy(full_idx[b:e]), torch.from_numpy(full_val[b:e]), torch.from_numpy(full_len[b:e]))
+        assert np.array_equal(a_idx.numpy(), full_idx) and np.array_equal(a_val.numpy(), full_val)
+        assert np.array_equal(a_len.numpy(), full_len)
+        sums = torch.tensor([1.0 + rank, 2.0, 10.0 * (rank + 1)], dtype=torch.float64)
+        dist.all_reduce(sums)
+        assert sums.tolist() == [3.0, 4.0, 30.0]
+        open(os.path.join(tmpdir, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_exchange_on_gloo_world_size_2(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
