@@ -151,6 +151,19 @@ RPK_EXPORT int rpk_metrics_topn(rpk_ctx* ctx, int64_t U, int N,
                      const double* discount, const double* idcg, int maxK,
                      double* per_user, double* sums, int64_t* n_users);
 
+/*
+ * Dense leg of the fit on the tensor cores (tcgen05 int8 MMA, int32 accumulation in TMEM):
+ * G[i][j] = sum_k A[i][k] * A[j][k] for a 0/1 matrix A (uint8 [I x Kd] row-major, Kd <= 32768),
+ * written as uint16 [I x I].  rpk_fit_topk uses this kernel for the densest user columns when
+ * rpk_fit_config enables it; this entry point exposes it for verification.
+ */
+RPK_EXPORT int rpk_gram_dense_u16(rpk_ctx* ctx, int64_t I, int64_t Kd, const uint8_t* A, uint16_t* out_G);
+
+/* Fit configuration.  dense_users: how many of the users with the longest histories go through the
+ * tensor-core Gram (0 = none, -1 = automatic, at most 4096); the remaining users go through the
+ * sparse kernel.  The result of rpk_fit_topk does not depend on this setting. */
+RPK_EXPORT int rpk_fit_config(rpk_ctx* ctx, int dense_users);
+
 #ifdef __cplusplus
 }
 #endif

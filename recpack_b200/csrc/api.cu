@@ -154,4 +154,17 @@ int rpk_metrics_topn(rpk_ctx* ctx, int64_t U, int N, const int32_t* top_idx, con
   RPK_API_END(ctx)
 }
 
+int rpk_gram_dense_u16(rpk_ctx* ctx, int64_t I, int64_t Kd, const uint8_t* A, uint16_t* out_G) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_gram_dense_u16(ctx, I, Kd, A, out_G);
+  RPK_API_END(ctx)
+}
+
+int rpk_fit_config(rpk_ctx* ctx, int dense_users) {
+  RPK_API_BEGIN(ctx)
+  if (dense_users < -1 || dense_users > 4096) throw rpk::Error("dense_users must be in [-1, 4096]");
+  ctx->dense_users = dense_users;
+  RPK_API_END(ctx)
+}
+
 }  // extern "C"

@@ -49,6 +49,7 @@ struct rpk_ctx {
   std::string err;
   int64_t launches = 0;
   int flags = 0;
+  int dense_users = 0;  // users routed through the tensor-core Gram (-1 = automatic)
   int sm_count = 0;
   int smem_max = 0;  // max opt-in dynamic shared memory per block
   std::map<std::string, rpk::Buf> bufs;

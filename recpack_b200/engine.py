@@ -120,6 +120,16 @@ class Engine:
         self._check(self._lib.rpk_fit_item_counts(self._h, _addr(out, np.int32), int(I)))
         return out
 
+    def fit_config(self, dense_users: int = -1):
+        self._check(self._lib.rpk_fit_config(self._h, int(dense_users)))
+
+    def gram_dense_u16(self, A):
+        """G = A A^T on the tensor cores for a 0/1 uint8 matrix A [I, Kd] (verification entry)."""
+        I, Kd = A.shape
+        out = _empty_like_kind(A, (I, I), np.uint16)
+        self._check(self._lib.rpk_gram_dense_u16(self._h, int(I), int(Kd), _addr(A, np.uint8), _addr(out, np.uint16)))
+        return out
+
     # -- model ----------------------------------------------------------------------------
     def model_load_topk(self, I, K, idx, val, ln):
         self._check(self._lib.rpk_model_load_topk(self._h, int(I), int(K), _addr(idx, np.int32), _addr(val, np.float64),
