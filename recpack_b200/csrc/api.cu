@@ -47,6 +47,7 @@ int rpk_create(int device, rpk_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->smem_max = (int)prop.sharedMemPerBlockOptin;
+    c->dense_users = -1;  // automatic
     *out = c;
   } catch (const std::exception& e) {
     g_create_error = e.what();

@@ -17,6 +17,18 @@ namespace rpk {
 // ------------------------------------------------------------------------------------------
 // CSR preparation: item popularities, CSC transpose, per-row work estimate
 // ------------------------------------------------------------------------------------------
+// Per-item number of users that stay on the sparse path (one warp per user).
+__global__ void k_item_counts_light(const int64_t* __restrict__ indptr, const int* __restrict__ indices, int64_t U,
+                                    const int* __restrict__ dense_slot, int* __restrict__ n_light) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t u = warp; u < U; u += nwarps) {
+    if (dense_slot[u] >= 0) continue;
+    for (int64_t k = indptr[u] + lane; k < indptr[u + 1]; k += 32) atomicAdd(&n_light[indices[k]], 1);
+  }
+}
+
 __global__ void k_item_counts(const int* __restrict__ indices, int64_t nnz, int* __restrict__ n) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += stride) atomicAdd(&n[indices[e]], 1);
@@ -24,12 +36,13 @@ __global__ void k_item_counts(const int* __restrict__ indices, int64_t nnz, int*
 
 // One warp per user: scatter the user id into the lists of its items; work[j] += d_u.
 __global__ void k_fill_csc(const int64_t* __restrict__ indptr, const int* __restrict__ indices, int64_t U,
-                           const int64_t* __restrict__ cscptr, int* __restrict__ cursor, int* __restrict__ csc_users,
-                           u64* __restrict__ work) {
+                           const int* __restrict__ dense_slot, const int64_t* __restrict__ cscptr, int* __restrict__ cursor,
+                           int* __restrict__ csc_users, u64* __restrict__ work) {
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t u = warp; u < U; u += nwarps) {
+    if (dense_slot && dense_slot[u] >= 0) continue;  // handled by the tensor-core Gram
     int64_t b = indptr[u], e = indptr[u + 1];
     u64 d = (u64)(e - b);
     for (int64_t k = b + lane; k < e; k += 32) {
@@ -38,6 +51,80 @@ __global__ void k_fill_csc(const int64_t* __restrict__ indptr, const int* __rest
       csc_users[cscptr[j] + pos] = (int)u;
       atomicAdd(&work[j], d);
     }
+  }
+}
+
+// ---- hybrid split: the users with the longest histories go through the tensor-core Gram ----
+__global__ void k_len_hist(const int64_t* __restrict__ indptr, int64_t U, int64_t I, int* __restrict__ hist) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u < U) {
+    int64_t d = indptr[u + 1] - indptr[u];
+    if (d > I) d = I;
+    atomicAdd(&hist[d], 1);
+  }
+}
+// Smallest history length tau >= min_len such that at most hmax users have d >= tau (one block).
+// out[0] = tau, out[1] = 0 (slot counter).
+__global__ void __launch_bounds__(1024) k_pick_dense_threshold(const int* __restrict__ hist, int64_t I, int hmax, int min_len,
+                                                               int* __restrict__ out) {
+  __shared__ int s_tot[1024];
+  const int tid = threadIdx.x;
+  const int64_t per = (I + 1 + blockDim.x - 1) / blockDim.x;
+  // thread t owns lengths [I - (t+1)*per + 1, I - t*per] (descending blocks from the top)
+  const int64_t hi = I - (int64_t)tid * per, lo = max((int64_t)0, hi - per + 1);
+  int mine = 0;
+  for (int64_t d = hi; d >= lo && d >= 0; --d) mine += hist[d];
+  s_tot[tid] = mine;
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0;
+    int64_t tau = I + 1;
+    bool done = false;
+    for (int t = 0; t < blockDim.x && !done; ++t) {
+      const int64_t h = I - (int64_t)t * per, l = max((int64_t)0, h - per + 1);
+      if (h < 0) break;
+      if (acc + s_tot[t] <= hmax) {
+        acc += s_tot[t];
+        tau = l;
+      } else {
+        for (int64_t d = h; d >= l; --d) {
+          if (acc + hist[d] > hmax) {
+            done = true;
+            break;
+          }
+          acc += hist[d];
+          tau = d;
+        }
+        done = true;
+      }
+    }
+    if (tau < min_len) tau = min_len;
+    out[0] = (int)tau;
+    out[1] = 0;
+  }
+}
+__global__ void k_assign_dense_slots(const int64_t* __restrict__ indptr, int64_t U, int* __restrict__ thr_cnt, int hmax,
+                                     int* __restrict__ slot) {
+  int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  const int64_t d = indptr[u + 1] - indptr[u];
+  int s = -1;
+  if (d >= thr_cnt[0]) {
+    s = atomicAdd(&thr_cnt[1], 1);
+    if (s >= hmax) s = -1;  // cannot happen: the threshold admits at most hmax users
+  }
+  slot[u] = s;
+}
+// A[item][slot] = 1 for every interaction of a dense user (one warp per user).
+__global__ void k_fill_dense(const int64_t* __restrict__ indptr, const int* __restrict__ indices, int64_t U,
+                             const int* __restrict__ slot, int64_t kd_pad, unsigned char* __restrict__ A) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t u = warp; u < U; u += nwarps) {
+    const int s = slot[u];
+    if (s < 0) continue;
+    for (int64_t k = indptr[u] + lane; k < indptr[u + 1]; k += 32) A[(int64_t)indices[k] * kd_pad + s] = 1;
   }
 }
 
@@ -307,6 +394,8 @@ struct FitParams {
   const int* csc_users;
   const unsigned* pref;   // per-item exclusive prefix of history lengths (CSC order)
   const u64* work;        // per-item total of history lengths
+  const unsigned short* g16;  // dense-leg counts [I x ldg] (null: none)
+  int64_t ldg;
   SimKey sk;
   const int* order;       // rows of this launch, heaviest first
   const int* nrows_dev;   // number of rows in `order` (device side: no host round trip)
@@ -346,7 +435,7 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
     const int64_t orow = p.direct_out ? ((int64_t)i - p.item_begin) : ((int64_t)pos * p.P + pass);
     int* o_idx = p.out_idx + orow * p.K;
     int* o_cnt = p.out_cnt + orow * p.K;
-    if (ue == ub) {  // item never seen: empty row (base.py:257-279 warns about these)
+    if (p.sk.n[i] == 0) {  // item never seen: empty row (base.py:257-279 warns about these)
       for (int t = tid; t < p.K; t += nt) {
         o_idx[t] = -1;
         o_cnt[t] = 0;
@@ -355,7 +444,19 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       continue;
     }
     const int nwords = PACK16 ? (ns + 1) >> 1 : ns;
-    for (int s = tid; s < nwords; s += nt) cnt[s] = 0u;
+    if (p.g16) {
+      // start from the counts of the dense leg (tensor-core Gram over the densest users)
+      const unsigned short* grow = p.g16 + (int64_t)i * p.ldg + r0;
+      if (PACK16) {
+        const unsigned* gw = reinterpret_cast<const unsigned*>(grow);  // two uint16 counts = one packed word
+        for (int s = tid; s < nwords; s += nt) cnt[s] = gw[s];
+        if ((ns & 1) && tid == 0) cnt[nwords - 1] &= 0xffffu;
+      } else {
+        for (int s = tid; s < nwords; s += nt) cnt[s] = grow[s];
+      }
+    } else {
+      for (int s = tid; s < nwords; s += nt) cnt[s] = 0u;
+    }
     __syncthreads();
     const int64_t nu64 = ue - ub;
     if (!p.usplit) {
@@ -602,11 +703,52 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     k_item_counts<<<blocks, 256, 0, st>>>(indices, nnz, n);
     RPK_LAUNCH_CHECK(c);
   }
-  k_scan_i32_i64<<<1, 1024, 0, st>>>(n, cscptr, I);
+  // ---- hybrid split: the users with the longest histories carry most of the
+  //      sum of d_u^2; their Gram goes to the tensor cores, everybody else to the sparse kernel
+  int hmax = c->dense_users;
+  const int64_t rows_pad = (I + 255) / 256 * 256;
+  if (hmax < 0) {
+    const double g16_bytes = (double)I * (double)rows_pad * 2.0;
+    hmax = (I >= 4096 && U >= 8192 && g16_bytes <= 16e9) ? 1024 : 0;
+  }
+  if (hmax > U) hmax = (int)U;
+  if (nnz == 0 || I < 2) hmax = 0;
+  const int* dense_slot = nullptr;
+  const unsigned short* g16 = nullptr;
+  const int* n_sparse = n;  // per-item user counts on the sparse path
+  if (hmax > 0) {
+    const int64_t kd_pad = ((int64_t)hmax + 127) / 128 * 128;
+    int* lhist = c->buf<int>("fit_len_hist", (size_t)I + 2);
+    int* thr_cnt = c->buf<int>("fit_dense_thr", 4);
+    int* slot = c->buf<int>("fit_dense_slot", (size_t)U);
+    int* n_light = c->buf<int>("fit_n_light", (size_t)I);
+    unsigned char* A = c->buf<unsigned char>("fit_dense_A", (size_t)rows_pad * kd_pad);
+    unsigned short* G = c->buf<unsigned short>("fit_dense_G", (size_t)I * rows_pad);
+    RPK_CUDA(cudaMemsetAsync(lhist, 0, sizeof(int) * ((size_t)I + 2), st));
+    RPK_CUDA(cudaMemsetAsync(n_light, 0, sizeof(int) * (size_t)I, st));
+    RPK_CUDA(cudaMemsetAsync(A, 0, (size_t)rows_pad * kd_pad, st));
+    k_len_hist<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, I, lhist);
+    RPK_LAUNCH_CHECK(c);
+    // histories shorter than 32 items are never worth a dense column
+    k_pick_dense_threshold<<<1, 1024, 0, st>>>(lhist, I, hmax, 32, thr_cnt);
+    RPK_LAUNCH_CHECK(c);
+    k_assign_dense_slots<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, thr_cnt, hmax, slot);
+    RPK_LAUNCH_CHECK(c);
+    const int wblocks = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
+    k_fill_dense<<<wblocks, 256, 0, st>>>(indptr, indices, U, slot, kd_pad, A);
+    RPK_LAUNCH_CHECK(c);
+    k_item_counts_light<<<wblocks, 256, 0, st>>>(indptr, indices, U, slot, n_light);
+    RPK_LAUNCH_CHECK(c);
+    run_gram_dense_tc(c, A, rows_pad, kd_pad, I, G, rows_pad);
+    dense_slot = slot;
+    g16 = G;
+    n_sparse = n_light;
+  }
+  k_scan_i32_i64<<<1, 1024, 0, st>>>(n_sparse, cscptr, I);
   RPK_LAUNCH_CHECK(c);
   if (nnz > 0 && U > 0) {
     int blocks = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
-    k_fill_csc<<<blocks, 256, 0, st>>>(indptr, indices, U, cscptr, cursor, csc_users, work);
+    k_fill_csc<<<blocks, 256, 0, st>>>(indptr, indices, U, dense_slot, cscptr, cursor, csc_users, work);
     RPK_LAUNCH_CHECK(c);
   }
   unsigned* pref = c->buf<unsigned>("fit_pref", (size_t)nnz);
@@ -699,6 +841,8 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
       fp.csc_users = csc_users;
       fp.pref = pref;
       fp.work = work;
+      fp.g16 = g16;
+      fp.ldg = rows_pad;
       fp.sk = sk;
       fp.order = wide ? order_h : order_l;
       fp.nrows_dev = split_cnt + wide;

@@ -156,6 +156,26 @@ def test_fit_matches_oracle_on_synthetic(engine, case, flags):
     _assert_fit_equal(got, orc.canon_fit(X, K=K, similarity=sim, pop_discount=pd_))
 
 
+@pytest.mark.parametrize("flags", [0, 1, 4])
+@pytest.mark.parametrize("dense_users", [16, 200, 4096])
+@pytest.mark.parametrize("case", [CASES[1], CASES[2], CASES[3], CASES[7]])
+def test_fit_hybrid_dense_users_gives_identical_results(engine, case, dense_users, flags):
+    """The users with the longest histories go through the tcgen05 Gram, the rest through the sparse
+    kernel: counts, lists and values must not change."""
+    from recpack_b200.synth import synth_interactions
+
+    U, I, nnz, K, sim, pd_ = case
+    X = synth_interactions(U, I, nnz, seed=U + I)
+    engine.debug_flags(flags)
+    engine.fit_config(dense_users)
+    try:
+        got = _fit_lists(engine, X, K, sim, pd_)
+    finally:
+        engine.fit_config(-1)
+        engine.debug_flags(0)
+    _assert_fit_equal(got, orc.canon_fit(X, K=K, similarity=sim, pop_discount=pd_))
+
+
 @pytest.mark.parametrize("flags", [0, 2, 6])
 def test_fit_total_ties(engine, flags):
     """Every pair ties: 3 users who all saw all items.  The canonical pick is the lowest indices."""
