@@ -138,20 +138,31 @@ __global__ void k_csc_prefix(const int64_t* __restrict__ cscptr, const int* __re
   for (int64_t i = warp; i < I; i += nwarps) {
     const int64_t b = cscptr[i], e = cscptr[i + 1];
     unsigned carry = 0;
-    for (int64_t base = b; base < e; base += 32) {
-      const int64_t k = base + lane;
-      unsigned v = 0;
-      if (k < e) {
-        const int u = csc_users[k];
-        v = (unsigned)(indptr[u + 1] - indptr[u]);
+    for (int64_t base = b; base < e; base += 128) {  // 4 users per lane: four independent loads in flight
+      unsigned v[4], tot = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t k = base + 4 * lane + q;
+        v[q] = 0;
+        if (k < e) {
+          const int u = csc_users[k];
+          v[q] = (unsigned)(indptr[u + 1] - indptr[u]);
+        }
+        tot += v[q];
       }
-      unsigned incl = v;
+      unsigned incl = tot;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
       }
-      if (k < e) pref[k] = carry + incl - v;
+      unsigned run = carry + incl - tot;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t k = base + 4 * lane + q;
+        if (k < e) pref[k] = run;
+        run += v[q];
+      }
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
@@ -448,8 +459,16 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       // start from the counts of the dense leg (tensor-core Gram over the densest users)
       const unsigned short* grow = p.g16 + (int64_t)i * p.ldg + r0;
       if (PACK16) {
-        const unsigned* gw = reinterpret_cast<const unsigned*>(grow);  // two uint16 counts = one packed word
-        for (int s = tid; s < nwords; s += nt) cnt[s] = gw[s];
+        // two uint16 counts = one packed word: the row is copied as it is, 16 B per cp.async, all copies of a
+        // thread in flight at once (the row comes from HBM: 118 KB at ML-25M shape)
+        const int nvec = nwords >> 2;
+        const uint4* gv = reinterpret_cast<const uint4*>(grow);
+        for (int s = tid; s < nvec; s += nt)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(cnt + 4 * s)), "l"(gv + s) : "memory");
+        const unsigned* gw = reinterpret_cast<const unsigned*>(grow);
+        for (int s = 4 * nvec + tid; s < nwords; s += nt) cnt[s] = gw[s];
+        asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
         if ((ns & 1) && tid == 0) cnt[nwords - 1] &= 0xffffu;
       } else {
         for (int s = tid; s < nwords; s += nt) cnt[s] = grow[s];
