@@ -742,7 +742,9 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     int* slot = c->buf<int>("fit_dense_slot", (size_t)U);
     int* n_light = c->buf<int>("fit_n_light", (size_t)I);
     unsigned char* A = c->buf<unsigned char>("fit_dense_A", (size_t)rows_pad * kd_pad);
-    unsigned short* G = c->buf<unsigned short>("fit_dense_G", (size_t)I * rows_pad);
+    // only this shard's item rows of the dense Gram are needed (row block aligned down to the 128-row tile)
+    const int64_t g_row0 = item_begin / 128 * 128;
+    unsigned short* G = c->buf<unsigned short>("fit_dense_G", (size_t)(item_end - g_row0 + 1) * rows_pad);
     RPK_CUDA(cudaMemsetAsync(lhist, 0, sizeof(int) * ((size_t)I + 2), st));
     RPK_CUDA(cudaMemsetAsync(n_light, 0, sizeof(int) * (size_t)I, st));
     RPK_CUDA(cudaMemsetAsync(A, 0, (size_t)rows_pad * kd_pad, st));
@@ -758,9 +760,9 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     RPK_LAUNCH_CHECK(c);
     k_item_counts_light<<<wblocks, 256, 0, st>>>(indptr, indices, U, slot, n_light);
     RPK_LAUNCH_CHECK(c);
-    run_gram_dense_tc(c, A, rows_pad, kd_pad, I, G, rows_pad);
+    run_gram_dense_tc(c, A, rows_pad, kd_pad, g_row0, item_end, G, rows_pad);
     dense_slot = slot;
-    g16 = G;
+    g16 = G - g_row0 * rows_pad;  // indexed by absolute item row in the fit kernel
     n_sparse = n_light;
   }
   k_scan_i32_i64<<<1, 1024, 0, st>>>(n_sparse, cscptr, I);

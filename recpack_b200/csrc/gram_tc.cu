@@ -97,7 +97,9 @@ __host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N) {
 
 struct GramParams {
   int m_tiles, n_tiles, k_blocks;
-  int rows_valid;   // rows / columns of G that exist
+  int row_begin;    // first row of G that is computed (multiple of 128); G points at it
+  int rows_valid;   // rows of A / columns of G that exist; rows >= row_end are not written
+  int row_end;
   int64_t ldg;      // leading dimension of G in elements (multiple of 32)
   unsigned short* G;
 };
@@ -151,7 +153,7 @@ k_gram_i8_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], TC_STAGE_BYTES);
-          tma_load_2d(smem_a + (size_t)stage * TC_A_BYTES, &map_a, &full_bar[stage], kb * TC_BK, m_blk * TC_BM);
+          tma_load_2d(smem_a + (size_t)stage * TC_A_BYTES, &map_a, &full_bar[stage], kb * TC_BK, p.row_begin + m_blk * TC_BM);
           tma_load_2d(smem_b + (size_t)stage * TC_B_BYTES, &map_b, &full_bar[stage], kb * TC_BK, n_blk * TC_BN);
           if (++stage == TC_STAGES) {
             stage = 0;
@@ -202,8 +204,8 @@ k_gram_i8_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       const int m_blk = t / p.n_tiles, n_blk = t % p.n_tiles;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int row = m_blk * TC_BM + quarter * 32 + lane;
-      unsigned short* grow = p.G + (int64_t)row * p.ldg + (int64_t)n_blk * TC_BN;
+      const int row = p.row_begin + m_blk * TC_BM + quarter * 32 + lane;
+      unsigned short* grow = p.G + (int64_t)(row - p.row_begin) * p.ldg + (int64_t)n_blk * TC_BN;
 #pragma unroll 1
       for (int c = 0; c < TC_BN / 32; ++c) {
         uint32_t v[32];
@@ -219,7 +221,7 @@ k_gram_i8_tc(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             : "r"(taddr)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < p.rows_valid) {
+        if (row < p.row_end) {
           uint4* dst = reinterpret_cast<uint4*>(grow + c * 32);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -266,12 +268,15 @@ static EncodeTiledFn get_encode_tiled() {
 }
 
 // A: device, [rows_pad x kd_pad] uint8 row-major, rows_pad % 256 == 0, kd_pad % 128 == 0.
-// G: device, [rows_valid x ldg] uint16, ldg >= rows_pad.
-void run_gram_dense_tc(rpk_ctx* c, const unsigned char* A, int64_t rows_pad, int64_t kd_pad, int64_t rows_valid,
-                       unsigned short* G, int64_t ldg) {
+// Computes rows [row_begin, row_end) of G = A A^T (row_begin % 128 == 0) against all columns.
+// G: device, [(row_end - row_begin) x ldg] uint16, ldg >= rows_pad.
+void run_gram_dense_tc(rpk_ctx* c, const unsigned char* A, int64_t rows_pad, int64_t kd_pad, int64_t row_begin,
+                       int64_t row_end, unsigned short* G, int64_t ldg) {
   RPK_REQUIRE(rows_pad % TC_BN == 0 && kd_pad % TC_BK == 0 && kd_pad >= TC_BK, "dense Gram: operand is not tile aligned");
   RPK_REQUIRE(kd_pad <= 65535, "dense Gram: counts must fit 16 bits");
   RPK_REQUIRE(ldg >= rows_pad && ldg % 32 == 0, "dense Gram: bad output stride");
+  RPK_REQUIRE(row_begin % TC_BM == 0 && row_begin <= row_end && row_end <= rows_pad, "dense Gram: bad row range");
+  if (row_end == row_begin) return;
   CUtensorMap map_a, map_b;
   const cuuint64_t dims[2] = {(cuuint64_t)kd_pad, (cuuint64_t)rows_pad};
   const cuuint64_t strides[1] = {(cuuint64_t)kd_pad};
@@ -288,11 +293,12 @@ void run_gram_dense_tc(rpk_ctx* c, const unsigned char* A, int64_t rows_pad, int
   p.m_tiles = (int)(rows_pad / TC_BM);
   p.n_tiles = (int)(rows_pad / TC_BN);
   p.k_blocks = (int)(kd_pad / TC_BK);
-  p.rows_valid = (int)rows_valid;
+  p.row_begin = (int)row_begin;
+  p.row_end = (int)row_end;
+  p.rows_valid = (int)row_end;
   p.ldg = ldg;
   p.G = G;
-  // rows beyond rows_valid produce no output; skip the m-tiles that hold none
-  p.m_tiles = (int)((rows_valid + TC_BM - 1) / TC_BM);
+  p.m_tiles = (int)((row_end - row_begin + TC_BM - 1) / TC_BM);
   RPK_CUDA(cudaFuncSetAttribute(k_gram_i8_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
   const int grid = std::min(c->sm_count, p.m_tiles * p.n_tiles);
   k_gram_i8_tc<<<std::max(grid, 1), TC_THREADS, TC_SMEM, c->stream>>>(map_a, map_b, p);
@@ -309,7 +315,7 @@ void run_gram_dense_u16(rpk_ctx* c, int64_t I, int64_t Kd, const unsigned char* 
   RPK_CUDA(cudaMemsetAsync(A, 0, (size_t)rows_pad * kd_pad, st));
   RPK_CUDA(cudaMemcpy2DAsync(A, (size_t)kd_pad, A_in, (size_t)Kd, (size_t)Kd, (size_t)I, cudaMemcpyDeviceToDevice, st));
   unsigned short* G = c->buf<unsigned short>("tc_G", (size_t)I * rows_pad);
-  run_gram_dense_tc(c, A, rows_pad, kd_pad, I, G, rows_pad);
+  run_gram_dense_tc(c, A, rows_pad, kd_pad, 0, I, G, rows_pad);
   Out<unsigned short> o;
   o.init(c, G_u, (size_t)I * I, "tc_G_out");
   RPK_CUDA(cudaMemcpy2DAsync(o.dev, (size_t)I * 2, G, (size_t)rows_pad * 2, (size_t)I * 2, (size_t)I, cudaMemcpyDeviceToDevice, st));

@@ -29,7 +29,7 @@ void run_metrics_topn(rpk_ctx* c, int64_t U, int N, const int32_t* top_idx, cons
                       double* per_user, double* sums, int64_t* n_users);
 
 void run_gram_dense_u16(rpk_ctx* c, int64_t I, int64_t Kd, const unsigned char* A, unsigned short* G);
-void run_gram_dense_tc(rpk_ctx* c, const unsigned char* A, int64_t rows_pad, int64_t kd_pad, int64_t rows_valid,
-                       unsigned short* G, int64_t ldg);
+void run_gram_dense_tc(rpk_ctx* c, const unsigned char* A, int64_t rows_pad, int64_t kd_pad, int64_t row_begin,
+                       int64_t row_end, unsigned short* G, int64_t ldg);
 
 }  // namespace rpk
