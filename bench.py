@@ -259,7 +259,7 @@ def run_gpu(args):
                "len": torch.empty((nU,), dtype=torch.int32, device=dev)}
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # > L2 (126 MB)
     metrics = [("ndcg", 10), ("recall", 20)]
-    phase_ms = {"fit": [], "exchange": [], "score": []}
+    phase_ms = {"fit": [], "exchange": [], "score": [], "gram_tc": [], "fit_rows": [], "predict": []}
 
     def one_step(record):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -280,6 +280,10 @@ def run_gpu(args):
         ev[3].record()
         torch.cuda.synchronize()
         if record:
+            kt = eng.last_timings()
+            phase_ms["gram_tc"].append(kt["gram_tc_ms"])
+            phase_ms["fit_rows"].append(kt["fit_rows_ms"])
+            phase_ms["predict"].append(kt["predict_ms"])
             phase_ms["fit"].append(ev[0].elapsed_time(ev[1]))
             phase_ms["exchange"].append(ev[1].elapsed_time(ev[2]))
             phase_ms["score"].append(ev[2].elapsed_time(ev[3]))
@@ -325,15 +329,33 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         fit_frac_share = (ie - ib) / I
-        dominant = "fit" if fit_ms >= score_ms else "score"
-        if dominant == "fit":
-            alg = stats["fit_bytes"] * (item_work[ib:ie].sum() / item_work.sum())
-            ach = alg / (fit_ms * 1e-3) / 1e9
-            kname = "k_fit_rows"
-        else:
+        k_gram, k_rows, k_pred = (float(np.mean(phase_ms[k])) for k in ("gram_tc", "fit_rows", "predict"))
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath) and world == 1:
+            with open(tpath) as f:
+                traffic = json.load(f)
+        # dominant kernel = the longer of the two big kernels; algorithmic bytes per launch
+        if k_pred >= k_rows:
+            kname, kms = "k_predict", k_pred
             alg = stats["score_bytes"] * (d_u[ub:ue].sum() / d_u.sum())
-            ach = alg / (score_ms * 1e-3) / 1e9
-            kname = "k_predict"
+        else:
+            kname, kms = "k_fit_rows", k_rows
+            alg = stats["fit_bytes"] * (item_work[ib:ie].sum() / item_work.sum())
+        ach = alg / (kms * 1e-3) / 1e9
+        tensor = None
+        if k_gram > 0:
+            bf16 = None
+            mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(mp):
+                with open(mp) as f:
+                    bf16 = float(json.load(f)["bf16_tflops"])
+            ops = 2.0 * 1024 * (ie - ib) * I  # 2 * Kd * rows * I, Kd = 1024 dense users
+            tops = ops / (k_gram * 1e-3) / 1e12
+            tensor = {"bound": "tensor", "kernel": "k_gram_i8_tc", "achieved": tops, "unit": "TOP/s (int8)", "ms": k_gram,
+                      "peak": 2 * bf16 if bf16 else 4500.0,
+                      "peak_source": "2 x measured bf16 cuBLAS burst (MEASURED_PEAKS.json): int8 issues at twice the bf16 rate" if bf16 else "nominal dense int8",
+                      "frac": tops / (2 * bf16 if bf16 else 4500.0), "traffic": traffic.get("k_gram_i8_tc")}
         line = {
             "metric": METRIC, "value": U / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -345,10 +367,13 @@ def run_gpu(args):
             "fit_seconds": fit_ms * 1e-3, "scoring_users_per_s": U / (score_ms * 1e-3), "exchange_ms": exch_ms,
             "ndcg10": ndcg10, "recall20": recall20, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "peak_source": peak_src,
-                         "note": "algorithmic bytes / CUDA-event time of the phase that contains the kernel; operands are L2-resident so this "
-                                 "can exceed the HBM copy peak"},
+                         "traffic": traffic.get(kname), "peak_source": peak_src, "kernel_ms": kms,
+                         "note": "algorithmic bytes per launch / CUDA-event duration of the kernel; operands are L2-resident "
+                                 "(measured DRAM traffic is far below the algorithmic bytes), the kernel is bound by shared-memory "
+                                 "atomics and instruction issue, not by HBM"},
+            "roofline_tensor": tensor,
             "phases_ms": {"fit": fit_ms, "exchange": exch_ms, "score": score_ms},
+            "kernels_ms": {"k_gram_i8_tc": k_gram, "k_fit_rows": k_rows, "k_predict": k_pred},
             "dense_equiv_int8_ops_per_s": stats["dense_equiv_ops"] * fit_frac_share / (fit_ms * 1e-3),
             "clocks": clocks,
         }

@@ -159,6 +159,11 @@ RPK_EXPORT int rpk_metrics_topn(rpk_ctx* ctx, int64_t U, int N,
  */
 RPK_EXPORT int rpk_gram_dense_u16(rpk_ctx* ctx, int64_t I, int64_t Kd, const uint8_t* A, uint16_t* out_G);
 
+/* Device time (CUDA events on the context's stream) of the dominant kernels of the last calls:
+ * out_ms[0] = tensor-core Gram of the last fit, out_ms[1] = sparse fit kernels of the last fit,
+ * out_ms[2] = scoring kernel of the last predict; -1 where the kernel did not run.  Synchronises. */
+RPK_EXPORT int rpk_last_timings(rpk_ctx* ctx, double* out_ms);
+
 /* Fit configuration.  dense_users: how many of the users with the longest histories go through the
  * tensor-core Gram (0 = none, -1 = automatic, at most 4096); the remaining users go through the
  * sparse kernel.  The result of rpk_fit_topk does not depend on this setting. */

@@ -32,6 +32,7 @@ _SIGNATURES = {
     "rpk_topk_csr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, _f64p, C.c_int, _i32p, _i32p]),
     "rpk_gram_dense_u16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _vp, _vp]),
     "rpk_fit_config": (C.c_int, [C.c_void_p, C.c_int]),
+    "rpk_last_timings": (C.c_int, [C.c_void_p, _vp]),
     "rpk_metrics_topn": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, _i32p, _i32p, _i64p, _i32p, C.c_int64, C.c_int,
                                    _i32p, _i32p, _f64p, _f64p, C.c_int, _f64p, _f64p, _i64p]),
 }

@@ -63,6 +63,8 @@ void rpk_destroy(rpk_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->bufs)
     if (kv.second.p) cudaFree(kv.second.p);
+  for (auto& e : ctx->ev)
+    if (e) cudaEventDestroy(e);
   delete ctx;
 }
 
@@ -158,6 +160,21 @@ int rpk_metrics_topn(rpk_ctx* ctx, int64_t U, int N, const int32_t* top_idx, con
 int rpk_gram_dense_u16(rpk_ctx* ctx, int64_t I, int64_t Kd, const uint8_t* A, uint16_t* out_G) {
   RPK_API_BEGIN(ctx)
   rpk::run_gram_dense_u16(ctx, I, Kd, A, out_G);
+  RPK_API_END(ctx)
+}
+
+int rpk_last_timings(rpk_ctx* ctx, double* out_ms) {
+  RPK_API_BEGIN(ctx)
+  if (!out_ms) throw rpk::Error("out_ms must not be null");
+  RPK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 3; ++k) {
+    out_ms[k] = -1.0;
+    if (ctx->ev_valid[k]) {
+      float ms = 0.f;
+      RPK_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2 * k], ctx->ev[2 * k + 1]));
+      out_ms[k] = ms;
+    }
+  }
   RPK_API_END(ctx)
 }
 

@@ -54,6 +54,13 @@ struct rpk_ctx {
   int smem_max = 0;  // max opt-in dynamic shared memory per block
   std::map<std::string, rpk::Buf> bufs;
   bool host_out_pending = false;
+  // CUDA events around the dominant kernels of the last fit / predict (rpk_last_timings)
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool ev_valid[3] = {false, false, false};
+  void ev_record(int k) {
+    if (!ev[k]) RPK_CUDA(cudaEventCreate(&ev[k]));
+    RPK_CUDA(cudaEventRecord(ev[k], stream));
+  }
 
   // ---- state of the last fit (device pointers into bufs)
   int64_t fit_I = 0;

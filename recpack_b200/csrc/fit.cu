@@ -735,6 +735,8 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
   const int* dense_slot = nullptr;
   const unsigned short* g16 = nullptr;
   const int* n_sparse = n;  // per-item user counts on the sparse path
+  c->ev_valid[0] = false;
+  c->ev_valid[1] = false;
   if (hmax > 0) {
     const int64_t kd_pad = ((int64_t)hmax + 127) / 128 * 128;
     int* lhist = c->buf<int>("fit_len_hist", (size_t)I + 2);
@@ -760,7 +762,10 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     RPK_LAUNCH_CHECK(c);
     k_item_counts_light<<<wblocks, 256, 0, st>>>(indptr, indices, U, slot, n_light);
     RPK_LAUNCH_CHECK(c);
+    c->ev_record(0);
     run_gram_dense_tc(c, A, rows_pad, kd_pad, g_row0, item_end, G, rows_pad);
+    c->ev_record(1);
+    c->ev_valid[0] = true;
     dense_slot = slot;
     g16 = G - g_row0 * rows_pad;  // indexed by absolute item row in the fit kernel
     n_sparse = n_light;
@@ -827,6 +832,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     const size_t avail = (size_t)c->smem_max - fixed - 1024;  // 1 KB slack for static shared memory
     const SimKey sk{n, rnf, pw, nmax, reinterpret_cast<const double*>(pwmin), mode};
 
+    c->ev_record(2);
     for (int wide = 0; wide < 2; ++wide) {
       // geometry: item-range passes so that the counters of one pass fit shared memory
       const int bytes_per_item = wide ? 4 : 2;
@@ -910,6 +916,8 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
         RPK_LAUNCH_CHECK(c);
       }
     }
+    c->ev_record(3);
+    c->ev_valid[1] = true;
     if (o_val.dev) {
       k_fit_values<<<ceil_div(nrows * K, 256), 256, 0, st>>>(o_idx.dev, cnt_dev, n, pw, mode, item_begin, nrows, K, o_val.dev);
       RPK_LAUNCH_CHECK(c);

@@ -646,8 +646,11 @@ static void launch_predict(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_
   RPK_REQUIRE(occ >= 1, "predict kernel does not fit on an SM");
   const int64_t total = U * g.P;
   const int grid = (int)std::min<int64_t>(total, (int64_t)c->sm_count * occ);
+  c->ev_record(4);
   k_predict<<<grid, g.nt, g.smem, st>>>(pp);
   RPK_LAUNCH_CHECK(c);
+  c->ev_record(5);
+  c->ev_valid[2] = true;
 }
 
 static void fill_common(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_t U, const int64_t* indptr,
