@@ -7,6 +7,8 @@
 //   recpack/util.py:50-96                           get_top_K_ranks / get_top_K_values
 // Row i of the Gram is  c_ij = sum_{u in users(i)} [j in hist(u)]: one CTA owns (row i, item range p),
 // walks users(i) through the CSC copy of X and bumps 32-bit shared-memory counters (native ATOMS.ADD).
+#include <vector>
+
 #include "common.cuh"
 #include "internal.h"
 #include "prims.cuh"
@@ -61,46 +63,6 @@ __global__ void k_len_hist(const int64_t* __restrict__ indptr, int64_t U, int64_
     int64_t d = indptr[u + 1] - indptr[u];
     if (d > I) d = I;
     atomicAdd(&hist[d], 1);
-  }
-}
-// Smallest history length tau >= min_len such that at most hmax users have d >= tau (one block).
-// out[0] = tau, out[1] = 0 (slot counter).
-__global__ void __launch_bounds__(1024) k_pick_dense_threshold(const int* __restrict__ hist, int64_t I, int hmax, int min_len,
-                                                               int* __restrict__ out) {
-  __shared__ int s_tot[1024];
-  const int tid = threadIdx.x;
-  const int64_t per = (I + 1 + blockDim.x - 1) / blockDim.x;
-  // thread t owns lengths [I - (t+1)*per + 1, I - t*per] (descending blocks from the top)
-  const int64_t hi = I - (int64_t)tid * per, lo = max((int64_t)0, hi - per + 1);
-  int mine = 0;
-  for (int64_t d = hi; d >= lo && d >= 0; --d) mine += hist[d];
-  s_tot[tid] = mine;
-  __syncthreads();
-  if (tid == 0) {
-    int acc = 0;
-    int64_t tau = I + 1;
-    bool done = false;
-    for (int t = 0; t < blockDim.x && !done; ++t) {
-      const int64_t h = I - (int64_t)t * per, l = max((int64_t)0, h - per + 1);
-      if (h < 0) break;
-      if (acc + s_tot[t] <= hmax) {
-        acc += s_tot[t];
-        tau = l;
-      } else {
-        for (int64_t d = h; d >= l; --d) {
-          if (acc + hist[d] > hmax) {
-            done = true;
-            break;
-          }
-          acc += hist[d];
-          tau = d;
-        }
-        done = true;
-      }
-    }
-    if (tau < min_len) tau = min_len;
-    out[0] = (int)tau;
-    out[1] = 0;
   }
 }
 __global__ void k_assign_dense_slots(const int64_t* __restrict__ indptr, int64_t U, int* __restrict__ thr_cnt, int hmax,
@@ -726,12 +688,50 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
   //      sum of d_u^2; their Gram goes to the tensor cores, everybody else to the sparse kernel
   int hmax = c->dense_users;
   const int64_t rows_pad = (I + 255) / 256 * 256;
-  if (hmax < 0) {
-    const double g16_bytes = (double)I * (double)rows_pad * 2.0;
-    hmax = (I >= 4096 && U >= 8192 && g16_bytes <= 16e9) ? 1024 : 0;
+  const bool dense_auto = hmax < 0;
+  if (dense_auto) {
+    const double g16_bytes = (double)nrows * (double)rows_pad * 2.0;
+    hmax = (I >= 4096 && U >= 8192 && g16_bytes <= 16e9) ? 4096 : 0;
   }
   if (hmax > U) hmax = (int)U;
-  if (nnz == 0 || I < 2) hmax = 0;
+  if (nnz == 0 || I < 2 || nrows == 0) hmax = 0;
+  int dense_tau = 32;  // histories shorter than this are never worth a dense column
+  int* lhist = nullptr;
+  if (hmax > 0) {
+    lhist = c->buf<int>("fit_len_hist", (size_t)I + 2);
+    RPK_CUDA(cudaMemsetAsync(lhist, 0, sizeof(int) * ((size_t)I + 2), st));
+    k_len_hist<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, I, lhist);
+    RPK_LAUNCH_CHECK(c);
+    // The split is chosen per density on the host from the history-length histogram (one small copy):
+    // moving the H longest histories to the tensor cores costs 2*H*rows*I int8 ops (+ the count matrix
+    // traffic) and saves sum(d_u^2) * rows/I counter updates of the sparse kernel.
+    std::vector<int> h((size_t)I + 1);
+    RPK_CUDA(cudaMemcpyAsync(h.data(), lhist, sizeof(int) * ((size_t)I + 1), cudaMemcpyDeviceToHost, st));
+    RPK_CUDA(cudaStreamSynchronize(st));
+    const double share = (double)nrows / (double)I;
+    const double dense_rate = 1.6e15, sparse_rate = 7e11, hbm = 5e12;  // measured on B200 (profiles/r1_summary.md)
+    const double fixed = (double)nrows * (double)rows_pad * 4.0 / hbm;
+    double best_gain = 0.0, saved = 0.0;
+    int best_h = 0, best_tau = 0;
+    int64_t taken = 0;
+    for (int64_t d = I; d >= dense_tau; --d) {
+      const int cnt_d = h[(size_t)d];
+      if (cnt_d == 0) continue;
+      if (taken + cnt_d > hmax) break;
+      taken += cnt_d;
+      saved += (double)cnt_d * (double)d * (double)d * share / sparse_rate;
+      const double kd = (double)((taken + 127) / 128 * 128);
+      const double cost = 2.0 * kd * (double)nrows * (double)rows_pad / dense_rate + fixed;
+      const double gain = saved - cost;
+      if (!dense_auto || gain > best_gain) {  // a fixed request takes as many users as allowed
+        best_gain = gain;
+        best_h = (int)taken;
+        best_tau = (int)d;
+      }
+    }
+    hmax = best_h;
+    dense_tau = best_tau;
+  }
   const int* dense_slot = nullptr;
   const unsigned short* g16 = nullptr;
   const int* n_sparse = n;  // per-item user counts on the sparse path
@@ -739,7 +739,6 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
   c->ev_valid[1] = false;
   if (hmax > 0) {
     const int64_t kd_pad = ((int64_t)hmax + 127) / 128 * 128;
-    int* lhist = c->buf<int>("fit_len_hist", (size_t)I + 2);
     int* thr_cnt = c->buf<int>("fit_dense_thr", 4);
     int* slot = c->buf<int>("fit_dense_slot", (size_t)U);
     int* n_light = c->buf<int>("fit_n_light", (size_t)I);
@@ -747,14 +746,10 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     // only this shard's item rows of the dense Gram are needed (row block aligned down to the 128-row tile)
     const int64_t g_row0 = item_begin / 128 * 128;
     unsigned short* G = c->buf<unsigned short>("fit_dense_G", (size_t)(item_end - g_row0 + 1) * rows_pad);
-    RPK_CUDA(cudaMemsetAsync(lhist, 0, sizeof(int) * ((size_t)I + 2), st));
+    const int thr_init[2] = {dense_tau, 0};
+    RPK_CUDA(cudaMemcpyAsync(thr_cnt, thr_init, sizeof(thr_init), cudaMemcpyHostToDevice, st));
     RPK_CUDA(cudaMemsetAsync(n_light, 0, sizeof(int) * (size_t)I, st));
     RPK_CUDA(cudaMemsetAsync(A, 0, (size_t)rows_pad * kd_pad, st));
-    k_len_hist<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, I, lhist);
-    RPK_LAUNCH_CHECK(c);
-    // histories shorter than 32 items are never worth a dense column
-    k_pick_dense_threshold<<<1, 1024, 0, st>>>(lhist, I, hmax, 32, thr_cnt);
-    RPK_LAUNCH_CHECK(c);
     k_assign_dense_slots<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, thr_cnt, hmax, slot);
     RPK_LAUNCH_CHECK(c);
     const int wblocks = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
