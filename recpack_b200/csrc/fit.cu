@@ -262,13 +262,29 @@ struct RowCountSrc {
     const int tid = threadIdx.x, nt = blockDim.x;
     if (PACK16) {
       const int nwords = (ns + 1) >> 1;
-      for (int w = tid * wstride; w < nwords; w += nt * wstride) {
-        const unsigned v = cnt[w];
-        if (v == 0u) continue;
-        const int c0 = (int)(v & 0xffffu), c1 = (int)(v >> 16);
-        const int j0 = r0 + 2 * w;
-        if (c0 >= cmin && j0 != self) f(2 * w, sk.akey(c0, j0));
-        if (!low_half_only && c1 >= cmin && j0 + 1 != self) f(2 * w + 1, sk.akey(c1, j0 + 1));
+      const int step = nt * wstride;
+      // four words (eight counters) per thread and iteration: all keys -- each needs a popularity load from
+      // L2 -- are computed before the first callback, so the loads overlap instead of queueing up
+      for (int wb = tid * wstride; wb < nwords; wb += 4 * step) {
+        unsigned v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = wb + q * step < nwords ? cnt[wb + q * step] : 0u;
+        if ((v[0] | v[1] | v[2] | v[3]) == 0u) continue;
+        u64 k[8];
+        bool ok[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int w = wb + q * step;
+          const int c0 = (int)(v[q] & 0xffffu), c1 = (int)(v[q] >> 16);
+          const int j0 = r0 + 2 * w;
+          ok[2 * q] = c0 >= cmin && j0 != self;
+          ok[2 * q + 1] = !low_half_only && c1 >= cmin && j0 + 1 != self;
+          k[2 * q] = ok[2 * q] ? sk.akey(c0, j0) : 0ull;
+          k[2 * q + 1] = ok[2 * q + 1] ? sk.akey(c1, j0 + 1) : 0ull;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (ok[q]) f(2 * (wb + (q >> 1) * step) + (q & 1), k[q]);
       }
     } else {
       for (int w = tid * wstride; w < ns; w += nt * wstride) {
@@ -380,6 +396,10 @@ struct FitParams {
   int* out_idx;
   int* out_cnt;
   int* out_len;
+  int defer_max;   // > 0: rows with at most this many survivors are sorted by k_fit_sort_rows instead
+  int* scr_idx;    // [rows x defer_max] unsorted survivors (item, count)
+  int* scr_cnt;
+  int* scr_len;    // [rows] survivors in scratch, -1 = row already final in out_*
 };
 
 template <bool PACK16>
@@ -413,7 +433,10 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
         o_idx[t] = -1;
         o_cnt[t] = 0;
       }
-      if (tid == 0) p.out_len[orow] = 0;
+      if (tid == 0) {
+        p.out_len[orow] = 0;
+        if (p.defer_max > 0) p.scr_len[orow] = -1;
+      }
       continue;
     }
     const int nwords = PACK16 ? (ns + 1) >> 1 : ns;
@@ -525,7 +548,22 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
     __syncthreads();
     // ---- fused epilogue: similarity ordering, diagonal removal, top-K -- all on the shared-memory row
     RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i, 1};
-    const int m = block_select_topk(src, p.K, list, p.cap, p.direct_cap, hist, sh);
+    bool sorted = true;
+    const int m = block_select_topk(src, p.K, list, p.cap, p.direct_cap, hist, sh, p.defer_max, &sorted);
+    if (!sorted) {
+      // hand the unsorted survivors to k_fit_sort_rows: many small CTAs sort rows concurrently there,
+      // instead of this 1024-thread CTA idling through the sort's barriers
+      int* s_idx = p.scr_idx + orow * p.defer_max;
+      int* s_cnt = p.scr_cnt + orow * p.defer_max;
+      for (int t = tid; t < m; t += nt) {
+        s_idx[t] = list[t].idx;
+        s_cnt[t] = list[t].aux;
+      }
+      if (tid == 0) p.scr_len[orow] = m;
+      __syncthreads();
+      continue;
+    }
+    if (p.defer_max > 0 && tid == 0) p.scr_len[orow] = -1;
     for (int t = tid; t < p.K; t += nt) {
       o_idx[t] = t < m ? list[t].idx : -1;
       o_cnt[t] = t < m ? list[t].aux : 0;
@@ -564,6 +602,55 @@ __global__ void __launch_bounds__(256) k_fit_merge(MergeParams p) {
       p.out_cnt[row * p.K + t] = t < m ? list[t].aux : 0;
     }
     if (tid == 0) p.out_len[row] = m;
+    __syncthreads();
+  }
+}
+
+// Sorts the unsorted survivors of a row (written by k_fit_rows) with the exact order and writes the K best.
+struct ListOrder {  // comparator-only "source" for the sort helpers
+  SimKey sk;
+  __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const { return sk.cmp3(a, b); }
+};
+struct SortParams {
+  SimKey sk;
+  const int* scr_idx;
+  const int* scr_cnt;
+  const int* scr_len;
+  int defer_max, K;
+  int64_t nrows;
+  int* out_idx;
+  int* out_cnt;
+  int* out_len;
+};
+__global__ void __launch_bounds__(256) k_fit_sort_rows(SortParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Entry* list = reinterpret_cast<Entry*>(smem);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  ListOrder ord{p.sk};
+  for (int64_t row = blockIdx.x; row < p.nrows; row += gridDim.x) {
+    const int m = p.scr_len[row];
+    if (m < 0) continue;  // already final
+    int n2 = 2;
+    while (n2 < m) n2 <<= 1;
+    for (int t = tid; t < n2; t += nt) {
+      Entry e;
+      if (t < m) {
+        p.sk.entry(p.scr_cnt[row * p.defer_max + t], p.scr_idx[row * p.defer_max + t], e);
+      } else {
+        e.key = 0;
+        e.idx = SENTINEL_IDX;
+        e.aux = 0;
+      }
+      list[t] = e;
+    }
+    __syncthreads();
+    bitonic_sort_entries(ord, list, n2);
+    const int keep = m < p.K ? m : p.K;
+    for (int t = tid; t < p.K; t += nt) {
+      p.out_idx[row * p.K + t] = t < keep ? list[t].idx : -1;
+      p.out_cnt[row * p.K + t] = t < keep ? list[t].aux : 0;
+    }
+    if (tid == 0) p.out_len[row] = keep;
     __syncthreads();
   }
 }
@@ -828,6 +915,12 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     const SimKey sk{n, rnf, pw, nmax, reinterpret_cast<const double*>(pwmin), mode};
 
     c->ev_record(2);
+    const int defer_max = std::min(cap, 512);
+    int* scr_idx = c->buf<int>("fit_scr_idx", (size_t)nrows * defer_max);
+    int* scr_cnt = c->buf<int>("fit_scr_cnt", (size_t)nrows * defer_max);
+    int* scr_len = c->buf<int>("fit_scr_len", (size_t)nrows);
+    RPK_CUDA(cudaMemsetAsync(scr_len, 0xff, sizeof(int) * (size_t)nrows, st));  // -1: nothing deferred
+    bool any_deferred = false;
     for (int wide = 0; wide < 2; ++wide) {
       // geometry: item-range passes so that the counters of one pass fit shared memory
       const int bytes_per_item = wide ? 4 : 2;
@@ -880,6 +973,12 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
       fp.out_idx = part_idx;
       fp.out_cnt = part_cnt;
       fp.out_len = part_len;
+      // rows written directly to the final arrays may defer their sort to k_fit_sort_rows
+      fp.defer_max = (P == 1 && !tiny) ? defer_max : 0;
+      fp.scr_idx = scr_idx;
+      fp.scr_cnt = scr_cnt;
+      fp.scr_len = scr_len;
+      any_deferred = any_deferred || fp.defer_max > 0;
       auto kern = wide ? k_fit_rows<false> : k_fit_rows<true>;
       RPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int occ = 0;
@@ -910,6 +1009,24 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
         k_fit_merge<<<std::max(1, mgrid), 256, fixed, st>>>(mp);
         RPK_LAUNCH_CHECK(c);
       }
+    }
+    if (any_deferred) {
+      SortParams sp;
+      sp.sk = sk;
+      sp.scr_idx = scr_idx;
+      sp.scr_cnt = scr_cnt;
+      sp.scr_len = scr_len;
+      sp.defer_max = defer_max;
+      sp.K = K;
+      sp.nrows = nrows;
+      sp.out_idx = o_idx.dev;
+      sp.out_cnt = cnt_dev;
+      sp.out_len = o_len.dev;
+      const size_t ssm = (size_t)defer_max * sizeof(Entry);
+      RPK_CUDA(cudaFuncSetAttribute(k_fit_sort_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+      const int sgrid = (int)std::min<int64_t>(nrows, (int64_t)c->sm_count * 8);
+      k_fit_sort_rows<<<sgrid, 256, ssm, st>>>(sp);
+      RPK_LAUNCH_CHECK(c);
     }
     c->ev_record(3);
     c->ev_valid[1] = true;

@@ -299,10 +299,11 @@ __device__ int compact_above(Src& src, u64 thr, Entry* list, int cap, SelShared*
 }
 
 // Returns m = number of selected entries (<= K); list[0..m) holds them best-first.
-// Requirements: blockDim.x multiple of 32; cap >= K, cap a power of two; direct_cap <= cap;
-// hist has SEL_BINS ints; list has cap + SEL_RANK_MAX entries.
+// defer_max > 0: when at most defer_max survivors remain they are returned UNSORTED (*sorted = false,
+// return value = their number, possibly > K) so that the caller can sort them elsewhere.
 template <class Src>
-__device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int direct_cap, int* hist, SelShared* sh) {
+__device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int direct_cap, int* hist, SelShared* sh,
+                                 int defer_max = 0, bool* sorted = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const u64 M = src.margin();
   if (K > cap) K = cap;
@@ -499,6 +500,12 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
   // ---- D: exact sort of the survivors
   src.set_floor(0ull);
   if (m > cap) m = cap;
+  if (sorted) *sorted = true;
+  if (defer_max > 0 && m <= defer_max) {
+    *sorted = false;
+    __syncthreads();
+    return m;
+  }
   if (m <= SEL_RANK_MAX) {
     rank_sort_entries(src, list, list + cap, m);
   } else {
