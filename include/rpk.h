@@ -161,7 +161,9 @@ RPK_EXPORT int rpk_gram_dense_u16(rpk_ctx* ctx, int64_t I, int64_t Kd, const uin
 
 /* Device time (CUDA events on the context's stream) of the dominant kernels of the last calls:
  * out_ms[0] = tensor-core Gram of the last fit, out_ms[1] = sparse fit kernels of the last fit,
- * out_ms[2] = scoring kernel of the last predict; -1 where the kernel did not run.  Synchronises. */
+ * out_ms[2] = scoring kernel of the last predict; -1 where the kernel did not run;
+ * out_ms[3] = users the last fit routed to the tensor cores, out_ms[4] = that number padded to the MMA
+ * k-block.  out_ms must hold 5 doubles.  Synchronises. */
 RPK_EXPORT int rpk_last_timings(rpk_ctx* ctx, double* out_ms);
 
 /* Fit configuration.  dense_users: how many of the users with the longest histories go through the

@@ -175,6 +175,8 @@ int rpk_last_timings(rpk_ctx* ctx, double* out_ms) {
       out_ms[k] = ms;
     }
   }
+  out_ms[3] = ctx->last_dense_users;
+  out_ms[4] = ctx->last_dense_kd;
   RPK_API_END(ctx)
 }
 

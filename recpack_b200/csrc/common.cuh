@@ -57,6 +57,8 @@ struct rpk_ctx {
   // CUDA events around the dominant kernels of the last fit / predict (rpk_last_timings)
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid[3] = {false, false, false};
+  int last_dense_users = 0;  // users routed to the tensor-core Gram by the last fit
+  int last_dense_kd = 0;     // ... padded to the MMA k-block
   void ev_record(int k) {
     if (!ev[k]) RPK_CUDA(cudaEventCreate(&ev[k]));
     RPK_CUDA(cudaEventRecord(ev[k], stream));

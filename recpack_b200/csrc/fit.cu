@@ -824,6 +824,8 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
   const int* n_sparse = n;  // per-item user counts on the sparse path
   c->ev_valid[0] = false;
   c->ev_valid[1] = false;
+  c->last_dense_users = hmax;
+  c->last_dense_kd = hmax > 0 ? (int)(((int64_t)hmax + 127) / 128 * 128) : 0;
   if (hmax > 0) {
     const int64_t kd_pad = ((int64_t)hmax + 127) / 128 * 128;
     int* thr_cnt = c->buf<int>("fit_dense_thr", 4);

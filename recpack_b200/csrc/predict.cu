@@ -238,13 +238,27 @@ struct ScoreSrc {
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return 0ull; }
   __device__ __forceinline__ void set_floor(u64 thr) { floor_ = thr; }
-  __device__ __forceinline__ void stats(SelShared* sh) const { generic_stats(*this, sh); }
+  // Selection key: the score rounded toward zero to float, as a bit pattern.  The map is monotone
+  // (a <= b => key(a) <= key(b)), so margin() = 0 is right: equal keys are told apart by cmp3 on the exact
+  // score.  Scores lie in [1, 2^53), which gives constant key bounds -- no pass over the slots is needed.
+  __device__ __forceinline__ static u64 key_of(u64 score) { return (u64)__float_as_uint(__ull2float_rz(score)); }
+  __device__ __forceinline__ void stats(SelShared* sh) const {
+    if (threadIdx.x == 0) {
+      sh->count = ns;  // upper bound of the candidate count (slots can be empty or masked)
+      sh->kmin = (u64)__float_as_uint(1.0f);
+      sh->kmax = (u64)__float_as_uint(9007199254740992.0f);
+    }
+    __syncthreads();
+  }
   template <class F>
   __device__ __forceinline__ void visit(F f, int stride) const {
     for (int slot = threadIdx.x * stride; slot < ns; slot += blockDim.x * stride) {
       const int j = touched ? touched[slot] : slot;
-      const u64 k = score_at(j);
-      if (k != 0 && k >= floor_) f(slot, k);
+      const u64 sc = score_at(j);
+      if (sc != 0) {
+        const u64 k = key_of(sc);
+        if (k >= floor_) f(slot, k);
+      }
     }
   }
   template <class F>
@@ -299,6 +313,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
   unsigned* acc_hi = acc_lo + p.R;
   int* touched = reinterpret_cast<int*>(acc64 + p.R);
   __shared__ int s_work;
+  __shared__ int s_next;      // work item fetched ahead (its user row is warmed in L2 on the way)
   __shared__ u64 s_bound;
   __shared__ int s_cnt;
   __shared__ int s_ntouched;
@@ -306,9 +321,16 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int total = p.U * p.P;
   for (int s = tid; s < p.R; s += nt) acc64[s] = 0ull;
+  if (tid == 0) s_next = atomicAdd(p.queue, 1);
   for (;;) {
     if (tid == 0) {
-      s_work = atomicAdd(p.queue, 1);
+      s_work = s_next;
+      const int nx = atomicAdd(p.queue, 1);
+      s_next = nx;
+      if (nx < total) {  // touch the next user's row pointers so that they are in cache when needed
+        const int un = p.order[nx / p.P];
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.indptr + un) : "memory");
+      }
       s_bound = 0;
       s_cnt = 0;
       s_ntouched = 0;

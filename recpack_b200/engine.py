@@ -122,9 +122,10 @@ class Engine:
 
     def last_timings(self):
         """dict(gram_tc_ms, fit_rows_ms, predict_ms): device time of the dominant kernels of the last calls."""
-        out = np.zeros(3, dtype=np.float64)
+        out = np.zeros(5, dtype=np.float64)
         self._check(self._lib.rpk_last_timings(self._h, _addr(out)))
-        return {"gram_tc_ms": float(out[0]), "fit_rows_ms": float(out[1]), "predict_ms": float(out[2])}
+        return {"gram_tc_ms": float(out[0]), "fit_rows_ms": float(out[1]), "predict_ms": float(out[2]),
+                "dense_users": int(out[3]), "dense_kd": int(out[4])}
 
     def fit_config(self, dense_users: int = -1):
         self._check(self._lib.rpk_fit_config(self._h, int(dense_users)))
