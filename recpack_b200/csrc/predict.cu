@@ -13,6 +13,8 @@
 // result independent of the order in which the atomics land, so the top-N lists are deterministic.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "internal.h"
 #include "prims.cuh"
@@ -286,7 +288,7 @@ struct PredParams {
   const u64* m_ent;
   const int* m_seg;
   const unsigned* m_rowmax;
-  const int* order;
+  const int4* work_tab;  // {user, history length, row start lo, hi} in processing order
   int U, P, R, I, N, mask, mode, force_wide;
   int cap, direct_cap, tcap;
   int* queue;
@@ -327,10 +329,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       s_work = s_next;
       const int nx = atomicAdd(p.queue, 1);
       s_next = nx;
-      if (nx < total) {  // touch the next user's row pointers so that they are in cache when needed
-        const int un = p.order[nx / p.P];
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.indptr + un) : "memory");
-      }
+      if (nx < total) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.work_tab + nx / p.P) : "memory");
       s_bound = 0;
       s_cnt = 0;
       s_ntouched = 0;
@@ -339,12 +338,13 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
     const int w = s_work;
     __syncthreads();
     if (w >= total) break;
-    const int u = p.order[w / p.P];
+    const int4 rec = p.work_tab[w / p.P];
+    const int u = rec.x;
     const int pass = w % p.P;
     const int r0 = pass * p.R;
     const int ns = min(p.R, p.I - r0);
-    const int64_t xb = p.indptr[u];
-    const int d = (int)(p.indptr[u + 1] - xb);
+    const int64_t xb = ((int64_t)(unsigned)rec.z) | ((int64_t)rec.w << 32);
+    const int d = rec.y;
     const int64_t slot_out = (int64_t)u * p.P + pass;
     if (d == 0) {  // user without history: empty prediction row (algorithms/base.py:123-127)
       if (p.mode == PRED_TOPN) {
@@ -374,89 +374,97 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
     // ---- accumulate: history rows are dealt to the warps in chunks (<= 32 rows, one per lane, so that the
     //      segment bounds are fetched in parallel); rows are added in groups of LIMB_CHUNK so that the low
     //      limb (20 bits per term) cannot overflow 32 bits between normalisations
-    for (int c0 = 0; c0 < d; c0 += LIMB_CHUNK) {
-      const int c1 = min(d, c0 + LIMB_CHUNK);
-      int chunk = (c1 - c0 + nwarps - 1) / nwarps;
-      chunk = chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk);
-      for (int base = c0 + warp * chunk; base < c1; base += nwarps * chunk) {
-        const int nvalid = min(chunk, c1 - base);
-        int64_t beg = 0;
-        int len = 0;
-        if (lane < nvalid) {
-          const int i = p.indices[xb + base + lane];
-          const int* sg = p.m_seg + (int64_t)i * (p.P + 1) + pass;
-          const int s0 = sg[0];
-          beg = p.m_ptr[i] + s0;
-          len = sg[1] - s0;
-        }
-        // add one entry to the accumulators; in sparse mode record the slot on its first touch
-        auto add_entry = [&](u64 ent) {
-          bool first = false;
-          int j = 0;
-          if (ent != 0ull) {
-            j = (int)(ent >> 40) - r0;
-            const u64 q = ent & Q_MASK40;
-            if (wide) {
-              atomicAdd(&acc64[j], q);
-            } else {
-              const unsigned old = atomicAdd(&acc_lo[j], (unsigned)q & LIMB_MASK);
-              atomicAdd(&acc_hi[j], (unsigned)(q >> LIMB_BITS));
-              first = old == 0u;
-            }
+    // the loop is instantiated for the three accumulator modes so that the hot path carries no mode tests
+    auto accumulate = [&](auto wide_c, auto track_c) {
+      constexpr bool WIDE = decltype(wide_c)::value;
+      constexpr bool TRACK = decltype(track_c)::value;
+      for (int c0 = 0; c0 < d; c0 += LIMB_CHUNK) {
+        const int c1 = min(d, c0 + LIMB_CHUNK);
+        int chunk = (c1 - c0 + nwarps - 1) / nwarps;
+        chunk = chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk);
+        for (int base = c0 + warp * chunk; base < c1; base += nwarps * chunk) {
+          const int nvalid = min(chunk, c1 - base);
+          int64_t beg = 0;
+          int len = 0;
+          if (lane < nvalid) {
+            const int i = p.indices[xb + base + lane];
+            const int* sg = p.m_seg + (int64_t)i * (p.P + 1) + pass;
+            const int s0 = sg[0];
+            beg = p.m_ptr[i] + s0;
+            len = sg[1] - s0;
           }
-          if (track) {
-            const unsigned m = __ballot_sync(0xffffffffu, first);
-            if (m) {
-              const int leader = __ffs(m) - 1;
-              int pos = 0;
-              if (lane == leader) pos = atomicAdd(&s_ntouched, __popc(m));
-              pos = __shfl_sync(0xffffffffu, pos, leader);
-              if (first) {
-                const int my = pos + __popc(m & ((1u << lane) - 1u));
-                if (my < p.tcap) touched[my] = j;
+          // add one entry to the accumulators; in sparse mode record the slot on its first touch
+          auto add_entry = [&](u64 ent) {
+            bool first = false;
+            int j = 0;
+            if (ent != 0ull) {
+              j = (int)(ent >> 40) - r0;
+              const u64 q = ent & Q_MASK40;
+              if (WIDE) {
+                atomicAdd(&acc64[j], q);
+              } else {
+                const unsigned old = atomicAdd(&acc_lo[j], (unsigned)q & LIMB_MASK);
+                atomicAdd(&acc_hi[j], (unsigned)(q >> LIMB_BITS));
+                first = old == 0u;
+              }
+            }
+            if (TRACK) {
+              const unsigned m = __ballot_sync(0xffffffffu, first);
+              if (m) {
+                const int leader = __ffs(m) - 1;
+                int pos = 0;
+                if (lane == leader) pos = atomicAdd(&s_ntouched, __popc(m));
+                pos = __shfl_sync(0xffffffffu, pos, leader);
+                if (first) {
+                  const int my = pos + __popc(m & ((1u << lane) - 1u));
+                  if (my < p.tcap) touched[my] = j;
+                }
+              }
+            }
+          };
+          // rows are taken four at a time: the first 96 entries of each (a row segment rarely has more) are
+          // loaded up front -- 12 independent loads in flight per lane -- and only then added
+          for (int l0 = 0; l0 < nvalid; l0 += 4) {
+            u64 ent[4][3];
+            int64_t bq[4];
+            int nq[4];
+  #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int l = l0 + q;  // lanes >= nvalid hold len = 0
+              bq[q] = __shfl_sync(0xffffffffu, beg, l & 31);
+              nq[q] = l < nvalid ? __shfl_sync(0xffffffffu, len, l & 31) : 0;
+  #pragma unroll
+              for (int it = 0; it < 3; ++it) {
+                const int e = it * 32 + lane;
+                ent[q][it] = e < nq[q] ? p.m_ent[bq[q] + e] : 0ull;
+              }
+            }
+  #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+  #pragma unroll
+              for (int it = 0; it < 3; ++it)
+                if (it * 32 < nq[q]) add_entry(ent[q][it]);
+              for (int e0 = 96; e0 < nq[q]; e0 += 32) {
+                const int e = e0 + lane;
+                add_entry(e < nq[q] ? p.m_ent[bq[q] + e] : 0ull);
               }
             }
           }
-        };
-        // rows are taken four at a time: the first 96 entries of each (a row segment rarely has more) are
-        // loaded up front -- 12 independent loads in flight per lane -- and only then added
-        for (int l0 = 0; l0 < nvalid; l0 += 4) {
-          u64 ent[4][3];
-          int64_t bq[4];
-          int nq[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int l = l0 + q;  // lanes >= nvalid hold len = 0
-            bq[q] = __shfl_sync(0xffffffffu, beg, l & 31);
-            nq[q] = l < nvalid ? __shfl_sync(0xffffffffu, len, l & 31) : 0;
-#pragma unroll
-            for (int it = 0; it < 3; ++it) {
-              const int e = it * 32 + lane;
-              ent[q][it] = e < nq[q] ? p.m_ent[bq[q] + e] : 0ull;
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-#pragma unroll
-            for (int it = 0; it < 3; ++it)
-              if (it * 32 < nq[q]) add_entry(ent[q][it]);
-            for (int e0 = 96; e0 < nq[q]; e0 += 32) {
-              const int e = e0 + lane;
-              add_entry(e < nq[q] ? p.m_ent[bq[q] + e] : 0ull);
-            }
-          }
-        }
-      }
-      __syncthreads();
-      if (!wide && c1 < d) {  // carry the low limb into the high limb before the next chunk
-        for (int s = tid; s < ns; s += nt) {
-          unsigned l = acc_lo[s];
-          acc_hi[s] += l >> LIMB_BITS;
-          acc_lo[s] = l & LIMB_MASK;
         }
         __syncthreads();
+        if (!WIDE && c1 < d) {  // carry the low limb into the high limb before the next chunk
+          for (int s = tid; s < ns; s += nt) {
+            unsigned l = acc_lo[s];
+            acc_hi[s] += l >> LIMB_BITS;
+            acc_lo[s] = l & LIMB_MASK;
+          }
+          __syncthreads();
+        }
       }
-    }
+    };
+    if (wide) accumulate(std::true_type{}, std::false_type{});
+    else if (track) accumulate(std::false_type{}, std::true_type{});
+    else accumulate(std::false_type{}, std::false_type{});
     const int n_touched = s_ntouched;
     const bool sparse = track && n_touched <= p.tcap;
     if (p.mask) {  // pipelines/pipeline.py:174-175 -- before the truncation to N
@@ -567,6 +575,18 @@ __global__ void k_predict_finalize(const int* __restrict__ part_idx, const u64* 
   }
 }
 
+// Work table in processing order: one 16-byte record per user {user, history length, row start}, so that a
+// CTA needs a single load (prefetched one item ahead) to start on a user.
+__global__ void k_build_work_tab(const int* __restrict__ order, const int64_t* __restrict__ indptr, int64_t U,
+                                 int4* __restrict__ tab) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= U) return;
+  const int u = order[k];
+  const int64_t xb = indptr[u];
+  const int64_t d = indptr[u + 1] - xb;
+  tab[k] = make_int4(u, (int)d, (int)(xb & 0xffffffffll), (int)(xb >> 32));
+}
+
 __global__ void k_row_lengths(const int64_t* __restrict__ indptr, int64_t U, u64* __restrict__ work) {
   int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (u < U) work[u] = (u64)(indptr[u + 1] - indptr[u]);
@@ -660,7 +680,10 @@ static void launch_predict(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_
   RPK_LAUNCH_CHECK(c);
   k_bucket_scatter<<<ceil_div(U, 256), 256, 0, st>>>(work, 0, U, boff, order);
   RPK_LAUNCH_CHECK(c);
-  pp.order = order;
+  int4* tab = c->buf<int4>("p_work_tab", (size_t)U);
+  k_build_work_tab<<<ceil_div(U, 256), 256, 0, st>>>(order, indptr, U, tab);
+  RPK_LAUNCH_CHECK(c);
+  pp.work_tab = tab;
   pp.queue = queue;
   RPK_CUDA(cudaFuncSetAttribute(k_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
   int occ = 0;
