@@ -144,6 +144,15 @@ __global__ void k_item_extremes(const int* __restrict__ n, const double* __restr
   }
 }
 
+// code[j] = round(12 * log2(n_j)) clamped to [0, 255]: 1/n_j to within half a code step.
+__global__ void k_pop_code(const int* __restrict__ n, unsigned char* __restrict__ code, int64_t I) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < I) {
+    const int v = n[j] > 0 ? __float2int_rn(12.0f * log2f((float)n[j])) : 0;
+    code[j] = (unsigned char)(v < 0 ? 0 : (v > 255 ? 255 : v));
+  }
+}
+
 __global__ void k_recip_f32(const int* __restrict__ n, float* __restrict__ rnf, int64_t I) {
   int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < I) rnf[j] = n[j] > 0 ? __frcp_rn((float)n[j]) : 0.f;
@@ -179,16 +188,24 @@ struct SimKey {
   const double* pw;
   const int* nmax;      // largest item popularity (device scalar)
   const double* pwmin;  // smallest item_pow among seen items (device scalar, mode 2)
+  // cosine, inside k_fit_rows: 1/n_j rounded to a 12-steps-per-octave code (1 byte per item, kept in shared
+  // memory) so that the selection scans need no global load per candidate; null: use rnf
+  const unsigned char* code;
+  const float* code_tab;  // [256] code -> 2^(-code/12)
   int mode;  // 0 cosine, 1 conditional probability, 2 conditional probability with pop_discount
 
-  __device__ __forceinline__ u64 margin() const { return mode == 0 ? 32ull : 0ull; }
+  // Two keys can be mis-ordered only if their bit patterns differ by at most margin(): a few ulp with the
+  // exact reciprocal; with the coded one each key is off by up to half a code step (2^(1/24)), so two keys
+  // up to 2^(1/12) - 1 = 5.95 % apart can swap: 0.0595 * 2^24 patterns at most -> 2^20
+  __device__ __forceinline__ u64 margin() const { return mode != 0 ? 0ull : (code ? (1ull << 20) : 32ull); }
 
   // cosine: approximate fp32 key c^2/n_j (a few ulp of error, covered by margin()); the exact order is
   // restored by cmp3 on (c, n_j).  conditional probability: the exact float64 key itself.
   __device__ __forceinline__ u64 akey(int c, int j) const {
     if (mode == 0) {
       const float a = (float)c;
-      return (u64)__float_as_uint(__fmul_rn(__fmul_rn(a, a), rnf[j]));
+      const float r = code ? code_tab[code[j]] : rnf[j];
+      return (u64)__float_as_uint(__fmul_rn(__fmul_rn(a, a), r));
     }
     if (mode == 1) return (u64)__double_as_longlong((double)c);
     return (u64)__double_as_longlong(__dmul_rn((double)c, pw[j]));
@@ -198,7 +215,7 @@ struct SimKey {
     if (mode == 0) {
       const float a = (float)cmax;
       hi = (u64)__float_as_uint(__fmul_rn(a, a));
-      lo = (u64)__float_as_uint(__frcp_rn((float)nmax[0]));
+      lo = (u64)__float_as_uint(__frcp_rn((float)nmax[0]) * 0.94f);  // 6 % slack for the coded reciprocal
     } else if (mode == 1) {
       hi = (u64)__double_as_longlong((double)cmax);
       lo = (u64)__double_as_longlong(1.0);
@@ -396,6 +413,7 @@ struct FitParams {
   int* out_idx;
   int* out_cnt;
   int* out_len;
+  const unsigned char* pop_code;  // global [I], null: no coded reciprocals
   int defer_max;   // > 0: rows with at most this many survivors are sorted by k_fit_sort_rows instead
   int* scr_idx;    // [rows x defer_max] unsorted survivors (item, count)
   int* scr_cnt;
@@ -410,9 +428,19 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
   SelShared* sh = reinterpret_cast<SelShared*>(hist + SEL_BINS);
   unsigned* cnt = reinterpret_cast<unsigned*>(smem + sel_smem_bytes(p.cap));
   __shared__ int s_work;
+  __shared__ float s_code_tab[256];
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int total = p.nrows_dev[0] * p.P;
+  // coded item popularities for the selection keys: one byte per item behind the counters, loaded once
+  if (p.pop_code) {
+    unsigned char* code_s = reinterpret_cast<unsigned char*>(cnt) + (size_t)p.R * (PACK16 ? 2 : 4);
+    for (int j = tid; j < p.I; j += nt) code_s[j] = p.pop_code[j];
+    for (int t = tid; t < 256; t += nt) s_code_tab[t] = exp2f(-(float)t / 12.0f);
+    p.sk.code = code_s;
+    p.sk.code_tab = s_code_tab;
+    __syncthreads();
+  }
   for (;;) {
     if (tid == 0) s_work = atomicAdd(p.queue, 1);
     __syncthreads();
@@ -497,16 +525,44 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
             len = (int)(p.indptr[u + 1] - beg);
           }
           if (__shfl_sync(0xffffffffu, pf, 0) >= hi) break;
+          // software pipeline over the users of the batch: the first 128 indices of user l+1 are loaded
+          // while the counters of user l are updated
+          int jn[4] = {-1, -1, -1, -1};
+          int64_t bn = 0;
+          int sn = 0, en = 0;
+          auto fetch = [&](int l) {  // clip user l to [lo, hi) and issue its first loads
+            sn = 0;
+            en = 0;
+            if (l < 32) {
+              const unsigned pfl = __shfl_sync(0xffffffffu, pf, l);
+              const int n = __shfl_sync(0xffffffffu, len, l);
+              bn = __shfl_sync(0xffffffffu, beg, l);
+              if (pfl < hi) {
+                sn = lo > pfl ? (int)(lo - pfl) : 0;
+                en = (int)min((unsigned)n, hi - pfl);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int e = sn + lane + 32 * q;
+              jn[q] = e < en ? p.indices[bn + e] - r0 : -1;
+            }
+          };
+          fetch(0);
           for (int l = 0; l < 32; ++l) {
-            const unsigned pfl = __shfl_sync(0xffffffffu, pf, l);
-            if (pfl >= hi) break;
-            const int n = __shfl_sync(0xffffffffu, len, l);
-            const int64_t bb = __shfl_sync(0xffffffffu, beg, l);
-            const int s0 = lo > pfl ? (int)(lo - pfl) : 0;
-            const int e1 = (int)min((unsigned)n, hi - pfl);
-            // four index loads in flight per lane, then the four counter updates
-            for (int e = s0 + lane; e < e1; e += 128) {
-              int jj[4];
+            if (__shfl_sync(0xffffffffu, pf, l) >= hi) break;
+            int jj[4] = {jn[0], jn[1], jn[2], jn[3]};
+            const int64_t bb = bn;
+            const int s0 = sn, e1 = en;
+            fetch(l + 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (jj[q] >= 0) {
+                if (PACK16) atomicAdd(&cnt[jj[q] >> 1], 1u << ((jj[q] & 1) * 16));
+                else atomicAdd(&cnt[jj[q]], 1u);
+              }
+            // long histories: the rest, four loads in flight per lane
+            for (int e = s0 + 128 + lane; e < e1; e += 128) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) jj[q] = e + 32 * q < e1 ? p.indices[bb + e + 32 * q] - r0 : -1;
 #pragma unroll
@@ -876,6 +932,8 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     RPK_LAUNCH_CHECK(c);
     k_recip_f32<<<ceil_div(I, 256), 256, 0, st>>>(n, rnf, I);
     RPK_LAUNCH_CHECK(c);
+    k_pop_code<<<ceil_div(I, 256), 256, 0, st>>>(n, c->buf<unsigned char>("fit_pop_code", (size_t)I), I);
+    RPK_LAUNCH_CHECK(c);
   }
 
   Out<int32_t> o_idx, o_cnt, o_len;
@@ -913,11 +971,14 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     const int direct_cap = tiny ? K : std::min(cap, std::max(2 * K, 64));
     const size_t fixed = sel_smem_bytes(cap);
     RPK_REQUIRE((size_t)c->smem_max > fixed + 1024 + 4096, "K too large for shared memory");
-    const size_t avail = (size_t)c->smem_max - fixed - 1024;  // 1 KB slack for static shared memory
-    const SimKey sk{n, rnf, pw, nmax, reinterpret_cast<const double*>(pwmin), mode};
+    const size_t avail = (size_t)c->smem_max - fixed - 2048;  // 2 KB slack for static shared memory
+    const SimKey sk{n, rnf, pw, nmax, reinterpret_cast<const double*>(pwmin), nullptr, nullptr, mode};
+    // coded reciprocals (1 B per item in shared memory) when the catalogue leaves room for them
+    const bool use_code = mode == 0 && (size_t)I + 65536 < avail && U < ((int64_t)1 << 21);  // code 255 = 2.5M users
+    const size_t code_bytes = use_code ? (((size_t)I + 15) & ~(size_t)15) : 0;
 
     c->ev_record(2);
-    const int defer_max = std::min(cap, 512);
+    const int defer_max = cap;
     int* scr_idx = c->buf<int>("fit_scr_idx", (size_t)nrows * defer_max);
     int* scr_cnt = c->buf<int>("fit_scr_cnt", (size_t)nrows * defer_max);
     int* scr_len = c->buf<int>("fit_scr_len", (size_t)nrows);
@@ -926,12 +987,12 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     for (int wide = 0; wide < 2; ++wide) {
       // geometry: item-range passes so that the counters of one pass fit shared memory
       const int bytes_per_item = wide ? 4 : 2;
-      int64_t Rmax = (int64_t)(avail / bytes_per_item) & ~(int64_t)7;
+      int64_t Rmax = (int64_t)((avail - code_bytes) / bytes_per_item) & ~(int64_t)7;
       int P = (int)((I + Rmax - 1) / Rmax);
       if (P < 1) P = 1;
       if ((c->flags & DBG_MULTI_PASS) && P < 2 && I >= 16) P = 2;
       const int R = (int)(((I + P - 1) / P + 7) & ~(int64_t)7);
-      const size_t smem = fixed + (size_t)R * bytes_per_item;
+      const size_t smem = fixed + (size_t)R * bytes_per_item + code_bytes;
       const int nt = R >= 16384 ? 1024 : (R >= 4096 ? 512 : 256);
       const int64_t* usplit = nullptr;
       if (P > 1) {
@@ -976,6 +1037,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
       fp.out_cnt = part_cnt;
       fp.out_len = part_len;
       // rows written directly to the final arrays may defer their sort to k_fit_sort_rows
+      fp.pop_code = use_code ? c->get<unsigned char>("fit_pop_code") : nullptr;
       fp.defer_max = (P == 1 && !tiny) ? defer_max : 0;
       fp.scr_idx = scr_idx;
       fp.scr_cnt = scr_cnt;
