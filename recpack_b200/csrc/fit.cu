@@ -663,16 +663,12 @@ __global__ void __launch_bounds__(256) k_fit_merge(MergeParams p) {
 }
 
 // Sorts the unsorted survivors of a row (written by k_fit_rows) with the exact order and writes the K best.
-struct ListOrder {  // comparator-only "source" for the sort helpers
-  SimKey sk;
-  __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const { return sk.cmp3(a, b); }
-};
 struct SortParams {
   SimKey sk;
   const int* scr_idx;
   const int* scr_cnt;
   const int* scr_len;
-  int defer_max, K;
+  int defer_max, K, cap, direct_cap;
   int64_t nrows;
   int* out_idx;
   int* out_cnt;
@@ -681,27 +677,16 @@ struct SortParams {
 __global__ void __launch_bounds__(256) k_fit_sort_rows(SortParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   Entry* list = reinterpret_cast<Entry*>(smem);
+  int* hist = reinterpret_cast<int*>(smem + sel_list_bytes(p.cap));
+  SelShared* sh = reinterpret_cast<SelShared*>(hist + SEL_BINS);
   const int tid = threadIdx.x, nt = blockDim.x;
-  ListOrder ord{p.sk};
   for (int64_t row = blockIdx.x; row < p.nrows; row += gridDim.x) {
     const int m = p.scr_len[row];
     if (m < 0) continue;  // already final
-    int n2 = 2;
-    while (n2 < m) n2 <<= 1;
-    for (int t = tid; t < n2; t += nt) {
-      Entry e;
-      if (t < m) {
-        p.sk.entry(p.scr_cnt[row * p.defer_max + t], p.scr_idx[row * p.defer_max + t], e);
-      } else {
-        e.key = 0;
-        e.idx = SENTINEL_IDX;
-        e.aux = 0;
-      }
-      list[t] = e;
-    }
-    __syncthreads();
-    bitonic_sort_entries(ord, list, n2);
-    const int keep = m < p.K ? m : p.K;
+    // exact selection + sort of the survivors with the precise keys (exact reciprocal popularity): the same
+    // routine as everywhere else, now on a list of a few hundred entries, many rows per SM at once
+    PairListSrc src{p.sk, p.scr_idx + row * p.defer_max, p.scr_cnt + row * p.defer_max, m};
+    const int keep = block_select_topk(src, p.K, list, p.cap, p.direct_cap, hist, sh);
     for (int t = tid; t < p.K; t += nt) {
       p.out_idx[row * p.K + t] = t < keep ? list[t].idx : -1;
       p.out_cnt[row * p.K + t] = t < keep ? list[t].aux : 0;
@@ -1082,13 +1067,17 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
       sp.scr_len = scr_len;
       sp.defer_max = defer_max;
       sp.K = K;
+      sp.cap = std::max(256, next_pow2(2 * K));
+      sp.direct_cap = std::min(sp.cap, std::max(K + K / 4, 64));
       sp.nrows = nrows;
       sp.out_idx = o_idx.dev;
       sp.out_cnt = cnt_dev;
       sp.out_len = o_len.dev;
-      const size_t ssm = (size_t)defer_max * sizeof(Entry);
+      const size_t ssm = sel_smem_bytes(sp.cap);
       RPK_CUDA(cudaFuncSetAttribute(k_fit_sort_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
-      const int sgrid = (int)std::min<int64_t>(nrows, (int64_t)c->sm_count * 8);
+      int socc = 0;
+      RPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&socc, k_fit_sort_rows, 256, ssm));
+      const int sgrid = (int)std::min<int64_t>(nrows, (int64_t)c->sm_count * std::max(socc, 1));
       k_fit_sort_rows<<<sgrid, 256, ssm, st>>>(sp);
       RPK_LAUNCH_CHECK(c);
     }
