@@ -65,6 +65,9 @@ void rpk_destroy(rpk_ctx* ctx) {
     if (kv.second.p) cudaFree(kv.second.p);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->side_ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
   delete ctx;
 }
 

@@ -57,6 +57,9 @@ struct rpk_ctx {
   // CUDA events around the dominant kernels of the last fit / predict (rpk_last_timings)
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool ev_valid[3] = {false, false, false};
+  // side stream for the few heavy rows of a fit (runs next to the main row kernel)
+  cudaStream_t side = nullptr;
+  cudaEvent_t side_ev[2] = {nullptr, nullptr};
   int last_dense_users = 0;  // users routed to the tensor-core Gram by the last fit
   int last_dense_kd = 0;     // ... padded to the MMA k-block
   void ev_record(int k) {

@@ -969,7 +969,18 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     int* scr_len = c->buf<int>("fit_scr_len", (size_t)nrows);
     RPK_CUDA(cudaMemsetAsync(scr_len, 0xff, sizeof(int) * (size_t)nrows, st));  // -1: nothing deferred
     bool any_deferred = false;
-    for (int wide = 0; wide < 2; ++wide) {
+    // the handful of rows with >= 65536 users (32-bit counters) run on a side stream next to the main
+    // launch: they occupy a few SMs for a long time and would otherwise serialise behind it
+    if (!c->side) {
+      RPK_CUDA(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+      RPK_CUDA(cudaEventCreateWithFlags(&c->side_ev[0], cudaEventDisableTiming));
+      RPK_CUDA(cudaEventCreateWithFlags(&c->side_ev[1], cudaEventDisableTiming));
+    }
+    RPK_CUDA(cudaEventRecord(c->side_ev[0], st));
+    RPK_CUDA(cudaStreamWaitEvent(c->side, c->side_ev[0], 0));
+    cudaStream_t main_st = st;
+    for (int wide = 1; wide >= 0; --wide) {
+      cudaStream_t st = wide ? c->side : main_st;  // shadows the outer stream inside this launch
       // geometry: item-range passes so that the counters of one pass fit shared memory
       const int bytes_per_item = wide ? 4 : 2;
       int64_t Rmax = (int64_t)((avail - code_bytes) / bytes_per_item) & ~(int64_t)7;
@@ -1059,6 +1070,8 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
         RPK_LAUNCH_CHECK(c);
       }
     }
+    RPK_CUDA(cudaEventRecord(c->side_ev[1], c->side));
+    RPK_CUDA(cudaStreamWaitEvent(st, c->side_ev[1], 0));
     if (any_deferred) {
       SortParams sp;
       sp.sk = sk;
