@@ -8,6 +8,12 @@ rep, kre, cubin, mangled = sys.argv[1:5]
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 30
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", f"regex:{kre}"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
+import os
+want = os.environ.get("KERNEL_SUBSTR", "")
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and want in r[1]]
+first = starts[0]
+nxt = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and i > first]
+rows = rows[first:(nxt[0] if nxt else len(rows))]
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 hdr = rows[hi]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
