@@ -106,6 +106,11 @@ RPK_EXPORT int rpk_fit_item_counts(rpk_ctx* ctx, int32_t* out_counts, int64_t I)
  */
 RPK_EXPORT int rpk_model_load_topk(rpk_ctx* ctx, int64_t I, int K,
                         const int32_t* idx, const double* val, const int32_t* len);
+/* Every rpk_fit_topk increments the context's fit token.  When the last fit covered all item rows and
+ * produced values, its lists stay resident on the device and rpk_model_load_last_fit(token) builds the
+ * model from them without any host round trip; it fails when `token` is not the current one. */
+RPK_EXPORT int64_t rpk_fit_token(const rpk_ctx* ctx);
+RPK_EXPORT int rpk_model_load_last_fit(rpk_ctx* ctx, int64_t token);
 RPK_EXPORT int rpk_model_load_csr(rpk_ctx* ctx, int64_t I, int64_t nnz,
                        const int64_t* indptr, const int32_t* indices, const double* values);
 

@@ -114,7 +114,10 @@ class ItemSimilarityMatrixAlgorithm(Algorithm):
             return
         lists = getattr(self, "_fit_lists", None)
         if lists is not None and lists.get("key") == self._device_model_key():
-            engine.model_load_topk(S.shape[0], lists["idx"].shape[1], lists["idx"], lists["val"], lists["len"])
+            if lists.get("token") == (engine.nonce, engine.fit_token()):
+                engine.model_load_last_fit(lists["token"][1])  # the fit result is still on the device
+            else:
+                engine.model_load_topk(S.shape[0], lists["idx"].shape[1], lists["idx"], lists["val"], lists["len"])
         else:
             if not S.has_canonical_format:
                 S = S.copy()

@@ -115,6 +115,14 @@ int rpk_model_load_topk(rpk_ctx* ctx, int64_t I, int K, const int32_t* idx, cons
   RPK_API_END(ctx)
 }
 
+int64_t rpk_fit_token(const rpk_ctx* ctx) { return ctx ? ctx->lf_token : 0; }
+
+int rpk_model_load_last_fit(rpk_ctx* ctx, int64_t token) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_model_load_last_fit(ctx, token);
+  RPK_API_END(ctx)
+}
+
 int rpk_model_load_csr(rpk_ctx* ctx, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices,
                        const double* values) {
   RPK_API_BEGIN(ctx)

@@ -69,6 +69,13 @@ struct rpk_ctx {
 
   // ---- state of the last fit (device pointers into bufs)
   int64_t fit_I = 0;
+  // device copies of the last complete fit's lists (valid until the next fit on this context)
+  const int32_t* lf_idx = nullptr;
+  const double* lf_val = nullptr;
+  const int32_t* lf_len = nullptr;
+  int64_t lf_I = 0;
+  int lf_K = 0;
+  int64_t lf_token = 0;  // incremented by every fit
 
   // ---- loaded model
   int64_t m_I = 0;

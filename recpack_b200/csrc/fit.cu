@@ -39,7 +39,7 @@ __global__ void k_item_counts(const int* __restrict__ indices, int64_t nnz, int*
 // One warp per user: scatter the user id into the lists of its items; work[j] += d_u.
 __global__ void k_fill_csc(const int64_t* __restrict__ indptr, const int* __restrict__ indices, int64_t U,
                            const int* __restrict__ dense_slot, const int64_t* __restrict__ cscptr, int* __restrict__ cursor,
-                           int* __restrict__ csc_users, u64* __restrict__ work) {
+                           int* __restrict__ csc_users, u64* __restrict__ work, int item_begin, int item_end) {
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -49,6 +49,7 @@ __global__ void k_fill_csc(const int64_t* __restrict__ indptr, const int* __rest
     u64 d = (u64)(e - b);
     for (int64_t k = b + lane; k < e; k += 32) {
       int j = indices[k];
+      if (j < item_begin || j >= item_end) continue;  // only this shard's item rows are fitted
       int pos = atomicAdd(&cursor[j], 1);
       csc_users[cscptr[j] + pos] = (int)u;
       atomicAdd(&work[j], d);
@@ -93,11 +94,12 @@ __global__ void k_fill_dense(const int64_t* __restrict__ indptr, const int* __re
 // pref[k] = sum of the history lengths of the users listed before position k of the same item
 // (exclusive, in CSC order): lets the fit kernel cut a row's work into equal pieces per warp.
 __global__ void k_csc_prefix(const int64_t* __restrict__ cscptr, const int* __restrict__ csc_users,
-                             const int64_t* __restrict__ indptr, int64_t I, unsigned* __restrict__ pref) {
+                             const int64_t* __restrict__ indptr, int64_t item_begin, int64_t item_end,
+                             unsigned* __restrict__ pref) {
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = warp; i < I; i += nwarps) {
+  for (int64_t i = item_begin + warp; i < item_end; i += nwarps) {
     const int64_t b = cscptr[i], e = cscptr[i + 1];
     unsigned carry = 0;
     for (int64_t base = b; base < e; base += 128) {  // 4 users per lane: four independent loads in flight
@@ -899,13 +901,14 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
   RPK_LAUNCH_CHECK(c);
   if (nnz > 0 && U > 0) {
     int blocks = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
-    k_fill_csc<<<blocks, 256, 0, st>>>(indptr, indices, U, dense_slot, cscptr, cursor, csc_users, work);
+    k_fill_csc<<<blocks, 256, 0, st>>>(indptr, indices, U, dense_slot, cscptr, cursor, csc_users, work, (int)item_begin,
+                                        (int)item_end);
     RPK_LAUNCH_CHECK(c);
   }
   unsigned* pref = c->buf<unsigned>("fit_pref", (size_t)nnz);
   if (nnz > 0 && I > 0) {
-    int blocks = (int)std::min<int64_t>((I * 32 + 255) / 256, (int64_t)c->sm_count * 32);
-    k_csc_prefix<<<blocks, 256, 0, st>>>(cscptr, csc_users, indptr, I, pref);
+    int blocks = (int)std::min<int64_t>((nrows * 32 + 255) / 256, (int64_t)c->sm_count * 32);
+    k_csc_prefix<<<std::max(blocks, 1), 256, 0, st>>>(cscptr, csc_users, indptr, item_begin, item_end, pref);
     RPK_LAUNCH_CHECK(c);
   }
   int* nmax = c->buf<int>("fit_nmax", 4);
@@ -1100,6 +1103,16 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
       k_fit_values<<<ceil_div(nrows * K, 256), 256, 0, st>>>(o_idx.dev, cnt_dev, n, pw, mode, item_begin, nrows, K, o_val.dev);
       RPK_LAUNCH_CHECK(c);
     }
+  }
+  // remember where the lists live on the device: predict can load its model from them without a round trip
+  c->lf_token++;
+  c->lf_idx = nullptr;
+  if (item_begin == 0 && item_end == I && o_val.dev) {
+    c->lf_idx = o_idx.dev;
+    c->lf_val = o_val.dev;
+    c->lf_len = o_len.dev;
+    c->lf_I = I;
+    c->lf_K = K;
   }
   o_idx.finish(c);
   o_cnt.finish(c);

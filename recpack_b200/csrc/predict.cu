@@ -197,6 +197,11 @@ void run_model_load_topk(rpk_ctx* c, int64_t I, int K, const int32_t* idx_u, con
   c->m_max_len = K;
 }
 
+void run_model_load_last_fit(rpk_ctx* c, int64_t token) {
+  RPK_REQUIRE(c->lf_idx != nullptr && token == c->lf_token, "no complete fit result of that token is resident on the device");
+  run_model_load_topk(c, c->lf_I, c->lf_K, c->lf_idx, c->lf_val, c->lf_len);
+}
+
 void run_model_load_csr(rpk_ctx* c, int64_t I, int64_t nnz, const int64_t* indptr_u, const int32_t* indices_u,
                         const double* values_u) {
   model_common_begin(c, I);

@@ -60,6 +60,9 @@ class Engine:
             raise RpkError("rpk_create failed: " + self._lib.rpk_last_error(None).decode())
         self._h = h
         self.device = int(device)
+        import secrets
+
+        self.nonce = secrets.randbits(62)  # identifies this context in (picklable) fit tokens
 
     def close(self):
         if getattr(self, "_h", None):
@@ -141,6 +144,12 @@ class Engine:
     def model_load_topk(self, I, K, idx, val, ln):
         self._check(self._lib.rpk_model_load_topk(self._h, int(I), int(K), _addr(idx, np.int32), _addr(val, np.float64),
                                                   _addr(ln, np.int32)))
+
+    def fit_token(self) -> int:
+        return int(self._lib.rpk_fit_token(self._h))
+
+    def model_load_last_fit(self, token: int):
+        self._check(self._lib.rpk_model_load_last_fit(self._h, int(token)))
 
     def model_load_csr(self, I, indptr, indices, values):
         self._check(self._lib.rpk_model_load_csr(self._h, int(I), int(indices.shape[0]), _addr(indptr, np.int64),

@@ -74,6 +74,8 @@ class ItemKNN(TopKItemSimilarityMatrixAlgorithm):
         K = int(self.K)
         out = engine.fit_topk(U, I, indptr, indices, K, similarity=self.similarity, item_pow=item_pow)
         self._set_similarity_from_lists(out, I)
+        if not self.normalize_sim:  # the device copy holds the un-normalised values
+            self._fit_lists["token"] = (engine.nonce, engine.fit_token())
 
     def _set_similarity_from_lists(self, out, I):
         idx, val, ln = out["idx"], out["val"], out["len"]

@@ -436,3 +436,25 @@ def test_mid_shape_metrics_vs_reference_numbers():
         m.calculate(ytrue, pred)
         ref = float(g[f"{tag}{k}_value"])
         assert abs(m.value - ref) <= 1e-3 * ref, (tag, m.value, ref)
+
+
+def test_predict_after_pickle_and_model_reuse():
+    """The fitted estimator pickles (similarity_matrix_ is a plain scipy CSR); predict gives the same lists
+    whether the model comes from the device-resident fit result, from the host lists or from the CSR."""
+    import pickle
+
+    from recpack_b200 import ItemKNN
+    from recpack_b200.synth import synth_interactions
+
+    X = synth_interactions(400, 250, 6000, seed=9)
+    algo = ItemKNN(K=30, predict_topK=15, remove_history=True).fit(X)
+    a = algo.predict(X)                                   # model from the device-resident fit result
+    other = ItemKNN(K=7).fit(synth_interactions(50, 40, 300, seed=1))  # invalidates the resident result
+    b = algo.predict(X)                                   # model rebuilt from the host lists
+    clone = pickle.loads(pickle.dumps(algo))
+    clone._fit_lists = None
+    c = clone.predict(X)                                  # model from similarity_matrix_ (CSR path)
+    for other_pred in (b, c):
+        assert np.array_equal(a._rpk_topn[0], other_pred._rpk_topn[0])
+        assert np.array_equal(a.data, other_pred.data)
+    assert other.similarity_matrix_.shape == (40, 40)
