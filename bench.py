@@ -251,10 +251,13 @@ def run_gpu(args):
     nU = ue - ub
 
     rows = ie - ib
-    fit_out = {"idx": torch.empty((rows, K_NEIGH), dtype=torch.int32, device=dev), "cnt": None,
-               "val": torch.empty((rows, K_NEIGH), dtype=torch.float64, device=dev),
-               "len": torch.empty((rows,), dtype=torch.int32, device=dev)}
     exchange = ShardExchange(icut, K_NEIGH, dev, dist) if world > 1 else None
+    if world > 1:
+        fit_out = exchange.local_out()  # the fit writes straight into the all-gather send buffers
+    else:
+        fit_out = {"idx": torch.empty((rows, K_NEIGH), dtype=torch.int32, device=dev), "cnt": None,
+                   "val": torch.empty((rows, K_NEIGH), dtype=torch.float64, device=dev),
+                   "len": torch.empty((rows,), dtype=torch.int32, device=dev)}
     top_out = {"idx": torch.empty((nU, N_LIST), dtype=torch.int32, device=dev), "val": None,
                "len": torch.empty((nU,), dtype=torch.int32, device=dev)}
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # > L2 (126 MB)
@@ -267,8 +270,8 @@ def run_gpu(args):
         eng.fit_topk(U, I, t_ptr_full, t_idx_full, K_NEIGH, item_begin=ib, item_end=ie, out=fit_out)
         ev[1].record()
         if world > 1:
-            all_idx, all_val, all_len = exchange.gather(fit_out["idx"], fit_out["val"], fit_out["len"])
-            eng.model_load_topk(I, K_NEIGH, all_idx, all_val, all_len)
+            g_idx, g_val, g_len = exchange.gather_padded()
+            eng.model_load_topk_rows(I, K_NEIGH, g_idx.shape[0], g_idx, g_val, g_len, exchange.row_source())
         else:
             eng.model_load_topk(I, K_NEIGH, fit_out["idx"], fit_out["val"], fit_out["len"])
         ev[2].record()
@@ -429,8 +432,10 @@ def run_e2e(train, test_out, eng, steps):
         if s > 0:
             times.append(time.perf_counter() - t0)
     t = float(np.mean(times))
-    h2d = 2 * (train.nnz * 4 + (U + 1) * 8) + I * K_NEIGH * 12 + I * 4 + 2 * (U * N_LIST * 4 + U * 4 + test_out.nnz * 4 + (U + 1) * 8)
-    d2h = I * K_NEIGH * 16 + I * 4 + U * N_LIST * 12 + U * 4 + 2 * (U * 8 + 16)
+    # fit: X; predict: X again (the model is built from the device-resident fit result); metrics: lists + y_true, twice
+    h2d = 2 * (train.nnz * 4 + (U + 1) * 8) + 2 * (U * N_LIST * 4 + U * 4 + test_out.nnz * 4 + (U + 1) * 8)
+    # fit: idx + val + len; predict: idx + val + len; metrics: per-user values + sums, twice
+    d2h = I * K_NEIGH * 12 + I * 4 + U * N_LIST * 12 + U * 4 + 2 * (U * 8 + 16)
     return {"value": U / t, "unit": UNIT, "seconds": t, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ndcg10": float(v[0]), "recall20": float(v[1])}
 

@@ -106,6 +106,12 @@ RPK_EXPORT int rpk_fit_item_counts(rpk_ctx* ctx, int32_t* out_counts, int64_t I)
  */
 RPK_EXPORT int rpk_model_load_topk(rpk_ctx* ctx, int64_t I, int K,
                         const int32_t* idx, const double* val, const int32_t* len);
+/* As rpk_model_load_topk, for lists that live in a larger array (e.g. the all-gathered, padded per-rank
+ * shards of a multi-GPU fit): model row i is read from input row row_src[i] (int64[I]); the input arrays
+ * have rows_in rows. */
+RPK_EXPORT int rpk_model_load_topk_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in,
+                             const int32_t* idx, const double* val, const int32_t* len,
+                             const int64_t* row_src);
 /* Every rpk_fit_topk increments the context's fit token.  When the last fit covered all item rows and
  * produced values, its lists stay resident on the device and rpk_model_load_last_fit(token) builds the
  * model from them without any host round trip; it fails when `token` is not the current one. */

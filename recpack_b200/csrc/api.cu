@@ -115,6 +115,13 @@ int rpk_model_load_topk(rpk_ctx* ctx, int64_t I, int K, const int32_t* idx, cons
   RPK_API_END(ctx)
 }
 
+int rpk_model_load_topk_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in, const int32_t* idx, const double* val,
+                             const int32_t* len, const int64_t* row_src) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_model_load_topk_rows(ctx, I, K, rows_in, idx, val, len, row_src);
+  RPK_API_END(ctx)
+}
+
 int64_t rpk_fit_token(const rpk_ctx* ctx) { return ctx ? ctx->lf_token : 0; }
 
 int rpk_model_load_last_fit(rpk_ctx* ctx, int64_t token) {

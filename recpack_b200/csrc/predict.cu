@@ -40,7 +40,8 @@ __device__ __forceinline__ bool quantize(double v, u64& q) {
 
 // One CTA per row: pack (idx, q), sort by idx, write the row.
 __global__ void __launch_bounds__(256) k_model_from_topk(const int* __restrict__ idx, const double* __restrict__ val,
-                                                         const int* __restrict__ len, int K, int I,
+                                                         const int* __restrict__ len, const int64_t* __restrict__ row_src,
+                                                         int K, int I,
                                                          const int64_t* __restrict__ m_ptr, u64* __restrict__ m_ent,
                                                          unsigned* __restrict__ m_rowmax, int* __restrict__ flag) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -50,7 +51,8 @@ __global__ void __launch_bounds__(256) k_model_from_topk(const int* __restrict__
   int n2 = 2;
   while (n2 < K) n2 <<= 1;
   for (int i = blockIdx.x; i < I; i += gridDim.x) {
-    int m = len[i];
+    const int64_t src = row_src ? row_src[i] : (int64_t)i;  // where row i lives in the (gathered) input
+    int m = len[src];
     if (m > K) m = K;
     if (m < 0) m = 0;
     if (tid == 0) s_max = 0;
@@ -59,9 +61,9 @@ __global__ void __launch_bounds__(256) k_model_from_topk(const int* __restrict__
     for (int t = tid; t < n2; t += nt) {
       u64 packed = ~0ull;
       if (t < m) {
-        int j = idx[(int64_t)i * K + t];
+        int j = idx[src * K + t];
         u64 q = 1;
-        bool ok = quantize(val[(int64_t)i * K + t], q);
+        bool ok = quantize(val[src * K + t], q);
         if (!ok || j < 0 || j >= I) atomicOr(flag, 1);
         packed = ((u64)(unsigned)j << 40) | (q & Q_MASK40);
         lmax = max(lmax, (unsigned)(q >> LIMB_BITS) + 1u);
@@ -144,6 +146,11 @@ __global__ void k_model_seg(const int64_t* __restrict__ m_ptr, const u64* __rest
   seg[t] = (int)(lo - b);
 }
 
+__global__ void k_gather_len(const int* __restrict__ len, const int64_t* __restrict__ row_src, int64_t I, int* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < I) out[i] = len[row_src[i]];
+}
+
 static void model_common_begin(rpk_ctx* c, int64_t I) {
   RPK_REQUIRE(I >= 0 && I < ((int64_t)1 << 24), "item count must be below 2^24");
   c->m_I = I;
@@ -166,26 +173,37 @@ static void model_check_flag(rpk_ctx* c) {
   }
 }
 
-void run_model_load_topk(rpk_ctx* c, int64_t I, int K, const int32_t* idx_u, const double* val_u, const int32_t* len_u) {
+// rows_in: number of rows of the input arrays (>= I when row_src maps model rows into a larger, e.g.
+// all-gathered, array); row_src: int64[I] source row of every model row, or null for the identity.
+void run_model_load_topk_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, const int32_t* idx_u, const double* val_u,
+                              const int32_t* len_u, const int64_t* row_src_u) {
   RPK_REQUIRE(K >= 1 && K <= 4096, "K must be in [1, 4096]");
+  RPK_REQUIRE(rows_in >= I || row_src_u, "fewer input rows than items");
   model_common_begin(c, I);
   cudaStream_t st = c->stream;
-  const int32_t* idx = stage_in(c, idx_u, (size_t)I * K, "m_in_idx");
-  const double* val = stage_in(c, val_u, (size_t)I * K, "m_in_val");
-  const int32_t* len = stage_in(c, len_u, (size_t)I, "m_in_len");
+  const int32_t* idx = stage_in(c, idx_u, (size_t)rows_in * K, "m_in_idx");
+  const double* val = stage_in(c, val_u, (size_t)rows_in * K, "m_in_val");
+  const int32_t* len = stage_in(c, len_u, (size_t)rows_in, "m_in_len");
+  const int64_t* row_src = row_src_u ? stage_in(c, row_src_u, (size_t)I, "m_in_rowsrc") : nullptr;
   int64_t* m_ptr = c->buf<int64_t>("m_ptr", (size_t)I + 1);
-  k_scan_i32_i64<<<1, 1024, 0, st>>>(len, m_ptr, I);
-  RPK_LAUNCH_CHECK(c);
-  // row lengths are clamped to K inside the kernel; reject inconsistent input up front via total size
-  u64* m_ent = c->buf<u64>("m_ent", (size_t)I * K);
-  unsigned* m_rowmax = c->buf<unsigned>("m_rowmax", (size_t)I);
   int* m_len = c->buf<int>("m_len", (size_t)I);
   if (I > 0) {
-    RPK_CUDA(cudaMemcpyAsync(m_len, len, sizeof(int) * (size_t)I, cudaMemcpyDeviceToDevice, st));
+    if (row_src) {
+      k_gather_len<<<ceil_div(I, 256), 256, 0, st>>>(len, row_src, I, m_len);
+      RPK_LAUNCH_CHECK(c);
+    } else {
+      RPK_CUDA(cudaMemcpyAsync(m_len, len, sizeof(int) * (size_t)I, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  k_scan_i32_i64<<<1, 1024, 0, st>>>(m_len, m_ptr, I);
+  RPK_LAUNCH_CHECK(c);
+  u64* m_ent = c->buf<u64>("m_ent", (size_t)I * K);
+  unsigned* m_rowmax = c->buf<unsigned>("m_rowmax", (size_t)I);
+  if (I > 0) {
     int n2 = 2;
     while (n2 < K) n2 <<= 1;
     const int grid = (int)std::min<int64_t>(I, (int64_t)c->sm_count * 16);
-    k_model_from_topk<<<grid, 128, (size_t)n2 * sizeof(u64), st>>>(idx, val, len, K, (int)I, m_ptr, m_ent, m_rowmax,
+    k_model_from_topk<<<grid, 128, (size_t)n2 * sizeof(u64), st>>>(idx, val, len, row_src, K, (int)I, m_ptr, m_ent, m_rowmax,
                                                                   c->get<int>("m_flag"));
     RPK_LAUNCH_CHECK(c);
   }
@@ -195,6 +213,10 @@ void run_model_load_topk(rpk_ctx* c, int64_t I, int K, const int32_t* idx_u, con
   RPK_REQUIRE(total >= 0 && total <= I * (int64_t)K, "similarity model: row lengths exceed K");
   c->m_nnz = total;
   c->m_max_len = K;
+}
+
+void run_model_load_topk(rpk_ctx* c, int64_t I, int K, const int32_t* idx_u, const double* val_u, const int32_t* len_u) {
+  run_model_load_topk_rows(c, I, K, I, idx_u, val_u, len_u, nullptr);
 }
 
 void run_model_load_last_fit(rpk_ctx* c, int64_t token) {

@@ -51,19 +51,40 @@ class ShardExchange:
         self.all_val = mk((I, K), torch.float64, 0)
         self.all_len = mk((I,), torch.int32, 0)
 
+    def local_out(self):
+        """Views of this rank's send buffers shaped like its fit output: pass them as `out=` of the fit."""
+        rows = self.cuts[self.rank + 1] - self.cuts[self.rank]
+        return {"idx": self.p_idx[:rows], "cnt": None, "val": self.p_val[:rows], "len": self.p_len[:rows]}
+
+    def row_source(self):
+        """int64[I]: row of the gathered [world * maxrows, K] arrays that holds item row i."""
+        if getattr(self, "_row_src", None) is None:
+            import torch
+
+            src = np.empty(self.cuts[-1], dtype=np.int64)
+            for r in range(self.world):
+                b, e = self.cuts[r], self.cuts[r + 1]
+                src[b:e] = r * self.maxrows + np.arange(e - b)
+            self._row_src = torch.from_numpy(src).to(self.g_idx.device)
+        return self._row_src
+
+    def gather_padded(self):
+        """All-gather of the send buffers (filled through local_out()).  Returns the padded arrays
+        ([world * maxrows, K], [world * maxrows]) -- rpk_model_load_topk_rows reads them through row_source()."""
+        self.dist.all_gather_into_tensor(self.g_idx.view(-1, self.K), self.p_idx)
+        self.dist.all_gather_into_tensor(self.g_val.view(-1, self.K), self.p_val)
+        self.dist.all_gather_into_tensor(self.g_len.view(-1), self.p_len)
+        return self.g_idx.view(-1, self.K), self.g_val.view(-1, self.K), self.g_len.view(-1)
+
     def gather(self, idx, val, ln):
-        """idx/val/ln: this rank's rows (cuts[rank]..cuts[rank+1]).  Returns the full arrays."""
+        """idx/val/ln: this rank's rows (cuts[rank]..cuts[rank+1]).  Returns the full, unpadded arrays."""
         rows = self.cuts[self.rank + 1] - self.cuts[self.rank]
         self.p_idx[:rows].copy_(idx)
         self.p_val[:rows].copy_(val)
         self.p_len[:rows].copy_(ln)
-        # concatenated (2-D / 1-D) views: the layout both NCCL and gloo accept
-        self.dist.all_gather_into_tensor(self.g_idx.view(-1, self.K), self.p_idx)
-        self.dist.all_gather_into_tensor(self.g_val.view(-1, self.K), self.p_val)
-        self.dist.all_gather_into_tensor(self.g_len.view(-1), self.p_len)
-        for r in range(self.world):
-            b, e = self.cuts[r], self.cuts[r + 1]
-            self.all_idx[b:e].copy_(self.g_idx[r, : e - b])
-            self.all_val[b:e].copy_(self.g_val[r, : e - b])
-            self.all_len[b:e].copy_(self.g_len[r, : e - b])
+        g_idx, g_val, g_len = self.gather_padded()
+        src = self.row_source()
+        self.all_idx.copy_(g_idx[src])
+        self.all_val.copy_(g_val[src])
+        self.all_len.copy_(g_len[src])
         return self.all_idx, self.all_val, self.all_len

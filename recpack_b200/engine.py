@@ -145,6 +145,10 @@ class Engine:
         self._check(self._lib.rpk_model_load_topk(self._h, int(I), int(K), _addr(idx, np.int32), _addr(val, np.float64),
                                                   _addr(ln, np.int32)))
 
+    def model_load_topk_rows(self, I, K, rows_in, idx, val, ln, row_src):
+        self._check(self._lib.rpk_model_load_topk_rows(self._h, int(I), int(K), int(rows_in), _addr(idx, np.int32),
+                                                       _addr(val, np.float64), _addr(ln, np.int32), _addr(row_src, np.int64)))
+
     def fit_token(self) -> int:
         return int(self._lib.rpk_fit_token(self._h))
 

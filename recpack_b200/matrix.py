@@ -38,12 +38,23 @@ def binary_structure(X: csr_matrix):
     (the normal case) is passed through without a copy."""
     if not isinstance(X, csr_matrix):
         X = csr_matrix(X)
-    if X.nnz and not np.all(X.data):
-        X = X.copy()
-        X.eliminate_zeros()
-    if not X.has_canonical_format:
-        X = X.copy()
-        X.sum_duplicates()
-    indptr = np.ascontiguousarray(X.indptr, dtype=np.int64)
-    indices = np.ascontiguousarray(X.indices, dtype=np.int32)
-    return X, indptr, indices
+    memo = getattr(X, "_rpk_canon", None)
+    sig = (X.indptr.ctypes.data, X.indices.ctypes.data, X.data.ctypes.data, X.nnz, X.shape)
+    if memo is None or memo[0] != sig:
+        # validated once per matrix object (the checks are O(nnz) on the host); like scipy's own
+        # has_canonical_format flag the memo assumes the arrays are not modified in place afterwards
+        if X.nnz and not np.all(X.data):
+            X = X.copy()
+            X.eliminate_zeros()
+        if not X.has_canonical_format:
+            X = X.copy()
+            X.sum_duplicates()
+        indptr = np.ascontiguousarray(X.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(X.indices, dtype=np.int32)
+        sig = (X.indptr.ctypes.data, X.indices.ctypes.data, X.data.ctypes.data, X.nnz, X.shape)
+        try:
+            X._rpk_canon = (sig, indptr, indices)
+        except AttributeError:
+            pass
+        return X, indptr, indices
+    return X, memo[1], memo[2]

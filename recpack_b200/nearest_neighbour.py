@@ -72,7 +72,7 @@ class ItemKNN(TopKItemSimilarityMatrixAlgorithm):
             nz = n > 0
             item_pow[nz] = np.power(1 / n[nz], self.pop_discount)
         K = int(self.K)
-        out = engine.fit_topk(U, I, indptr, indices, K, similarity=self.similarity, item_pow=item_pow)
+        out = engine.fit_topk(U, I, indptr, indices, K, similarity=self.similarity, item_pow=item_pow, want_cnt=False)
         self._set_similarity_from_lists(out, I)
         if not self.normalize_sim:  # the device copy holds the un-normalised values
             self._fit_lists["token"] = (engine.nonce, engine.fit_token())

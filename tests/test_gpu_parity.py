@@ -458,3 +458,31 @@ def test_predict_after_pickle_and_model_reuse():
         assert np.array_equal(a._rpk_topn[0], other_pred._rpk_topn[0])
         assert np.array_equal(a.data, other_pred.data)
     assert other.similarity_matrix_.shape == (40, 40)
+
+
+def test_model_load_from_padded_shards(engine):
+    """rpk_model_load_topk_rows: model rows read through a row map from padded, gathered per-rank shards."""
+    from recpack_b200.matrix import binary_structure
+    from recpack_b200.synth import synth_interactions
+
+    X = synth_interactions(300, 200, 4000, seed=21)
+    K, N = 12, 10
+    want = orc.canon_fit(X, K=K)
+    cuts, maxrows = [0, 90, 97, 200], 103
+    g_idx = np.full((3 * maxrows, K), -1, dtype=np.int32)
+    g_val = np.zeros((3 * maxrows, K))
+    g_len = np.zeros(3 * maxrows, dtype=np.int32)
+    src = np.empty(200, dtype=np.int64)
+    for r in range(3):
+        b, e = cuts[r], cuts[r + 1]
+        g_idx[r * maxrows : r * maxrows + e - b] = want["idx"][b:e]
+        g_val[r * maxrows : r * maxrows + e - b] = want["val"][b:e]
+        g_len[r * maxrows : r * maxrows + e - b] = want["len"][b:e]
+        src[b:e] = r * maxrows + np.arange(e - b)
+    _, indptr, indices = binary_structure(X)
+    engine.model_load_topk(200, K, want["idx"], want["val"], want["len"])
+    a = engine.predict_topn(300, indptr, indices, N)
+    engine.model_load_topk_rows(200, K, 3 * maxrows, g_idx, g_val, g_len, src)
+    b_ = engine.predict_topn(300, indptr, indices, N)
+    for key in ("idx", "val", "len"):
+        assert np.array_equal(a[key], b_[key])
