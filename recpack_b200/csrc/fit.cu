@@ -91,6 +91,49 @@ __global__ void k_fill_dense(const int64_t* __restrict__ indptr, const int* __re
   }
 }
 
+// ---- items seen by >= 65536 users: a co-occurrence count between two of them may not fit 16 bits ----
+constexpr int HEAVY_CAP = 32;
+__global__ void k_find_heavy(const int* __restrict__ n, int64_t I, int* __restrict__ heavy_ids, int* __restrict__ heavy_n) {
+  int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < I && n[j] >= 65536) {
+    const int s = atomicAdd(heavy_n, 1);
+    if (s < HEAVY_CAP) heavy_ids[s] = (int)j;
+  }
+}
+// pair[a * HEAVY_CAP + b] = exact number of users with both heavy items a and b (one warp per user,
+// lane h looks heavy item h up in the user's sorted history).
+__global__ void k_heavy_pairs(const int64_t* __restrict__ indptr, const int* __restrict__ indices, int64_t U,
+                              const int* __restrict__ heavy_ids, const int* __restrict__ heavy_n, int* __restrict__ pair) {
+  const int H = heavy_n[0];
+  if (H < 2 || H > HEAVY_CAP) return;
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int target = lane < H ? heavy_ids[lane] : -1;
+  for (int64_t u = warp; u < U; u += nwarps) {
+    int64_t lo = indptr[u], hi = indptr[u + 1];
+    bool has = false;
+    if (target >= 0) {
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        const int v = indices[mid];
+        if (v < target) lo = mid + 1;
+        else hi = mid;
+      }
+      has = lo < indptr[u + 1] && indices[lo] == target;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, has);
+    if (has) {
+      unsigned others = m & ~(1u << lane);
+      while (others) {
+        const int b = __ffs(others) - 1;
+        others &= others - 1;
+        atomicAdd(&pair[lane * HEAVY_CAP + b], 1);
+      }
+    }
+  }
+}
+
 // pref[k] = sum of the history lengths of the users listed before position k of the same item
 // (exclusive, in CSC order): lets the fit kernel cut a row's work into equal pieces per warp.
 __global__ void k_csc_prefix(const int64_t* __restrict__ cscptr, const int* __restrict__ csc_users,
@@ -266,10 +309,17 @@ struct RowCountSrc {
   SimKey sk;
   const unsigned* cnt;
   int r0, ns, self;
+  // "extra" candidates: columns whose count may not fit 16 bits (both items seen by >= 65536 users) carry an
+  // exact 32-bit count from k_heavy_pairs; their packed counters are zeroed.  Slots ns .. ns+nex-1.
+  const int* ex_idx;
+  const int* ex_cnt;
+  int nex;
   __device__ __forceinline__ int count(int slot) const {
+    if (slot >= ns) return ex_cnt[slot - ns];
     if (PACK16) return (int)((cnt[slot >> 1] >> ((slot & 1) * 16)) & 0xffffu);
     return (int)cnt[slot];
   }
+  __device__ __forceinline__ int item(int slot) const { return slot >= ns ? ex_idx[slot - ns] : r0 + slot; }
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return sk.margin(); }
   int cmin;  // set_floor(): counts below this cannot reach the requested key
@@ -313,11 +363,20 @@ struct RowCountSrc {
     }
   }
   template <class F>
-  __device__ __forceinline__ void for_each(F f) const { visit(f, 1, false); }
+  __device__ __forceinline__ void visit_extras(F f) const {
+    const int t = threadIdx.x;
+    if (t < nex && ex_cnt[t] >= cmin && ex_cnt[t] > 0 && ex_idx[t] != self) f(ns + t, sk.akey(ex_cnt[t], ex_idx[t]));
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each(F f) const {
+    visit(f, 1, false);
+    visit_extras(f);
+  }
   template <class F>
   __device__ __forceinline__ void for_each_sampled(F f) const {
     if (PACK16) visit(f, SEL_SAMPLE / 2, true);  // the low counter of every 8th word = 1 slot in 16
     else visit(f, SEL_SAMPLE, false);
+    visit_extras(f);
   }
   // Integer-only pass over the packed counters: candidate count and the largest count; the key bounds
   // follow from that (no popularity loads, no float math).
@@ -348,6 +407,10 @@ struct RowCountSrc {
         cmax = max(cmax, c0);
       }
     }
+    if (tid < nex && ex_cnt[tid] > 0 && ex_idx[tid] != self) {
+      cntc++;
+      cmax = max(cmax, ex_cnt[tid]);
+    }
     cntc = __reduce_add_sync(0xffffffffu, cntc);
     cmax = __reduce_max_sync(0xffffffffu, cmax);
     if (lane == 0 && cntc) {
@@ -363,7 +426,7 @@ struct RowCountSrc {
     }
     __syncthreads();
   }
-  __device__ __forceinline__ void entry(int slot, Entry& e) const { sk.entry(count(slot), r0 + slot, e); }
+  __device__ __forceinline__ void entry(int slot, Entry& e) const { sk.entry(count(slot), item(slot), e); }
   __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const { return sk.cmp3(a, b); }
 };
 
@@ -416,6 +479,9 @@ struct FitParams {
   int* out_cnt;
   int* out_len;
   const unsigned char* pop_code;  // global [I], null: no coded reciprocals
+  const int* heavy_ids;   // items seen by >= 65536 users (PACK16 launch only), null: none handled here
+  const int* heavy_n;
+  const int* heavy_pair;  // exact counts between them, [HEAVY_CAP x HEAVY_CAP]
   int defer_max;   // > 0: rows with at most this many survivors are sorted by k_fit_sort_rows instead
   int* scr_idx;    // [rows x defer_max] unsorted survivors (item, count)
   int* scr_cnt;
@@ -431,6 +497,7 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
   unsigned* cnt = reinterpret_cast<unsigned*>(smem + sel_smem_bytes(p.cap));
   __shared__ int s_work;
   __shared__ float s_code_tab[256];
+  __shared__ int s_ex_idx[HEAVY_CAP], s_ex_cnt[HEAVY_CAP];
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int total = p.nrows_dev[0] * p.P;
@@ -605,7 +672,25 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
     }
     __syncthreads();
     // ---- fused epilogue: similarity ordering, diagonal removal, top-K -- all on the shared-memory row
-    RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i, 1};
+    // columns of a heavy row that are heavy themselves: their 16-bit counters may have wrapped -- zero them and
+    // use the exact pair counts instead
+    int nex = 0;
+    if (PACK16 && p.heavy_ids && p.sk.n[i] >= 65536) {
+      const int H = min(p.heavy_n[0], HEAVY_CAP);  // (more than HEAVY_CAP heavy items: those rows take the 32-bit launch)
+      if (tid < H) {
+        const int j = p.heavy_ids[tid];
+        s_ex_idx[tid] = j;
+        int me = 0;
+        for (int h = 0; h < H; ++h) me = p.heavy_ids[h] == i ? h : me;
+        const int sl = j - r0;
+        const bool mine = sl >= 0 && sl < ns;  // a column belongs to exactly one item range
+        s_ex_cnt[tid] = (mine && j != i) ? p.heavy_pair[me * HEAVY_CAP + tid] : 0;
+        if (mine) atomicAnd(&cnt[sl >> 1], (sl & 1) ? 0x0000ffffu : 0xffff0000u);
+      }
+      nex = H;
+      __syncthreads();
+    }
+    RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i, s_ex_idx, s_ex_cnt, nex, 1};
     bool sorted = true;
     const int m = block_select_topk(src, p.K, list, p.cap, p.direct_cap, hist, sh, p.defer_max, &sorted);
     if (!sorted) {
@@ -700,8 +785,11 @@ __global__ void __launch_bounds__(256) k_fit_sort_rows(SortParams p) {
 
 // Stable split of the heaviest-first row order into rows whose counts fit 16 bits and the rest (one block).
 __global__ void __launch_bounds__(1024) k_split_rows(const int* __restrict__ order, int nrows, const int* __restrict__ n,
-                                                     int limit, int* __restrict__ light, int* __restrict__ heavy,
-                                                     int* __restrict__ counts) {
+                                                     int limit_in, const int* __restrict__ heavy_n, int* __restrict__ light,
+                                                     int* __restrict__ heavy, int* __restrict__ counts) {
+  // when the heavy items are few enough to be handled as exact "extra" columns, every row stays on the
+  // 16-bit path; otherwise rows with >= limit users take the 32-bit path
+  const int limit = (limit_in > 0 && heavy_n && heavy_n[0] <= HEAVY_CAP) ? 0x7fffffff : limit_in;
   __shared__ int wl[32], wh[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   int nl = 0, nh = 0;
@@ -951,7 +1039,20 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     int* queues = c->buf<int>("fit_queues", 4);
     RPK_CUDA(cudaMemsetAsync(queues, 0, sizeof(int) * 4, st));
     const bool force_wide = (c->flags & DBG_WIDE_ACC) != 0;  // test hook: every row through the 32-bit path
-    k_split_rows<<<1, 1024, 0, st>>>(order, (int)nrows, n, force_wide ? 0 : 65536, order_l, order_h, split_cnt);
+    int* heavy_ids = c->buf<int>("fit_heavy_ids", HEAVY_CAP + 4);
+    int* heavy_n = heavy_ids + HEAVY_CAP;
+    int* heavy_pair = c->buf<int>("fit_heavy_pair", HEAVY_CAP * HEAVY_CAP);
+    RPK_CUDA(cudaMemsetAsync(heavy_ids, 0, sizeof(int) * (HEAVY_CAP + 4), st));
+    RPK_CUDA(cudaMemsetAsync(heavy_pair, 0, sizeof(int) * HEAVY_CAP * HEAVY_CAP, st));
+    if (!force_wide && U >= 65536) {
+      k_find_heavy<<<ceil_div(I, 256), 256, 0, st>>>(n, I, heavy_ids, heavy_n);
+      RPK_LAUNCH_CHECK(c);
+      const int hb = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
+      k_heavy_pairs<<<hb, 256, 0, st>>>(indptr, indices, U, heavy_ids, heavy_n, heavy_pair);
+      RPK_LAUNCH_CHECK(c);
+    }
+    k_split_rows<<<1, 1024, 0, st>>>(order, (int)nrows, n, force_wide ? 0 : 65536, force_wide ? nullptr : heavy_n, order_l,
+                                     order_h, split_cnt);
     RPK_LAUNCH_CHECK(c);
 
     const bool tiny = c->flags & DBG_TINY_LIST;
@@ -1037,6 +1138,9 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
       fp.out_len = part_len;
       // rows written directly to the final arrays may defer their sort to k_fit_sort_rows
       fp.pop_code = use_code ? c->get<unsigned char>("fit_pop_code") : nullptr;
+      fp.heavy_ids = (!wide && !force_wide) ? heavy_ids : nullptr;
+      fp.heavy_n = heavy_n;
+      fp.heavy_pair = heavy_pair;
       fp.defer_max = (P == 1 && !tiny) ? defer_max : 0;
       fp.scr_idx = scr_idx;
       fp.scr_cnt = scr_cnt;

@@ -486,3 +486,22 @@ def test_model_load_from_padded_shards(engine):
     b_ = engine.predict_topn(300, indptr, indices, N)
     for key in ("idx", "val", "len"):
         assert np.array_equal(a[key], b_[key])
+
+
+@pytest.mark.parametrize("flags,dense_users", [(0, 0), (0, 64), (4, 0), (1, 0)])
+def test_fit_items_seen_by_more_than_65535_users(engine, flags, dense_users):
+    """Counts between two items that both exceed 65,535 users do not fit the packed 16-bit counters: they come
+    from the exact pair kernel (or, with flag 1, from the 32-bit counter path)."""
+    rng = np.random.default_rng(4)
+    U, I, K = 70_000, 40, 12
+    p = np.concatenate([[0.99, 0.97, 0.95, 0.945], rng.random(I - 4) * 0.5 + 0.02])
+    X = csr_matrix((rng.random((U, I)) < p[None, :]).astype(np.int32))
+    assert (np.bincount(X.indices, minlength=I) >= 65536).sum() >= 3
+    engine.debug_flags(flags)
+    engine.fit_config(dense_users)
+    try:
+        got = _fit_lists(engine, X, K)
+    finally:
+        engine.fit_config(-1)
+        engine.debug_flags(0)
+    _assert_fit_equal(got, orc.canon_fit(X, K=K))
