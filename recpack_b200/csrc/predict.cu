@@ -22,11 +22,11 @@
 
 namespace rpk {
 
+
 constexpr u64 Q_MASK40 = (((u64)1) << 40) - 1;
 constexpr int LIMB_BITS = 20;
 constexpr unsigned LIMB_MASK = (1u << LIMB_BITS) - 1;
-constexpr int LIMB_CHUNK = 4095;
-constexpr int PRED_META_CAP = 1024;  // history item ids cached in shared memory up to this length  // rows that can be added before the low limb must be normalised
+constexpr int LIMB_CHUNK = 4095;  // rows that can be added before the low limb must be normalised
 
 // ------------------------------------------------------------------------------------------
 // Model construction
@@ -125,16 +125,16 @@ __global__ void k_model_from_csr(const int64_t* __restrict__ indptr, const int* 
   }
 }
 
-// seg[i*(P+1)+p] = position in m_ent of the first entry of row i with column >= p*R (absolute)
+// seg[i*(P+1)+p] = offset inside row i of the first entry with column >= p*R
 __global__ void k_model_seg(const int64_t* __restrict__ m_ptr, const u64* __restrict__ m_ent, int64_t I, int P, int R,
-                            int64_t* __restrict__ seg) {
+                            int* __restrict__ seg) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= I * (P + 1)) return;
   int64_t i = t / (P + 1);
   int p = (int)(t % (P + 1));
   int64_t b = m_ptr[i], lo = b, hi = m_ptr[i + 1];
   if (p == P) {
-    seg[t] = hi;
+    seg[t] = (int)(hi - b);
     return;
   }
   u64 target = (u64)p * (u64)R;
@@ -143,7 +143,7 @@ __global__ void k_model_seg(const int64_t* __restrict__ m_ptr, const u64* __rest
     if ((m_ent[mid] >> 40) < target) lo = mid + 1;
     else hi = mid;
   }
-  seg[t] = lo;
+  seg[t] = (int)(lo - b);
 }
 
 __global__ void k_gather_len(const int* __restrict__ len, const int64_t* __restrict__ row_src, int64_t I, int* __restrict__ out) {
@@ -313,7 +313,7 @@ struct PredParams {
   const int* indices;
   const int64_t* m_ptr;
   const u64* m_ent;
-  const int64_t* m_seg;  // [I x (P+1)] absolute segment bounds of every model row
+  const int* m_seg;
   const unsigned* m_rowmax;
   const int4* work_tab;  // {user, history length, row start lo, hi} in processing order
   int U, P, R, I, N, mask, mode, force_wide;
@@ -346,10 +346,9 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
   __shared__ u64 s_bound;
   __shared__ int s_cnt;
   __shared__ int s_ntouched;
-  __shared__ int s_items[PRED_META_CAP];
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  const int total = p.U;  // work item = user; its P item ranges are processed back to back by the same CTA
+  const int total = p.U * p.P;
   for (int s = tid; s < p.R; s += nt) acc64[s] = 0ull;
   if (tid == 0) s_next = atomicAdd(p.queue, 1);
   for (;;) {
@@ -357,28 +356,22 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       s_work = s_next;
       const int nx = atomicAdd(p.queue, 1);
       s_next = nx;
-      if (nx < total) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.work_tab + nx) : "memory");
-    }
-    __syncthreads();
-    const int w = s_work;
-    if (w >= total) break;
-    const int4 rec = p.work_tab[w];
-    const int u = rec.x;
-    const int64_t xb = ((int64_t)(unsigned)rec.z) | ((int64_t)rec.w << 32);
-    const int d = rec.y;
-    // the history's item ids are read once per user and reused by every item-range pass
-    const bool cached = d <= PRED_META_CAP;
-    if (cached)
-      for (int r = tid; r < d; r += nt) s_items[r] = p.indices[xb + r];
-   for (int pass = 0; pass < p.P; ++pass) {
-    if (tid == 0) {
+      if (nx < total) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.work_tab + nx / p.P) : "memory");
       s_bound = 0;
       s_cnt = 0;
       s_ntouched = 0;
     }
     __syncthreads();
+    const int w = s_work;
+    __syncthreads();
+    if (w >= total) break;
+    const int4 rec = p.work_tab[w / p.P];
+    const int u = rec.x;
+    const int pass = w % p.P;
     const int r0 = pass * p.R;
     const int ns = min(p.R, p.I - r0);
+    const int64_t xb = ((int64_t)(unsigned)rec.z) | ((int64_t)rec.w << 32);
+    const int d = rec.y;
     const int64_t slot_out = (int64_t)u * p.P + pass;
     if (d == 0) {  // user without history: empty prediction row (algorithms/base.py:123-127)
       if (p.mode == PRED_TOPN) {
@@ -421,10 +414,11 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
           int64_t beg = 0;
           int len = 0;
           if (lane < nvalid) {
-            const int i = cached ? s_items[base + lane] : p.indices[xb + base + lane];
-            const int64_t* sg = p.m_seg + (int64_t)i * (p.P + 1) + pass;
-            beg = sg[0];
-            len = (int)(sg[1] - beg);
+            const int i = p.indices[xb + base + lane];
+            const int* sg = p.m_seg + (int64_t)i * (p.P + 1) + pass;
+            const int s0 = sg[0];
+            beg = p.m_ptr[i] + s0;
+            len = sg[1] - s0;
           }
           // add one entry to the accumulators; in sparse mode record the slot on its first touch
           auto add_entry = [&](u64 ent) {
@@ -502,7 +496,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
     const bool sparse = track && n_touched <= p.tcap;
     if (p.mask) {  // pipelines/pipeline.py:174-175 -- before the truncation to N
       for (int r = tid; r < d; r += nt) {
-        const int j = (cached ? s_items[r] : p.indices[xb + r]) - r0;
+        const int j = p.indices[xb + r] - r0;
         if (j >= 0 && j < ns) {
           if (wide) acc64[j] = 0ull;
           else {
@@ -567,7 +561,6 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
         for (int s = tid; s < ns; s += nt) acc_hi[s] = 0u;
     }
     __syncthreads();
-   }  // item ranges
   }
 }
 
@@ -656,7 +649,7 @@ static PredGeom predict_geometry(rpk_ctx* c, int N) {
   g.direct_cap = tiny ? std::max(N, 1) : std::min(g.cap, std::max(64, 2 * N));
   g.fixed = sel_smem_bytes(g.cap);
   RPK_REQUIRE((size_t)c->smem_max > g.fixed + 1024 + 8192, "N too large for shared memory");
-  const size_t avail = (size_t)c->smem_max - g.fixed - 6144;  // static shared memory: cached history + scalars
+  const size_t avail = (size_t)c->smem_max - g.fixed - 1024;
   const int64_t I = c->m_I;
   // 8 B of accumulator per item of a range + a list of touched slots (4 B each, up to 8192 of them)
   int P = 1;
@@ -687,7 +680,7 @@ static PredGeom predict_geometry(rpk_ctx* c, int N) {
 static void ensure_segments(rpk_ctx* c, const PredGeom& g) {
   if (c->m_P == g.P && c->m_R == g.R) return;
   const int64_t I = c->m_I;
-  int64_t* seg = c->buf<int64_t>("m_seg", (size_t)I * (g.P + 1));
+  int* seg = c->buf<int>("m_seg", (size_t)I * (g.P + 1));
   if (I > 0) {
     k_model_seg<<<ceil_div(I * (g.P + 1), 256), 256, 0, c->stream>>>(c->get<int64_t>("m_ptr"), c->get<u64>("m_ent"), I, g.P,
                                                                       g.R, seg);
@@ -738,7 +731,7 @@ static void fill_common(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_t U
   pp.indices = indices;
   pp.m_ptr = c->get<int64_t>("m_ptr");
   pp.m_ent = c->get<u64>("m_ent");
-  pp.m_seg = c->get<int64_t>("m_seg");
+  pp.m_seg = c->get<int>("m_seg");
   pp.m_rowmax = c->get<unsigned>("m_rowmax");
   pp.U = (int)U;
   pp.P = g.P;
