@@ -47,6 +47,7 @@ int rpk_create(int device, rpk_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     c->smem_max = (int)prop.sharedMemPerBlockOptin;
+    c->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     c->dense_users = -1;  // automatic
     *out = c;
   } catch (const std::exception& e) {
@@ -91,6 +92,7 @@ int rpk_debug_flags(rpk_ctx* ctx, int flags) {
   RPK_API_BEGIN(ctx)
   ctx->flags = flags;
   ctx->m_P = 0;  // predict geometry may change
+  ctx->m_P2 = 0;
   RPK_API_END(ctx)
 }
 

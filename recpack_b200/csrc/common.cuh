@@ -52,6 +52,7 @@ struct rpk_ctx {
   int dense_users = 0;  // users routed through the tensor-core Gram (-1 = automatic)
   int sm_count = 0;
   int smem_max = 0;  // max opt-in dynamic shared memory per block
+  int smem_per_sm = 0;  // shared memory of one SM (CTAs sharing an SM split this, 1 KB reserved each)
   std::map<std::string, rpk::Buf> bufs;
   bool host_out_pending = false;
   // CUDA events around the dominant kernels of the last fit / predict (rpk_last_timings)
@@ -82,6 +83,9 @@ struct rpk_ctx {
   int64_t m_nnz = 0;
   int m_P = 0;        // item-range passes of predict
   int m_R = 0;        // items per pass
+  int m_P2 = 0;       // the same for the 32-bit scoring kernel's segment table
+  int m_R2 = 0;
+  bool m_pad = false;  // padded block layout of the model is current
   int m_max_len = 0;  // longest model row
 
   // ---- per-pass candidate counts of the last rpk_predict_csr_count

@@ -146,6 +146,52 @@ __global__ void k_model_seg(const int64_t* __restrict__ m_ptr, const u64* __rest
   seg[t] = (int)(lo - b);
 }
 
+// ---- block layout for the 32-bit scoring kernel: every row padded to a multiple of 4 entries (32 bytes, one
+// sector) with all-ones entries, whose column 0xFFFFFF lies outside every item range.
+__global__ void k_model_pad_len(const int64_t* __restrict__ m_ptr, int64_t I, int* __restrict__ len4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < I) len4[i] = (int)((m_ptr[i + 1] - m_ptr[i] + 3) & ~(int64_t)3);
+}
+
+__global__ void k_model_pad(const int64_t* __restrict__ m_ptr, const u64* __restrict__ m_ent,
+                            const int64_t* __restrict__ ptr4, int64_t I, u64* __restrict__ ent4) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < I; i += nwarps) {
+    const int64_t b = m_ptr[i], n = m_ptr[i + 1] - b, o = ptr4[i], n4 = ptr4[i + 1] - o;
+    for (int64_t k = lane; k < n4; k += 32) ent4[o + k] = k < n ? m_ent[b + k] : ~0ull;
+  }
+}
+
+// blk[i*P + p] = {first 4-entry block, number of blocks} covering the entries of row i with column in
+// [p*R, (p+1)*R).  The blocks may also hold neighbours from the adjacent ranges of the same row (and
+// padding); the kernel drops those by their column.
+__global__ void k_model_blocks(const int64_t* __restrict__ m_ptr, const u64* __restrict__ m_ent,
+                               const int64_t* __restrict__ ptr4, int64_t I, int P, int R, int2* __restrict__ blk) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= I * P) return;
+  const int64_t i = t / P;
+  const int p = (int)(t % P);
+  const int64_t b = m_ptr[i], e = m_ptr[i + 1];
+  auto lower = [&](u64 target) {
+    int64_t lo = b, hi = e;
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if ((m_ent[mid] >> 40) < target) lo = mid + 1;
+      else hi = mid;
+    }
+    return lo - b;
+  };
+  const int64_t s0 = lower((u64)p * (u64)R), s1 = lower((u64)(p + 1) * (u64)R);
+  int2 r = make_int2(0, 0);
+  if (s1 > s0) {
+    const int64_t first = (ptr4[i] + s0) >> 2, last = (ptr4[i] + s1 + 3) >> 2;
+    r = make_int2((int)first, (int)(last - first));
+  }
+  blk[t] = r;
+}
+
 __global__ void k_gather_len(const int* __restrict__ len, const int64_t* __restrict__ row_src, int64_t I, int* __restrict__ out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < I) out[i] = len[row_src[i]];
@@ -154,7 +200,9 @@ __global__ void k_gather_len(const int* __restrict__ len, const int64_t* __restr
 static void model_common_begin(rpk_ctx* c, int64_t I) {
   RPK_REQUIRE(I >= 0 && I < ((int64_t)1 << 24), "item count must be below 2^24");
   c->m_I = I;
-  c->m_P = 0;  // segment table must be rebuilt
+  c->m_P = 0;  // segment tables must be rebuilt
+  c->m_P2 = 0;
+  c->m_pad = false;
   int* flag = c->buf<int>("m_flag", 1);
   RPK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
 }
@@ -316,6 +364,7 @@ struct PredParams {
   const int* m_seg;
   const unsigned* m_rowmax;
   const int4* work_tab;  // {user, history length, row start lo, hi} in processing order
+  const int* n_work;     // non-null: number of work_tab records (device side), replaces U
   int U, P, R, I, N, mask, mode, force_wide;
   int cap, direct_cap, tcap;
   int* queue;
@@ -326,7 +375,21 @@ struct PredParams {
   const int64_t* out_indptr;
   int* out_indices;
   double* out_values;
+  unsigned long long* prof;  // RPK_PHASE_PROF builds: cycles of thread 0 per phase
 };
+
+#ifdef RPK_PHASE_PROF
+#define PROF_MARK(k)                                         \
+  do {                                                       \
+    if (tid == 0) {                                          \
+      const long long t_now = clock64();                     \
+      atomicAdd(p.prof + (k), (unsigned long long)(t_now - t_prev)); \
+      t_prev = t_now;                                        \
+    }                                                        \
+  } while (0)
+#else
+#define PROF_MARK(k) do {} while (0)
+#endif
 
 // Invariant: the accumulators of a CTA are all zero between work items.  A light user touches few of
 // the R slots of a range, so its slots are recorded on first touch (the low limb of a touched slot can
@@ -348,10 +411,15 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
   __shared__ int s_ntouched;
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  const int total = p.U * p.P;
+  const int total = (p.n_work ? *p.n_work : p.U) * p.P;
+  if (total == 0) return;
   for (int s = tid; s < p.R; s += nt) acc64[s] = 0ull;
   if (tid == 0) s_next = atomicAdd(p.queue, 1);
+#ifdef RPK_PHASE_PROF
+  long long t_prev = clock64();
+#endif
   for (;;) {
+    PROF_MARK(7);
     if (tid == 0) {
       s_work = s_next;
       const int nx = atomicAdd(p.queue, 1);
@@ -373,6 +441,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
     const int64_t xb = ((int64_t)(unsigned)rec.z) | ((int64_t)rec.w << 32);
     const int d = rec.y;
     const int64_t slot_out = (int64_t)u * p.P + pass;
+    PROF_MARK(0);
     if (d == 0) {  // user without history: empty prediction row (algorithms/base.py:123-127)
       if (p.mode == PRED_TOPN) {
         for (int t = tid; t < p.N; t += nt) {
@@ -396,6 +465,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       __syncthreads();
       wide = s_bound >= (((u64)1) << 32);
     }
+    PROF_MARK(1);
     // sparse mode: track first touches (needs the limb accumulators and a single chunk)
     const bool track = !wide && d <= LIMB_CHUNK && p.mode == PRED_TOPN && p.tcap > 0;
     // ---- accumulate: history rows are dealt to the warps in chunks (<= 32 rows, one per lane, so that the
@@ -494,6 +564,14 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
     else accumulate(std::false_type{}, std::false_type{});
     const int n_touched = s_ntouched;
     const bool sparse = track && n_touched <= p.tcap;
+    PROF_MARK(2);
+#ifdef RPK_PHASE_PROF
+    if (tid == 0) {
+      atomicAdd(p.prof + 8, 1ull);
+      atomicAdd(p.prof + 9, (unsigned long long)sparse);
+      atomicAdd(p.prof + 10, (unsigned long long)n_touched);
+    }
+#endif
     if (p.mask) {  // pipelines/pipeline.py:174-175 -- before the truncation to N
       for (int r = tid; r < d; r += nt) {
         const int j = p.indices[xb + r] - r0;
@@ -508,8 +586,10 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       __syncthreads();
     }
     ScoreSrc src{acc_lo, acc_hi, wide ? acc64 : nullptr, sparse ? touched : nullptr, r0, sparse ? n_touched : ns, 0ull};
+    PROF_MARK(3);
     if (p.mode == PRED_TOPN) {
       const int m = block_select_topk(src, p.N, list, p.cap, p.direct_cap, hist, sh);
+      PROF_MARK(4);
       for (int t = tid; t < p.N; t += nt) {
         p.part_idx[slot_out * p.N + t] = t < m ? list[t].idx : -1;
         p.part_sq[slot_out * p.N + t] = t < m ? list[t].key : 0ull;
@@ -548,6 +628,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       }
     }
     __syncthreads();
+    PROF_MARK(5);
     // ---- restore the all-zero invariant
     if (sparse) {
       for (int t = tid; t < n_touched; t += nt) {
@@ -561,22 +642,348 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
         for (int s = tid; s < ns; s += nt) acc_hi[s] = 0u;
     }
     __syncthreads();
+    PROF_MARK(6);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Scoring kernel, top-N mode: 32-bit approximate accumulators + exact scores for the survivors
+// ------------------------------------------------------------------------------------------
+// The two-limb kernel above pays two shared-memory atomics per similarity entry and 8 bytes per item slot.
+// For top-N only a handful of scores per user matter, so this kernel runs two sweeps over the user's rows:
+//   1. a_j += (q >> s) | 1 with ONE 32-bit atomic per entry (s = 9 + ceil(log2 d) keeps every sum below
+//      2^32).  Each term is within 1 of q / 2^s, so |a_j - score_j / 2^s| <= d: a_j orders two items
+//      correctly whenever their a differ by more than 2d.
+//   2. the selection keeps every item whose a_j is within 2d of the N-th largest (a few more than N); their
+//      slots are marked and the rows are streamed again, adding the exact q of marked slots only.
+// The survivors are then ordered by their exact scores.  4 bytes per slot let two CTAs share an SM, so one
+// CTA's latency-bound steps (work fetch, selection, output) hide behind the other's atomics.  A user whose
+// survivors do not fit the list (huge groups of near-equal scores) is handed to the two-limb kernel.
+struct ApproxSrc {
+  const unsigned* acc;
+  const int* touched;  // non-null: slot list (sparse mode)
+  int r0, ns;
+  u64 floor_;
+  u64 margin_;
+  u64 kmax_;
+  __device__ __forceinline__ int nslots() const { return ns; }
+  __device__ __forceinline__ u64 margin() const { return margin_; }
+  __device__ __forceinline__ void set_floor(u64 thr) { floor_ = thr; }
+  __device__ __forceinline__ void stats(SelShared* sh) const {
+    if (threadIdx.x == 0) {
+      sh->count = ns;
+      sh->kmin = 1ull;
+      sh->kmax = kmax_;
+    }
+    __syncthreads();
+  }
+  template <class F>
+  __device__ __forceinline__ void visit(F f, int stride) const {
+    for (int slot = threadIdx.x * stride; slot < ns; slot += blockDim.x * stride) {
+      const int j = touched ? touched[slot] : slot;
+      const u64 k = (u64)acc[j];
+      if (k != 0 && k >= floor_) f(slot, k);
+    }
+  }
+  template <class F>
+  __device__ __forceinline__ void for_each(F f) const { visit(f, 1); }
+  template <class F>
+  __device__ __forceinline__ void for_each_sampled(F f) const { visit(f, SEL_SAMPLE); }
+  __device__ __forceinline__ void entry(int slot, Entry& e) const {
+    const int j = touched ? touched[slot] : slot;
+    e.key = (u64)acc[j];
+    e.idx = r0 + j;
+    e.aux = 0;
+  }
+  __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const {  // unused (SURVIVORS_ONLY)
+    if (a.key != b.key) return a.key > b.key ? 1 : -1;
+    return 0;
+  }
+};
+
+struct ExactOrder {
+  __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const {
+    if (a.key != b.key) return a.key > b.key ? 1 : -1;
+    return 0;
+  }
+};
+
+struct Pred32Params {
+  const int* indices;
+  const uint4* ent4;  // model rows in 4-entry blocks (two uint4 each)
+  const int2* blk;    // {first block, blocks} per (row, item range)
+  const int4* work_tab;
+  int U, P, R, I, N, mask;
+  int cap, direct_cap, tcap;
+  int* queue;
+  int* part_idx;
+  u64* part_sq;
+  int* part_len;
+  int* ovf_flag;   // per user: 1 = handed to the two-limb kernel
+  int* ovf_count;  // number of such users
+  int4* ovf_tab;   // their work records
+  unsigned long long* prof;
+};
+
+constexpr int A32_BITS = 11;            // selection histogram of the 32-bit kernel: 2048 bins
+constexpr int A32_BINS = 1 << A32_BITS;
+constexpr int A32_ROWS = 512;           // history rows staged per chunk (>= block size)
+
+// Row table of one chunk of the user's history: first block and number of blocks of every row's segment.
+struct RowTab {
+  int start[A32_ROWS];
+  int nb[A32_ROWS];
+};
+
+// Stages rows [c0, c0 + n) of the history, one row per thread.
+__device__ __forceinline__ void stage_rows(const Pred32Params& p, int64_t xb, int c0, int n, int pass, RowTab* rt) {
+  const int tid = threadIdx.x;
+  if (tid < n) {
+    const int i = p.indices[xb + c0 + tid];
+    const int2 sb = __ldg(p.blk + (int64_t)i * p.P + pass);
+    rt->start[tid] = sb.x;
+    rt->nb[tid] = sb.y;
+  }
+  __syncthreads();
+}
+
+// Calls f(entry) for every entry of the staged segments (entries of neighbouring ranges and padding
+// included -- f drops them by their column).  One warp per row, a lane per entry, so that a load covers
+// 256 contiguous bytes; two rows (up to six loads per lane) are in flight before anything is added.
+template <class F>
+__device__ __forceinline__ void sweep_rows(const Pred32Params& p, const RowTab* rt, int n, F f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const u64* ent = reinterpret_cast<const u64*>(p.ent4);
+  for (int r = warp; r < n; r += 2 * nwarps) {
+    const int r2 = r + nwarps;
+    const u64* b1 = ent + (int64_t)rt->start[r] * 4 + lane;
+    const int n1 = rt->nb[r] * 4 - lane;  // entries left from this lane's first one
+    const u64* b2 = b1;
+    int n2 = 0;
+    if (r2 < n) {
+      b2 = ent + (int64_t)rt->start[r2] * 4 + lane;
+      n2 = rt->nb[r2] * 4 - lane;
+    }
+    u64 e1[3], e2[3];
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+      e1[it] = 32 * it < n1 ? __ldg(b1 + 32 * it) : ~0ull;
+      e2[it] = 32 * it < n2 ? __ldg(b2 + 32 * it) : ~0ull;
+    }
+#pragma unroll
+    for (int it = 0; it < 3; ++it) {
+      f(e1[it]);
+      f(e2[it]);
+    }
+    for (int e = 96; e < n1; e += 32) f(__ldg(b1 + e));
+    for (int e = 96; e < n2; e += 32) f(__ldg(b2 + e));
+  }
+}
+
+#ifdef RPK_PHASE_PROF
+#define PROF32_MARK(k) PROF_MARK(k)
+#else
+#define PROF32_MARK(k) do {} while (0)
+#endif
+
+__host__ __device__ __forceinline__ size_t a32_fixed_bytes(int cap) {
+  return sel_smem_bytes(cap, A32_BINS) + ((sizeof(RowTab) + 15) / 16) * 16;
+}
+
+__global__ void __launch_bounds__(512, 2) k_predict_a32(Pred32Params p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  Entry* list = reinterpret_cast<Entry*>(smem);
+  int* hist = reinterpret_cast<int*>(smem + sel_list_bytes(p.cap));
+  SelShared* sh = reinterpret_cast<SelShared*>(hist + A32_BINS);
+  RowTab* rt = reinterpret_cast<RowTab*>(smem + sel_smem_bytes(p.cap, A32_BINS));
+  unsigned* acc = reinterpret_cast<unsigned*>(smem + a32_fixed_bytes(p.cap));
+  int* touched = reinterpret_cast<int*>(acc + p.R);
+  __shared__ int s_work;
+  __shared__ int s_next;
+  __shared__ int s_ntouched;
+
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int total = p.U * p.P;
+  for (int s = tid; s < p.R; s += nt) acc[s] = 0u;
+  if (tid == 0) s_next = atomicAdd(p.queue, 1);
+#ifdef RPK_PHASE_PROF
+  long long t_prev = clock64();
+#endif
+  for (;;) {
+    if (tid == 0) {
+      s_work = s_next;
+      const int nx = atomicAdd(p.queue, 1);
+      s_next = nx;
+      if (nx < total) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.work_tab + nx / p.P) : "memory");
+      s_ntouched = 0;
+    }
+    __syncthreads();
+    const int w = s_work;
+    __syncthreads();
+    if (w >= total) break;
+    const int4 rec = p.work_tab[w / p.P];
+    const int u = rec.x;
+    const int pass = w % p.P;
+    const int r0 = pass * p.R;
+    const int ns = min(p.R, p.I - r0);
+    const int64_t xb = ((int64_t)(unsigned)rec.z) | ((int64_t)rec.w << 32);
+    const int d = rec.y;
+    const int64_t slot_out = (int64_t)u * p.P + pass;
+    PROF32_MARK(0);
+    if (d == 0) {  // user without history: empty prediction row (algorithms/base.py:123-127)
+      for (int t = tid; t < p.N; t += nt) {
+        p.part_idx[slot_out * p.N + t] = -1;
+        p.part_sq[slot_out * p.N + t] = 0;
+      }
+      if (tid == 0) p.part_len[slot_out] = 0;
+      continue;
+    }
+    const int sft = 9 + (d > 1 ? 32 - __clz(d - 1) : 0);
+    const int rows_per_chunk = min(nt, A32_ROWS);
+    // ---- sweep 1: approximate scores, slots recorded on their first touch (a sum is never zero again)
+    for (int c0 = 0; c0 < d; c0 += rows_per_chunk) {
+      const int n = min(rows_per_chunk, d - c0);
+      if (c0 > 0) __syncthreads();  // the previous chunk's table is still being read
+      stage_rows(p, xb, c0, n, pass, rt);
+      sweep_rows(p, rt, n, [&](u64 e) {
+        const unsigned j = (unsigned)(e >> 40) - (unsigned)r0;
+        if (j < (unsigned)ns) {
+          const unsigned a = (unsigned)((e & Q_MASK40) >> sft) | 1u;
+          if (atomicAdd(&acc[j], a) == 0u) {
+            const int pos = atomicAdd(&s_ntouched, 1);
+            if (pos < p.tcap) touched[pos] = (int)j;
+          }
+        }
+      });
+    }
+    __syncthreads();
+    const int n_touched = s_ntouched;
+    const bool sparse = n_touched <= p.tcap;
+    PROF32_MARK(1);
+#ifdef RPK_PHASE_PROF
+    if (tid == 0) {
+      atomicAdd(p.prof + 8, 1ull);
+      atomicAdd(p.prof + 9, (unsigned long long)sparse);
+      atomicAdd(p.prof + 10, (unsigned long long)n_touched);
+    }
+#endif
+    if (p.mask) {  // pipelines/pipeline.py:174-175 -- before the truncation to N
+      for (int r = tid; r < d; r += nt) {
+        const int j = p.indices[xb + r] - r0;
+        if (j >= 0 && j < ns) acc[j] = 0u;
+      }
+      __syncthreads();
+    }
+    PROF32_MARK(2);
+    ApproxSrc src{acc, sparse ? touched : nullptr, r0, sparse ? n_touched : ns, 0ull, 2ull * (u64)d,
+                  (u64)d * ((1ull << (40 - sft)) + 1ull)};
+    const int m = block_select_topk<true, A32_BITS>(src, p.N, list, p.cap, p.direct_cap, hist, sh);
+    PROF32_MARK(3);
+#ifdef RPK_PHASE_PROF
+    if (tid == 0) atomicAdd(p.prof + 11, (unsigned long long)(m < 0 ? 0 : m));
+#endif
+    // ---- restore the all-zero invariant
+    if (sparse) {
+      for (int t = tid; t < n_touched; t += nt) acc[touched[t]] = 0u;
+    } else {
+      for (int s = tid; s < ns; s += nt) acc[s] = 0u;
+    }
+    if (m < 0) {  // survivors do not fit: the exact kernel takes the whole user
+      if (tid == 0 && atomicExch(&p.ovf_flag[u], 1) == 0) p.ovf_tab[atomicAdd(p.ovf_count, 1)] = rec;
+      __syncthreads();
+      continue;
+    }
+    __syncthreads();
+    // ---- sweep 2: exact scores of the survivors (slot -> survivor number + 1, key -> exact sum)
+    for (int t = tid; t < m; t += nt) {
+      acc[list[t].idx - r0] = (unsigned)t + 1u;
+      list[t].key = 0ull;
+    }
+    __syncthreads();
+    PROF32_MARK(4);
+    const bool limbs = d <= LIMB_CHUNK;  // two 32-bit adds (20-bit limbs) cannot overflow
+    if (m > 0) {
+      for (int c0 = 0; c0 < d; c0 += rows_per_chunk) {
+        const int n = min(rows_per_chunk, d - c0);
+        if (d > rows_per_chunk) {  // a single chunk is still staged from sweep 1
+          if (c0 > 0) __syncthreads();
+          stage_rows(p, xb, c0, n, pass, rt);
+        }
+        sweep_rows(p, rt, n, [&](u64 e) {
+          const unsigned j = (unsigned)(e >> 40) - (unsigned)r0;
+          if (j < (unsigned)ns) {
+            const unsigned cn = acc[j];
+            if (cn) {
+              const u64 q = e & Q_MASK40;
+              if (limbs) {
+                unsigned* wd = reinterpret_cast<unsigned*>(&list[cn - 1u].key);
+                atomicAdd(wd, (unsigned)q & LIMB_MASK);
+                atomicAdd(wd + 1, (unsigned)(q >> LIMB_BITS));
+              } else {
+                atomicAdd(&list[cn - 1u].key, q);
+              }
+            }
+          }
+        });
+      }
+      __syncthreads();
+    }
+    PROF32_MARK(5);
+    for (int t = tid; t < m; t += nt) {
+      acc[list[t].idx - r0] = 0u;
+      if (limbs) {
+        const u64 kv = list[t].key;
+        list[t].key = ((kv >> 32) << LIMB_BITS) + (kv & 0xffffffffull);
+      }
+    }
+    __syncthreads();
+    ExactOrder ord;
+    if (m <= SEL_RANK_MAX) {
+      rank_sort_entries(ord, list, list + p.cap, m);
+    } else {
+      int n2 = 1;
+      while (n2 < m) n2 <<= 1;
+      for (int i = m + tid; i < n2; i += nt) {
+        Entry s;
+        s.key = 0;
+        s.idx = SENTINEL_IDX;
+        s.aux = 0;
+        list[i] = s;
+      }
+      __syncthreads();
+      bitonic_sort_entries(ord, list, n2);
+    }
+    const int mo = m < p.N ? m : p.N;
+    for (int t = tid; t < p.N; t += nt) {
+      p.part_idx[slot_out * p.N + t] = t < mo ? list[t].idx : -1;
+      p.part_sq[slot_out * p.N + t] = t < mo ? list[t].key : 0ull;
+    }
+    if (tid == 0) p.part_len[slot_out] = mo;
+    __syncthreads();
+    PROF32_MARK(6);
   }
 }
 
 // One warp per user: merge the P per-range lists (each best-first) into the final top-N.
+// Users flagged in `alt_flag` take their lists from the second set (the exact kernel's, alt_P ranges).
 __global__ void k_predict_finalize(const int* __restrict__ part_idx, const u64* __restrict__ part_sq,
                                    const int* __restrict__ part_len, int64_t U, int P, int N, int* __restrict__ out_idx,
-                                   double* __restrict__ out_val, int* __restrict__ out_len) {
+                                   double* __restrict__ out_val, int* __restrict__ out_len,
+                                   const int* __restrict__ alt_flag, const int* __restrict__ alt_idx,
+                                   const u64* __restrict__ alt_sq, const int* __restrict__ alt_len, int alt_P) {
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int PN = P * N;
   for (int64_t u = warp; u < U; u += nwarps) {
-    const int* pi = part_idx + u * PN;
-    const u64* ps = part_sq + u * PN;
+    const bool alt = alt_flag && alt_flag[u];
+    const int Pu = alt ? alt_P : P;
+    const int PN = Pu * N;
+    const int* pi = (alt ? alt_idx : part_idx) + u * PN;
+    const u64* ps = (alt ? alt_sq : part_sq) + u * PN;
+    const int* pl = (alt ? alt_len : part_len) + u * Pu;
     int tot = 0;
-    for (int q = 0; q < P; ++q) tot += part_len[u * P + q];
+    for (int q = 0; q < Pu; ++q) tot += pl[q];
     const int m = min(N, tot);
     for (int e = lane; e < PN; e += 32) {
       const int je = pi[e];
@@ -677,28 +1084,125 @@ static PredGeom predict_geometry(rpk_ctx* c, int N) {
   return g;
 }
 
-static void ensure_segments(rpk_ctx* c, const PredGeom& g) {
-  if (c->m_P == g.P && c->m_R == g.R) return;
+// Segment tables (offset of each item range inside every model row); one for each scoring kernel.
+static const int* ensure_segments(rpk_ctx* c, int P, int R, int which = 0) {
+  int& cP = which ? c->m_P2 : c->m_P;
+  int& cR = which ? c->m_R2 : c->m_R;
+  const char* name = which ? "m_seg2" : "m_seg";
   const int64_t I = c->m_I;
-  int* seg = c->buf<int>("m_seg", (size_t)I * (g.P + 1));
+  if (cP == P && cR == R) return c->get<int>(name);
+  int* seg = c->buf<int>(name, (size_t)I * (P + 1));
   if (I > 0) {
-    k_model_seg<<<ceil_div(I * (g.P + 1), 256), 256, 0, c->stream>>>(c->get<int64_t>("m_ptr"), c->get<u64>("m_ent"), I, g.P,
-                                                                      g.R, seg);
+    k_model_seg<<<ceil_div(I * (P + 1), 256), 256, 0, c->stream>>>(c->get<int64_t>("m_ptr"), c->get<u64>("m_ent"), I, P, R, seg);
     RPK_LAUNCH_CHECK(c);
   }
-  c->m_P = g.P;
-  c->m_R = g.R;
+  cP = P;
+  cR = R;
+  return seg;
+}
+static void ensure_segments(rpk_ctx* c, const PredGeom& g) { ensure_segments(c, g.P, g.R, 0); }
+
+// Padded block layout of the model (once per model) and the block table of a geometry.
+static void ensure_blocks(rpk_ctx* c, int P, int R) {
+  const int64_t I = c->m_I;
+  cudaStream_t st = c->stream;
+  const int64_t* m_ptr = c->get<int64_t>("m_ptr");
+  const u64* m_ent = c->get<u64>("m_ent");
+  if (!c->m_pad) {
+    int* len4 = c->buf<int>("m_len4", (size_t)I);
+    int64_t* ptr4 = c->buf<int64_t>("m_ptr4", (size_t)I + 1);
+    k_model_pad_len<<<ceil_div(I, 256), 256, 0, st>>>(m_ptr, I, len4);
+    RPK_LAUNCH_CHECK(c);
+    k_scan_i32_i64<<<1, 1024, 0, st>>>(len4, ptr4, I);
+    RPK_LAUNCH_CHECK(c);
+    // rows are padded by at most 3 entries each
+    u64* ent4 = c->buf<u64>("m_ent4", (size_t)c->m_nnz + 3 * (size_t)I + 4);
+    k_model_pad<<<(int)std::min<int64_t>(ceil_div(I * 32, 256), (int64_t)c->sm_count * 32), 256, 0, st>>>(m_ptr, m_ent, ptr4, I, ent4);
+    RPK_LAUNCH_CHECK(c);
+    c->m_pad = true;
+    c->m_P2 = 0;
+  }
+  if (c->m_P2 == P && c->m_R2 == R) return;
+  int2* blk = c->buf<int2>("m_blk", (size_t)I * P);
+  k_model_blocks<<<ceil_div(I * P, 256), 256, 0, st>>>(m_ptr, m_ent, c->get<int64_t>("m_ptr4"), I, P, R, blk);
+  RPK_LAUNCH_CHECK(c);
+  c->m_P2 = P;
+  c->m_R2 = R;
 }
 
-static void launch_predict(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_t U, const int64_t* indptr) {
+// Geometry of the 32-bit kernel: two CTAs per SM when that costs at most one more item range than one CTA
+// per SM would need (or at most three ranges), else one.
+struct Pred32Geom {
+  int cap, direct_cap, P, R, nt, tcap, ctas;
+  size_t smem;
+};
+
+static Pred32Geom predict32_geometry(rpk_ctx* c, int N) {
+  Pred32Geom g;
+  const bool tiny = c->flags & DBG_TINY_LIST;
+  g.cap = std::max(tiny ? 64 : 256, next_pow2(2 * std::max(N, 1)));
+  g.direct_cap = tiny ? std::max(N, 1) : std::min(g.cap, std::max(64, 2 * N));
+  const size_t fixed = a32_fixed_bytes(g.cap);
+  const int64_t I = c->m_I;
+  auto solve = [&](int ctas, int& P, int64_t& R, int64_t& T) -> bool {
+    const size_t per_cta = std::min<size_t>((size_t)c->smem_max, (size_t)c->smem_per_sm / ctas - 1024);
+    if (per_cta < fixed + 1024 + 4096) return false;
+    const size_t avail = per_cta - fixed - 256;
+    for (P = 1;; ++P) {
+      R = ((I + P - 1) / P + 3) & ~(int64_t)3;
+      if (R < 4) R = 4;
+      // touched-slot list: what is left after the accumulators, at least 2048 slots (or all of them)
+      const int64_t left = ((int64_t)avail - R * 4) / 4;
+      T = std::min<int64_t>(R, tiny ? 48 : std::min<int64_t>(left, 8192));
+      if (left >= std::min<int64_t>(R, tiny ? 48 : 2048)) return true;
+      if (R <= 4) return false;
+    }
+  };
+  int P1 = 0, P2 = 0;
+  int64_t R1 = 0, T1 = 0, R2 = 0, T2 = 0;
+  const bool ok1 = solve(1, P1, R1, T1);
+  const bool ok2 = solve(2, P2, R2, T2);
+  RPK_REQUIRE(ok1, "N too large for shared memory");
+  bool two = ok2 && (P2 <= 3 || P2 <= P1 + 1);
+  if (const char* e = getenv("RPK_PRED_CTAS")) {  // tuning hook
+    const int v = atoi(e);
+    if (v == 1) two = false;
+    if (v == 2 && ok2) two = true;
+  }
+  g.ctas = two ? 2 : 1;
+  g.P = two ? P2 : P1;
+  int64_t R = two ? R2 : R1, T = two ? T2 : T1;
+  if ((c->flags & DBG_MULTI_PASS) && g.P < 2 && I >= 8) {
+    g.P = 2;
+    R = ((I + g.P - 1) / g.P + 3) & ~(int64_t)3;
+    T = std::min<int64_t>(R, tiny ? 48 : 4096);
+  }
+  g.R = (int)R;
+  g.tcap = (int)T;
+  g.smem = fixed + (size_t)R * 4 + (size_t)T * 4;
+  g.nt = two ? 512 : (g.R >= 8192 ? 1024 : (g.R >= 2048 ? 512 : 256));
+  if (g.nt > 512) g.nt = 512;  // the kernel is compiled for at most 512 threads
+  if (const char* e = getenv("RPK_PRED_NT")) {  // tuning hook
+    int v = atoi(e);
+    if (v >= 64 && v <= 512 && v % 32 == 0) g.nt = v;
+  }
+  return g;
+}
+
+// Users in processing order (heaviest first) as 16-byte work records, plus the zeroed work counters.
+struct PredWork {
+  int4* tab;
+  int* queue;   // [0]: two-limb kernel, [1]: 32-bit kernel
+};
+
+static PredWork prepare_work(rpk_ctx* c, int64_t U, const int64_t* indptr) {
   cudaStream_t st = c->stream;
-  // heaviest users first
   u64* work = c->buf<u64>("p_work", (size_t)U);
   int* order = c->buf<int>("p_order", (size_t)U);
-  int* bcnt = c->buf<int>("p_bcnt", 65 * 2 + 2);
+  int* bcnt = c->buf<int>("p_bcnt", 65 * 2 + 4);
   int* boff = bcnt + 65;
   int* queue = boff + 65;
-  RPK_CUDA(cudaMemsetAsync(bcnt, 0, sizeof(int) * (65 * 2 + 2), st));
+  RPK_CUDA(cudaMemsetAsync(bcnt, 0, sizeof(int) * (65 * 2 + 4), st));
   k_row_lengths<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, work);
   RPK_LAUNCH_CHECK(c);
   k_bucket_count<<<ceil_div(U, 256), 256, 0, st>>>(work, 0, U, bcnt);
@@ -710,17 +1214,33 @@ static void launch_predict(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_
   int4* tab = c->buf<int4>("p_work_tab", (size_t)U);
   k_build_work_tab<<<ceil_div(U, 256), 256, 0, st>>>(order, indptr, U, tab);
   RPK_LAUNCH_CHECK(c);
-  pp.work_tab = tab;
-  pp.queue = queue;
+  return PredWork{tab, queue};
+}
+
+// Launches the two-limb kernel on the records of pp.work_tab (pp.n_work: device-side count, or null = U).
+static void launch_predict_kernel(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_t U) {
   RPK_CUDA(cudaFuncSetAttribute(k_predict, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
   int occ = 0;
   RPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_predict, g.nt, g.smem));
   RPK_REQUIRE(occ >= 1, "predict kernel does not fit on an SM");
   const int64_t total = U * g.P;
   const int grid = (int)std::min<int64_t>(total, (int64_t)c->sm_count * occ);
-  c->ev_record(4);
-  k_predict<<<grid, g.nt, g.smem, st>>>(pp);
+  pp.prof = nullptr;
+#ifdef RPK_PHASE_PROF
+  pp.prof = c->buf<unsigned long long>("p_prof", 16);
+  RPK_CUDA(cudaMemsetAsync(pp.prof, 0, 16 * sizeof(unsigned long long), c->stream));
+#endif
+  k_predict<<<grid, g.nt, g.smem, c->stream>>>(pp);
   RPK_LAUNCH_CHECK(c);
+}
+
+static void launch_predict(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_t U, const int64_t* indptr) {
+  const PredWork w = prepare_work(c, U, indptr);
+  pp.work_tab = w.tab;
+  pp.n_work = nullptr;
+  pp.queue = w.queue;
+  c->ev_record(4);
+  launch_predict_kernel(c, pp, g, U);
   c->ev_record(5);
   c->ev_valid[2] = true;
 }
@@ -732,6 +1252,7 @@ static void fill_common(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_t U
   pp.m_ptr = c->get<int64_t>("m_ptr");
   pp.m_ent = c->get<u64>("m_ent");
   pp.m_seg = c->get<int>("m_seg");
+  pp.n_work = nullptr;
   pp.m_rowmax = c->get<unsigned>("m_rowmax");
   pp.U = (int)U;
   pp.P = g.P;
@@ -781,10 +1302,79 @@ void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr_
     pp.part_idx = c->buf<int>("p_part_idx", (size_t)U * g.P * N);
     pp.part_sq = c->buf<u64>("p_part_sq", (size_t)U * g.P * N);
     pp.part_len = c->buf<int>("p_part_len", (size_t)U * g.P);
-    launch_predict(c, pp, g, U, indptr);
-    const int grid = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
-    k_predict_finalize<<<grid, 256, 0, st>>>(pp.part_idx, pp.part_sq, pp.part_len, U, g.P, N, o_idx.dev, o_val.dev, o_len.dev);
-    RPK_LAUNCH_CHECK(c);
+    const int fgrid = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
+    if (c->flags & DBG_WIDE_ACC) {  // debug: every user through the two-limb kernel (64-bit accumulators)
+      launch_predict(c, pp, g, U, indptr);
+      k_predict_finalize<<<fgrid, 256, 0, st>>>(pp.part_idx, pp.part_sq, pp.part_len, U, g.P, N, o_idx.dev, o_val.dev,
+                                                o_len.dev, nullptr, nullptr, nullptr, nullptr, 0);
+      RPK_LAUNCH_CHECK(c);
+    } else {
+      const Pred32Geom g2 = predict32_geometry(c, N);
+      Pred32Params qp;
+      qp.indices = indices;
+      ensure_blocks(c, g2.P, g2.R);
+      qp.ent4 = reinterpret_cast<const uint4*>(c->get<u64>("m_ent4"));
+      qp.blk = c->get<int2>("m_blk");
+      qp.U = (int)U;
+      qp.P = g2.P;
+      qp.R = g2.R;
+      qp.I = (int)c->m_I;
+      qp.N = N;
+      qp.mask = mask_history;
+      qp.cap = g2.cap;
+      qp.direct_cap = g2.direct_cap;
+      qp.tcap = g2.tcap;
+      qp.part_idx = c->buf<int>("p_part2_idx", (size_t)U * g2.P * N);
+      qp.part_sq = c->buf<u64>("p_part2_sq", (size_t)U * g2.P * N);
+      qp.part_len = c->buf<int>("p_part2_len", (size_t)U * g2.P);
+      qp.ovf_flag = c->buf<int>("p_ovf_flag", (size_t)U + 1);
+      qp.ovf_count = qp.ovf_flag + U;
+      qp.ovf_tab = c->buf<int4>("p_ovf_tab", (size_t)U);
+      RPK_CUDA(cudaMemsetAsync(qp.ovf_flag, 0, sizeof(int) * ((size_t)U + 1), st));
+      const PredWork w = prepare_work(c, U, indptr);
+      qp.work_tab = w.tab;
+      qp.queue = w.queue + 1;
+      qp.prof = nullptr;
+#ifdef RPK_PHASE_PROF
+      qp.prof = c->buf<unsigned long long>("p_prof32", 16);
+      RPK_CUDA(cudaMemsetAsync(qp.prof, 0, 16 * sizeof(unsigned long long), st));
+#endif
+      RPK_CUDA(cudaFuncSetAttribute(k_predict_a32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2.smem));
+      int occ = 0;
+      RPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_predict_a32, g2.nt, g2.smem));
+      RPK_REQUIRE(occ >= 1, "predict kernel does not fit on an SM");
+      const int grid = (int)std::min<int64_t>(U * g2.P, (int64_t)c->sm_count * occ);
+      c->ev_record(4);
+      k_predict_a32<<<grid, g2.nt, g2.smem, st>>>(qp);
+      RPK_LAUNCH_CHECK(c);
+      // users whose survivors overflowed the list: exact two-limb kernel (normally none; the kernel then exits)
+      pp.work_tab = qp.ovf_tab;
+      pp.n_work = qp.ovf_count;
+      pp.queue = w.queue;
+      launch_predict_kernel(c, pp, g, U);
+      c->ev_record(5);
+      c->ev_valid[2] = true;
+#ifdef RPK_PHASE_PROF
+      {
+        unsigned long long h[16];
+        int novf = 0;
+        RPK_CUDA(cudaMemcpyAsync(h, qp.prof, sizeof(h), cudaMemcpyDeviceToHost, st));
+        RPK_CUDA(cudaMemcpyAsync(&novf, qp.ovf_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RPK_CUDA(cudaStreamSynchronize(st));
+        static const char* nm[7] = {"fetch", "sweep1", "mask", "select", "clean+mark", "sweep2", "sort+out"};
+        unsigned long long tot = 0;
+        for (int k = 0; k < 7; ++k) tot += h[k];
+        fprintf(stderr, "[predict32 phases] grid=%d nt=%d P=%d R=%d tcap=%d smem=%zu occ=%d items=%llu sparse=%llu touched/item=%.0f survivors/item=%.1f overflow users=%d cycles/item=%.0f\n",
+                grid, g2.nt, g2.P, g2.R, g2.tcap, g2.smem, occ, h[8], h[9], h[8] ? (double)h[10] / h[8] : 0.0,
+                h[8] ? (double)h[11] / h[8] : 0.0, novf, h[8] ? (double)tot / h[8] : 0.0);
+        for (int k = 0; k < 7; ++k)
+          fprintf(stderr, "  %-10s %5.1f%%  %8.0f cycles/item\n", nm[k], 100.0 * h[k] / (tot ? tot : 1), h[8] ? (double)h[k] / h[8] : 0.0);
+      }
+#endif
+      k_predict_finalize<<<fgrid, 256, 0, st>>>(qp.part_idx, qp.part_sq, qp.part_len, U, g2.P, N, o_idx.dev, o_val.dev,
+                                                o_len.dev, qp.ovf_flag, pp.part_idx, pp.part_sq, pp.part_len, g.P);
+      RPK_LAUNCH_CHECK(c);
+    }
   }
   o_idx.finish(c);
   o_val.finish(c);

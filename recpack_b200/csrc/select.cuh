@@ -58,8 +58,8 @@ struct SelShared {
 
 // Shared-memory layout of the selection workspace: [list: cap + SEL_RANK_MAX entries][hist][SelShared]
 __host__ __device__ __forceinline__ size_t sel_list_bytes(int cap) { return (size_t)(cap + SEL_RANK_MAX) * sizeof(Entry); }
-__host__ __device__ __forceinline__ size_t sel_smem_bytes(int cap) {
-  return sel_list_bytes(cap) + SEL_BINS * sizeof(int) + ((sizeof(SelShared) + 15) / 16) * 16;
+__host__ __device__ __forceinline__ size_t sel_smem_bytes(int cap, int bins = SEL_BINS) {
+  return sel_list_bytes(cap) + bins * sizeof(int) + ((sizeof(SelShared) + 15) / 16) * 16;
 }
 
 __device__ __forceinline__ u64 warp_min_u64(u64 v) {
@@ -207,11 +207,12 @@ __device__ __forceinline__ void find_boundary_bin(const int* hist, int nb, int g
   __syncthreads();
 }
 
-// Histogram geometry for keys in [lo, hi]: at most SEL_BINS bins of 2^shift consecutive keys.
+// Histogram geometry for keys in [lo, hi]: at most 2^BITS (<= SEL_BINS) bins of 2^shift consecutive keys.
+template <int BITS = 12>
 __device__ __forceinline__ void bin_geometry(u64 lo, u64 hi, int& shift, int& nb) {
   const u64 range = hi - lo;
   const int bits = range ? 64 - __clzll((long long)range) : 0;
-  shift = bits > 12 ? bits - 12 : 0;
+  shift = bits > BITS ? bits - BITS : 0;
   nb = (int)(range >> shift) + 1;
 }
 
@@ -246,13 +247,13 @@ __device__ void generic_stats(const Src& src, SelShared* sh) {
 // One refinement run over the candidates of `src`.  On entry [lo, hi] bounds the keys of interest,
 // n_in = candidates inside, g = candidates known to be above hi.  Descends while g + n_in > room and
 // lo < hi.  Results in sh->lo / sh->hi / sh->g_new / sh->n_in.
-template <class Src>
+template <int BITS = 12, class Src>
 __device__ void refine_keys(Src& src, int need, int room, u64 lo, u64 hi, int g, int n_in, int* hist, SelShared* sh) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const u64 M = src.margin();
   while (g + n_in > room && lo < hi) {
     int shift, nb;
-    bin_geometry(lo, hi, shift, nb);
+    bin_geometry<BITS>(lo, hi, shift, nb);
     for (int b = tid; b < nb; b += nt) hist[b] = 0;
     src.set_floor(lo > M ? lo - M : 0ull);
     __syncthreads();
@@ -282,8 +283,10 @@ __device__ void refine_keys(Src& src, int need, int room, u64 lo, u64 hi, int g,
 }
 
 // Copies every candidate with key >= thr to list; returns how many there were (may exceed cap).
+// With `certain` set, *certain is also incremented for every candidate with key >= edge (edge >= thr).
 template <class Src>
-__device__ int compact_above(Src& src, u64 thr, Entry* list, int cap, SelShared* sh) {
+__device__ int compact_above(Src& src, u64 thr, Entry* list, int cap, SelShared* sh, u64 edge = 0ull,
+                             int* certain = nullptr) {
   if (threadIdx.x == 0) sh->count = 0;
   src.set_floor(thr);
   __syncthreads();
@@ -292,6 +295,7 @@ __device__ int compact_above(Src& src, u64 thr, Entry* list, int cap, SelShared*
       Entry e;
       src.entry(slot, e);
       append_one(e, list, cap, &sh->count);
+      if (certain && k >= edge) atomicAdd(certain, 1);
     }
   });
   __syncthreads();
@@ -301,7 +305,10 @@ __device__ int compact_above(Src& src, u64 thr, Entry* list, int cap, SelShared*
 // Returns m = number of selected entries (<= K); list[0..m) holds them best-first.
 // defer_max > 0: when at most defer_max survivors remain they are returned UNSORTED (*sorted = false,
 // return value = their number, possibly > K) so that the caller can sort them elsewhere.
-template <class Src>
+// SURVIVORS_ONLY: the source cannot compare exactly (cmp3 unusable).  The call then returns every candidate
+// that could belong to the top K -- unsorted, their number (possibly > K, at most cap) as the result --
+// or -1 when they do not fit the list; the caller settles the order by other means.
+template <bool SURVIVORS_ONLY = false, int BITS = 12, class Src>
 __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int direct_cap, int* hist, SelShared* sh,
                                  int defer_max = 0, bool* sorted = nullptr) {
   const int tid = threadIdx.x, nt = blockDim.x;
@@ -327,7 +334,7 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
     //          candidates, which the copy itself verifies
     if (n_c >= SEL_GUESS_MIN && kmax > kmin) {
       int shift, nb;
-      bin_geometry(kmin, kmax, shift, nb);
+      bin_geometry<BITS>(kmin, kmax, shift, nb);
       for (int b = tid; b < nb; b += nt) hist[b] = 0;
       __syncthreads();
       src.for_each_sampled([&](int, u64 k) {
@@ -341,21 +348,30 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
       const u64 edge = kmin + ((u64)sh->bstar << shift);
       const u64 thr = edge > M ? edge - M : 0;
       __syncthreads();
-      const int got = compact_above(src, thr, list, cap, sh);
-      if (got >= K && got <= cap) m = got;
+      // the guess stands when at least K candidates lie at or above the edge (they certainly beat everything
+      // below edge - M) and the copy fitted
+      if (tid == 0) sh->count2 = 0;
+      const int got = compact_above(src, thr, list, cap, sh, edge, &sh->count2);
+      if (sh->count2 >= K && got <= cap) m = got;
+      __syncthreads();
     }
     if (m < 0) {
       // ---- B: exact radix refinement on the (approximate) key until the survivors fit
-      refine_keys(src, K, room, kmin, kmax, 0, n_c, hist, sh);
+      refine_keys<BITS>(src, K, room, kmin, kmax, 0, n_c, hist, sh);
       u64 lo = sh->lo, hi = sh->hi;
       int g = sh->g_new, n_in = sh->n_in;
       u64 thr = lo > M ? lo - M : 0;
       __syncthreads();
       m = compact_above(src, thr, list, cap, sh);
+      if (SURVIVORS_ONLY && m > cap) {
+        src.set_floor(0ull);
+        __syncthreads();
+        return -1;
+      }
       if (m > cap) {
         // ---- C: a band of (near-)equal keys is too large.  Pin tau = the K-th largest akey.
         __syncthreads();
-        refine_keys(src, K, -1, lo, hi, g, n_in, hist, sh);
+        refine_keys<BITS>(src, K, -1, lo, hi, g, n_in, hist, sh);
         const u64 tau = sh->lo;
         const u64 band_lo = tau > M ? tau - M : 0;
         const u64 band_hi = tau + M < tau ? ~0ull : tau + M;
@@ -460,7 +476,7 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
           const int iroom = cap - have;
           while (ig + iin > iroom && ilo < ihi) {
             int shift, nb;
-            bin_geometry(ilo, ihi, shift, nb);
+            bin_geometry<BITS>(ilo, ihi, shift, nb);
             for (int b = tid; b < nb; b += nt) hist[b] = 0;
             __syncthreads();
             src.for_each([&](int slot, u64 k) {
@@ -499,6 +515,10 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
   }
   // ---- D: exact sort of the survivors
   src.set_floor(0ull);
+  if (SURVIVORS_ONLY) {
+    __syncthreads();
+    return m > cap ? -1 : m;
+  }
   if (m > cap) m = cap;
   if (sorted) *sorted = true;
   if (defer_max > 0 && m <= defer_max) {
