@@ -781,6 +781,74 @@ __device__ __forceinline__ void sweep_rows(const Pred32Params& p, const RowTab* 
   }
 }
 
+// Survivors of the approximate scores in one histogram round: 2048 bins over [0, kmax] (kmax = the largest
+// sum seen by sweep 1), the bin holding the K-th largest key found with two barriers, then every candidate
+// with key >= that bin's lower edge - margin is copied to the list.  Returns their number (unsorted), or -1
+// when they do not fit -- the caller then runs the general refinement.  `hist` must be all zero on entry and is
+// all zero again on return.
+__device__ int a32_select(const unsigned* acc, const int* touched, int n, int r0, unsigned kmax, u64 margin, int K,
+                          Entry* list, int cap, int direct_cap, int* hist, SelShared* sh) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  unsigned thr = 1u;
+  if (tid == 0) sh->count = 0;
+  if (n > direct_cap) {
+    const int bits = 32 - __clz(kmax | 1u);
+    const int shift = bits > A32_BITS ? bits - A32_BITS : 0;
+    for (int slot = tid; slot < n; slot += nt) {
+      const unsigned k = acc[touched ? touched[slot] : slot];
+      if (k) atomicAdd(&hist[min(k >> shift, (unsigned)(A32_BINS - 1))], 1);
+    }
+    __syncthreads();
+    const int per = (A32_BINS + nt - 1) / nt;
+    const int b0 = min(A32_BINS, tid * per), b1 = min(A32_BINS, b0 + per);
+    int tsum = 0;
+    for (int b = b0; b < b1; ++b) tsum += hist[b];
+    int incl = tsum;  // members of my bins and of the higher lanes' bins
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_down_sync(0xffffffffu, incl, o);
+      if (lane + o < 32) incl += t;
+    }
+    if (lane == 0) sh->warp_tot[warp] = incl;
+    if (tid == 0) sh->bstar = 0;  // fewer than K candidates: everything survives
+    __syncthreads();
+    int above = incl - tsum;
+    for (int q = warp + 1; q < nwarps; ++q) above += sh->warp_tot[q];
+    if (above < K && above + tsum >= K) {
+      for (int b = b1 - 1; b >= b0; --b) {
+        above += hist[b];
+        if (above >= K) {
+          sh->bstar = b;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    for (int b = b0; b < b1; ++b) hist[b] = 0;
+    const u64 edge = (u64)sh->bstar << shift;
+    thr = edge > margin + 1ull ? (unsigned)(edge - margin) : 1u;
+  } else {
+    __syncthreads();
+  }
+  for (int slot = tid; slot < n; slot += nt) {
+    const int j = touched ? touched[slot] : slot;
+    const unsigned k = acc[j];
+    if (k >= thr) {
+      const int pos = atomicAdd(&sh->count, 1);
+      if (pos < cap) {
+        Entry e;
+        e.key = (u64)k;
+        e.idx = r0 + j;
+        e.aux = 0;
+        list[pos] = e;
+      }
+    }
+  }
+  __syncthreads();
+  const int m = sh->count;
+  return m > cap ? -1 : m;
+}
+
 #ifdef RPK_PHASE_PROF
 #define PROF32_MARK(k) PROF_MARK(k)
 #else
@@ -802,10 +870,12 @@ __global__ void __launch_bounds__(512, 2) k_predict_a32(Pred32Params p) {
   __shared__ int s_work;
   __shared__ int s_next;
   __shared__ int s_ntouched;
+  __shared__ unsigned s_kmax;
 
   const int tid = threadIdx.x, nt = blockDim.x;
   const int total = p.U * p.P;
   for (int s = tid; s < p.R; s += nt) acc[s] = 0u;
+  for (int b = tid; b < A32_BINS; b += nt) hist[b] = 0;
   if (tid == 0) s_next = atomicAdd(p.queue, 1);
 #ifdef RPK_PHASE_PROF
   long long t_prev = clock64();
@@ -817,6 +887,7 @@ __global__ void __launch_bounds__(512, 2) k_predict_a32(Pred32Params p) {
       s_next = nx;
       if (nx < total) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.work_tab + nx / p.P) : "memory");
       s_ntouched = 0;
+      s_kmax = 0u;
     }
     __syncthreads();
     const int w = s_work;
@@ -842,6 +913,7 @@ __global__ void __launch_bounds__(512, 2) k_predict_a32(Pred32Params p) {
     const int sft = 9 + (d > 1 ? 32 - __clz(d - 1) : 0);
     const int rows_per_chunk = min(nt, A32_ROWS);
     // ---- sweep 1: approximate scores, slots recorded on their first touch (a sum is never zero again)
+    unsigned mx = 0u;  // largest sum this thread produced
     for (int c0 = 0; c0 < d; c0 += rows_per_chunk) {
       const int n = min(rows_per_chunk, d - c0);
       if (c0 > 0) __syncthreads();  // the previous chunk's table is still being read
@@ -850,13 +922,17 @@ __global__ void __launch_bounds__(512, 2) k_predict_a32(Pred32Params p) {
         const unsigned j = (unsigned)(e >> 40) - (unsigned)r0;
         if (j < (unsigned)ns) {
           const unsigned a = (unsigned)((e & Q_MASK40) >> sft) | 1u;
-          if (atomicAdd(&acc[j], a) == 0u) {
+          const unsigned old = atomicAdd(&acc[j], a);
+          mx = max(mx, old + a);
+          if (old == 0u) {
             const int pos = atomicAdd(&s_ntouched, 1);
             if (pos < p.tcap) touched[pos] = (int)j;
           }
         }
       });
     }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((tid & 31) == 0 && mx) atomicMax(&s_kmax, mx);
     __syncthreads();
     const int n_touched = s_ntouched;
     const bool sparse = n_touched <= p.tcap;
@@ -878,7 +954,12 @@ __global__ void __launch_bounds__(512, 2) k_predict_a32(Pred32Params p) {
     PROF32_MARK(2);
     ApproxSrc src{acc, sparse ? touched : nullptr, r0, sparse ? n_touched : ns, 0ull, 2ull * (u64)d,
                   (u64)d * ((1ull << (40 - sft)) + 1ull)};
-    const int m = block_select_topk<true, A32_BITS>(src, p.N, list, p.cap, p.direct_cap, hist, sh);
+    int m = a32_select(acc, src.touched, src.ns, r0, s_kmax, src.margin_, p.N, list, p.cap, p.direct_cap, hist, sh);
+    if (m < 0) {  // a crowded boundary bin: general refinement
+      __syncthreads();
+      m = block_select_topk<true, A32_BITS>(src, p.N, list, p.cap, p.direct_cap, hist, sh);
+      for (int b = tid; b < A32_BINS; b += nt) hist[b] = 0;
+    }
     PROF32_MARK(3);
 #ifdef RPK_PHASE_PROF
     if (tid == 0) atomicAdd(p.prof + 11, (unsigned long long)(m < 0 ? 0 : m));
@@ -939,8 +1020,24 @@ __global__ void __launch_bounds__(512, 2) k_predict_a32(Pred32Params p) {
     }
     __syncthreads();
     ExactOrder ord;
+    const int mo = m < p.N ? m : p.N;
     if (m <= SEL_RANK_MAX) {
-      rank_sort_entries(ord, list, list + p.cap, m);
+      // rank every survivor by counting the ones that precede it (nt / 64 threads per survivor) and write
+      // it straight to its place
+      const int tpe = nt / SEL_RANK_MAX, i = tid / tpe, part = tid % tpe;
+      int rank = 0;
+      Entry a;
+      a.key = 0;
+      a.idx = 0;
+      if (i < m) {
+        a = list[i];
+        for (int f = part; f < m; f += tpe) rank += (f != i) && entry_before(ord, list[f], a);
+      }
+      for (int o = tpe >> 1; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+      if (i < m && part == 0 && rank < p.N) {
+        p.part_idx[slot_out * p.N + rank] = a.idx;
+        p.part_sq[slot_out * p.N + rank] = a.key;
+      }
     } else {
       int n2 = 1;
       while (n2 < m) n2 <<= 1;
@@ -953,11 +1050,14 @@ __global__ void __launch_bounds__(512, 2) k_predict_a32(Pred32Params p) {
       }
       __syncthreads();
       bitonic_sort_entries(ord, list, n2);
+      for (int t = tid; t < mo; t += nt) {
+        p.part_idx[slot_out * p.N + t] = list[t].idx;
+        p.part_sq[slot_out * p.N + t] = list[t].key;
+      }
     }
-    const int mo = m < p.N ? m : p.N;
-    for (int t = tid; t < p.N; t += nt) {
-      p.part_idx[slot_out * p.N + t] = t < mo ? list[t].idx : -1;
-      p.part_sq[slot_out * p.N + t] = t < mo ? list[t].key : 0ull;
+    for (int t = mo + tid; t < p.N; t += nt) {
+      p.part_idx[slot_out * p.N + t] = -1;
+      p.part_sq[slot_out * p.N + t] = 0ull;
     }
     if (tid == 0) p.part_len[slot_out] = mo;
     __syncthreads();
@@ -1184,7 +1284,7 @@ static Pred32Geom predict32_geometry(rpk_ctx* c, int N) {
   if (g.nt > 512) g.nt = 512;  // the kernel is compiled for at most 512 threads
   if (const char* e = getenv("RPK_PRED_NT")) {  // tuning hook
     int v = atoi(e);
-    if (v >= 64 && v <= 512 && v % 32 == 0) g.nt = v;
+    if (v == 64 || v == 128 || v == 256 || v == 512) g.nt = v;
   }
   return g;
 }
