@@ -812,8 +812,8 @@ __device__ int a32_select(const unsigned* acc, const int* touched, int n, int r0
     if (lane == 0) sh->warp_tot[warp] = incl;
     if (tid == 0) sh->bstar = 0;  // fewer than K candidates: everything survives
     __syncthreads();
-    int above = incl - tsum;
-    for (int q = warp + 1; q < nwarps; ++q) above += sh->warp_tot[q];
+    int above = (lane > warp && lane < nwarps) ? sh->warp_tot[lane] : 0;  // totals of the higher warps
+    above = __reduce_add_sync(0xffffffffu, above) + incl - tsum;
     if (above < K && above + tsum >= K) {
       for (int b = b1 - 1; b >= b0; --b) {
         above += hist[b];
