@@ -15,7 +15,7 @@ from sklearn.base import BaseEstimator
 from sklearn.utils.validation import check_is_fitted
 
 from .engine import get_engine
-from .matrix import binary_structure, to_csr_matrix
+from .matrix import binary_structure, device_structure, to_csr_matrix, to_host
 
 logger = logging.getLogger("recpack")
 
@@ -99,12 +99,61 @@ class ItemSimilarityMatrixAlgorithm(Algorithm):
     predict_topK = None
     remove_history = False
 
+    # -- similarity_matrix_: host CSR, materialised on first use when the fit result lives on the device ----
+    @property
+    def similarity_matrix_(self):
+        d = self.__dict__
+        S = d.get("_similarity_host")
+        if S is None:
+            if d.get("_fit_dev") is None:
+                raise AttributeError(f"{type(self).__name__} object has no attribute 'similarity_matrix_'")
+            S = self._materialize_similarity()
+        return S
+
+    @similarity_matrix_.setter
+    def similarity_matrix_(self, S):
+        self.__dict__["_similarity_host"] = S
+        self.__dict__["_fit_dev"] = None  # an assigned matrix replaces the device-resident fit result
+
+    def _materialize_similarity(self):
+        dev = self.__dict__["_fit_dev"]
+        idx, val, ln = to_host(dev["idx"], dev["val"], dev["len"])
+        S = lists_to_csr(idx, val, ln, dev["I"])
+        self.__dict__["_similarity_host"] = S
+        return S
+
+    def _set_device_fit(self, out, I, device):
+        """Keep the rank-ordered top-K lists of a fit on the device (torch tensors owned by this object)."""
+        d = self.__dict__
+        d["_similarity_host"] = None
+        d["_fit_dev"] = {"idx": out["idx"], "val": out["val"], "len": out["len"], "I": int(I), "device": int(device),
+                         "empty_rows": int((out["len"] == 0).sum().item())}
+
+    def __sklearn_is_fitted__(self):
+        d = self.__dict__
+        return d.get("_similarity_host") is not None or d.get("_fit_dev") is not None
+
+    def __getstate__(self):
+        if self.__dict__.get("_fit_dev") is not None:
+            self.similarity_matrix_  # pickles carry the host matrix, never device memory
+        state = dict(super().__getstate__())
+        state["_fit_dev"] = None
+        return state
+
     # -- device model management ---------------------------------------------------------------
     def _device_model_key(self):
         S = self.similarity_matrix_
         return (id(S), S.shape, S.nnz, S.data.ctypes.data, S.indices.ctypes.data)
 
     def _ensure_device_model(self, engine):
+        dev = self.__dict__.get("_fit_dev")
+        if dev is not None and dev["device"] == engine.device:
+            key = ("dev", engine.device, id(dev["idx"]))
+            if getattr(engine, "_model_key", None) != key:
+                engine.model_load_topk(dev["I"], dev["idx"].shape[1], dev["idx"], dev["val"], dev["len"])
+                engine._model_key = key
+                engine._model_owner = dev["idx"]  # keeps the id unique while it is the loaded model
+            return
         S = self.similarity_matrix_
         if not isinstance(S, csr_matrix):
             S = csr_matrix(S)
@@ -112,48 +161,49 @@ class ItemSimilarityMatrixAlgorithm(Algorithm):
         key = (engine.device,) + self._device_model_key()
         if getattr(engine, "_model_key", None) == key:
             return
-        lists = getattr(self, "_fit_lists", None)
-        if lists is not None and lists.get("key") == self._device_model_key():
-            if lists.get("token") == (engine.nonce, engine.fit_token()):
-                engine.model_load_last_fit(lists["token"][1])  # the fit result is still on the device
-            else:
-                engine.model_load_topk(S.shape[0], lists["idx"].shape[1], lists["idx"], lists["val"], lists["len"])
-        else:
-            if not S.has_canonical_format:
-                S = S.copy()
-                S.sum_duplicates()
-            if S.nnz and not np.all(S.data):
-                S = S.copy()
-                S.eliminate_zeros()
-            engine.model_load_csr(S.shape[0], np.ascontiguousarray(S.indptr, dtype=np.int64),
-                                  np.ascontiguousarray(S.indices, dtype=np.int32),
-                                  np.ascontiguousarray(S.data, dtype=np.float64))
+        if not S.has_canonical_format:
+            S = S.copy()
+            S.sum_duplicates()
+        if S.nnz and not np.all(S.data):
+            S = S.copy()
+            S.eliminate_zeros()
+        engine.model_load_csr(S.shape[0], np.ascontiguousarray(S.indptr, dtype=np.int64),
+                              np.ascontiguousarray(S.indices, dtype=np.int32),
+                              np.ascontiguousarray(S.data, dtype=np.float64))
         engine._model_key = key
+        engine._model_owner = self.__dict__.get("_similarity_host")
+
+    def _n_items(self):
+        dev = self.__dict__.get("_fit_dev")
+        return dev["I"] if dev is not None else self.similarity_matrix_.shape[0]
 
     def _predict(self, X: csr_matrix) -> csr_matrix:
         engine = get_engine()
-        S = self.similarity_matrix_
-        if X.shape[1] != S.shape[0]:
+        I = self._n_items()
+        if X.shape[1] != I:
             raise ValueError("matmul: dimension mismatch with signature (n?,k),(k,m?)->(n?,m?)")
         self._ensure_device_model(engine)
-        X, indptr, indices = binary_structure(X)
         U = X.shape[0]
         if self.predict_topK is None:
+            X, indptr, indices = binary_structure(X)
             o_ptr, o_idx, o_val = engine.predict_csr(U, indptr, indices, mask_history=bool(self.remove_history))
-            return csr_matrix((o_val, o_idx, o_ptr), shape=(U, S.shape[1]))
+            return csr_matrix((o_val, o_idx, o_ptr), shape=(U, I))
         N = int(self.predict_topK)
-        top = engine.predict_topn(U, indptr, indices, N, mask_history=bool(self.remove_history))
-        return lists_to_csr(top["idx"], top["val"], top["len"], S.shape[1], attach=True)
+        X, _, _, ptr_d, idx_d = device_structure(X, engine.device)
+        top = engine.predict_topn(U, ptr_d, idx_d, N, mask_history=bool(self.remove_history))
+        idx, val, ln = to_host(top["idx"], top["val"], top["len"])
+        M = lists_to_csr(idx, val, ln, I, attach=True)
+        M._rpk_topn_dev = (top["idx"], top["len"], engine.device)  # the metrics read the lists where they are
+        return M
 
     def _check_fit_complete(self):
         super()._check_fit_complete()
-        assert hasattr(self, "similarity_matrix_")
-        S = self.similarity_matrix_
-        lists = getattr(self, "_fit_lists", None)
-        if lists is not None and lists.get("key") == self._device_model_key():
-            missing = int(np.count_nonzero(lists["len"] == 0))
+        assert self.__sklearn_is_fitted__()  # hasattr(self, "similarity_matrix_") without building the matrix
+        dev = self.__dict__.get("_fit_dev")
+        if dev is not None:
+            missing = dev["empty_rows"]
         else:
-            S = csr_matrix(S)
+            S = csr_matrix(self.similarity_matrix_)
             rows_with_score = np.diff(S.indptr) > 0
             if S.nnz and not np.all(S.data):
                 rows_with_score = np.asarray((S != 0).sum(axis=1)).ravel() > 0

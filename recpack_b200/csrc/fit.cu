@@ -100,35 +100,42 @@ __global__ void k_find_heavy(const int* __restrict__ n, int64_t I, int* __restri
     if (s < HEAVY_CAP) heavy_ids[s] = (int)j;
   }
 }
-// pair[a * HEAVY_CAP + b] = exact number of users with both heavy items a and b (one warp per user,
-// lane h looks heavy item h up in the user's sorted history).
+// pair[a * HEAVY_CAP + b] = exact number of users with both heavy items a and b.  A group of G lanes
+// (G = H rounded up to a power of two) takes one user, lane h looks heavy item h up in the user's sorted
+// history; counts are kept per thread and flushed once.
 __global__ void k_heavy_pairs(const int64_t* __restrict__ indptr, const int* __restrict__ indices, int64_t U,
                               const int* __restrict__ heavy_ids, const int* __restrict__ heavy_n, int* __restrict__ pair) {
   const int H = heavy_n[0];
   if (H < 2 || H > HEAVY_CAP) return;
+  int G = 2;
+  while (G < H) G <<= 1;
   const int lane = threadIdx.x & 31;
+  const int h = lane & (G - 1), grp = lane / G, per_warp = 32 / G;
+  const unsigned gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int target = lane < H ? heavy_ids[lane] : -1;
-  for (int64_t u = warp; u < U; u += nwarps) {
-    int64_t lo = indptr[u], hi = indptr[u + 1];
+  const int target = h < H ? heavy_ids[h] : -1;
+  for (int64_t u0 = warp * per_warp; u0 < U; u0 += nwarps * per_warp) {
+    const int64_t u = u0 + grp;
     bool has = false;
-    if (target >= 0) {
+    if (u < U && target >= 0) {
+      int64_t lo = indptr[u], hi = indptr[u + 1];
+      const int64_t end = hi;
       while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
         const int v = indices[mid];
         if (v < target) lo = mid + 1;
         else hi = mid;
       }
-      has = lo < indptr[u + 1] && indices[lo] == target;
+      has = lo < end && indices[lo] == target;
     }
-    const unsigned m = __ballot_sync(0xffffffffu, has);
+    const unsigned m = (__ballot_sync(0xffffffffu, has) >> (grp * G)) & gmask;
     if (has) {
-      unsigned others = m & ~(1u << lane);
+      unsigned others = m & ~(1u << h);
       while (others) {
         const int b = __ffs(others) - 1;
         others &= others - 1;
-        atomicAdd(&pair[lane * HEAVY_CAP + b], 1);
+        atomicAdd(&pair[h * HEAVY_CAP + b], 1);
       }
     }
   }

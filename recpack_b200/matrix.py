@@ -5,6 +5,8 @@ wrappers recpack/algorithms/base.py:129-151 without importing recpack: an object
 is a scipy csr_matrix or quacks like recpack's InteractionMatrix (has ``values`` returning a CSR)."""
 from __future__ import annotations
 
+import warnings
+
 import numpy as np
 from scipy.sparse import csr_matrix
 
@@ -58,3 +60,49 @@ def binary_structure(X: csr_matrix):
             pass
         return X, indptr, indices
     return X, memo[1], memo[2]
+
+
+def device_structure(X: csr_matrix, device: int):
+    """binary_structure plus the two index arrays as torch CUDA tensors on ``device``.
+
+    The device copies are memoised on the (canonical) matrix object next to the host memo, so fitting and
+    predicting on the same matrix -- or evaluating several metrics against the same ``y_true`` -- uploads it
+    once; they are freed with the matrix.  Returns (X, indptr, indices, indptr_dev, indices_dev)."""
+    import torch
+
+    X, indptr, indices = binary_structure(X)
+    sig = getattr(X, "_rpk_canon", (None,))[0]
+    memo = getattr(X, "_rpk_dev", None)
+    if memo is not None and memo[0] == sig and memo[1] == device:
+        return X, indptr, indices, memo[2], memo[3]
+    dev = torch.device("cuda", device)
+    with warnings.catch_warnings():  # read-only numpy arrays are fine here: the tensors are only read
+        warnings.simplefilter("ignore")
+        ptr_d = torch.from_numpy(indptr).to(dev, non_blocking=True)
+        idx_d = torch.from_numpy(indices).to(dev, non_blocking=True)
+    if sig is not None:
+        try:
+            X._rpk_dev = (sig, device, ptr_d, idx_d)
+        except AttributeError:
+            pass
+    return X, indptr, indices, ptr_d, idx_d
+
+
+def to_host(*tensors):
+    """Device tensors -> numpy arrays through pinned staging buffers (torch's caching host allocator recycles
+    them, so steady-state calls pay the PCIe copy only).  One synchronisation for all of them."""
+    import torch
+
+    hs = []
+    for t in tensors:
+        if t is None:
+            hs.append(None)
+            continue
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        hs.append(h)
+    for t in tensors:
+        if t is not None:
+            torch.cuda.current_stream(t.device).synchronize()
+            break
+    return tuple(None if h is None else h.numpy() for h in hs)

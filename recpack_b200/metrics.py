@@ -12,7 +12,7 @@ import pandas as pd
 from scipy.sparse import csr_matrix
 
 from .engine import get_engine
-from .matrix import binary_structure
+from .matrix import device_structure, to_host
 from .util import ranks_from_lists, top_k_lists
 
 
@@ -52,16 +52,23 @@ class ListwiseMetricK:
         y_true = csr_matrix(y_true) if not isinstance(y_true, csr_matrix) else y_true
         self._verify_shape(y_true, y_pred)
         K = int(self.K)
+        engine = get_engine()
         lists = getattr(y_pred, "_rpk_topn", None)
+        top_idx = top_len = None
         if lists is not None and lists[0].shape[1] >= K and lists[0].shape[0] == y_true.shape[0]:
             idx, ln = lists
+            dev = getattr(y_pred, "_rpk_topn_dev", None)
+            if dev is not None and dev[2] == engine.device:
+                top_idx, top_len = dev[0], dev[1]  # the lists are still on the device: nothing to upload
         else:
             idx, ln = top_k_lists(y_pred, K)
-        yt, t_ptr, t_idx = binary_structure(y_true)
+        if top_idx is None:
+            top_idx, top_len = np.ascontiguousarray(idx), np.ascontiguousarray(ln)
+        yt, t_ptr, t_idx, t_ptr_d, t_idx_d = device_structure(y_true, engine.device)
         U, I = yt.shape
-        engine = get_engine()
-        sums, n_users, per_user = engine.metrics_topn(U, idx.shape[1], np.ascontiguousarray(idx), np.ascontiguousarray(ln),
-                                                      t_ptr, t_idx, [(self._kind, K)])
+        sums, n_users, per_user = engine.metrics_topn(U, idx.shape[1], top_idx, top_len, t_ptr_d, t_idx_d, [(self._kind, K)])
+        if not isinstance(per_user, np.ndarray):
+            (per_user,) = to_host(per_user)
         users = np.flatnonzero(np.diff(t_ptr) > 0)  # metrics/base.py:106-123
         self.user_id_map_ = users
         self.num_users_, self.num_items_ = len(users), I

@@ -12,7 +12,7 @@ from scipy.sparse import csr_matrix
 
 from .base import TopKItemSimilarityMatrixAlgorithm, lists_to_csr
 from .engine import get_engine
-from .matrix import binary_structure
+from .matrix import device_structure, to_host
 
 
 class ItemKNN(TopKItemSimilarityMatrixAlgorithm):
@@ -62,7 +62,7 @@ class ItemKNN(TopKItemSimilarityMatrixAlgorithm):
             # (SURVEY.md 8f-2).  No silent CPU path: say so.
             raise NotImplementedError("normalize_X=True is not implemented on the B200 path yet")
         engine = get_engine()
-        X, indptr, indices = binary_structure(X)
+        X, indptr, indices, ptr_d, idx_d = device_structure(X, engine.device)
         U, I = X.shape
         item_pow = None
         if self.similarity == "conditional_probability" and self.pop_discount:
@@ -72,20 +72,15 @@ class ItemKNN(TopKItemSimilarityMatrixAlgorithm):
             nz = n > 0
             item_pow[nz] = np.power(1 / n[nz], self.pop_discount)
         K = int(self.K)
-        out = engine.fit_topk(U, I, indptr, indices, K, similarity=self.similarity, item_pow=item_pow, want_cnt=False)
-        self._set_similarity_from_lists(out, I)
-        if not self.normalize_sim:  # the device copy holds the un-normalised values
-            self._fit_lists["token"] = (engine.nonce, engine.fit_token())
-
-    def _set_similarity_from_lists(self, out, I):
-        idx, val, ln = out["idx"], out["val"], out["len"]
+        # the rank-ordered lists stay on the device (torch tensors owned by this estimator); similarity_matrix_
+        # is built from them on first use
+        out = engine.fit_topk(U, I, ptr_d, idx_d, K, similarity=self.similarity, item_pow=item_pow, want_cnt=False)
         if self.normalize_sim:
-            # Normalizer(norm="l1") over the kept entries of each row (nearest_neighbour.py:220-222)
+            # Normalizer(norm="l1") over the kept entries of each row (nearest_neighbour.py:220-222), on the host
+            idx, val, ln = to_host(out["idx"], out["val"], out["len"])
             mask = np.arange(idx.shape[1])[None, :] < ln[:, None]
             row_sum = np.where(mask, np.abs(val), 0.0).sum(axis=1)
             row_sum[row_sum == 0] = 1.0
-            val = np.ascontiguousarray(val / row_sum[:, None])
-        S = lists_to_csr(idx, val, ln, I)
-        self.similarity_matrix_ = S
-        self._fit_lists = {"idx": idx, "val": val, "len": ln, "cnt": out.get("cnt")}
-        self._fit_lists["key"] = self._device_model_key()
+            self.similarity_matrix_ = lists_to_csr(idx, np.ascontiguousarray(val / row_sum[:, None]), ln, I)
+        else:
+            self._set_device_fit(out, I, engine.device)
