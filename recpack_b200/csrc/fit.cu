@@ -691,8 +691,20 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
         for (int h = 0; h < H; ++h) me = p.heavy_ids[h] == i ? h : me;
         const int sl = j - r0;
         const bool mine = sl >= 0 && sl < ns;  // a column belongs to exactly one item range
-        s_ex_cnt[tid] = (mine && j != i) ? p.heavy_pair[me * HEAVY_CAP + tid] : 0;
-        if (mine) atomicAnd(&cnt[sl >> 1], (sl & 1) ? 0x0000ffffu : 0xffff0000u);
+        const int exact = j != i ? p.heavy_pair[me * HEAVY_CAP + tid] : p.sk.n[i];  // what the counter summed to
+        s_ex_cnt[tid] = (mine && j != i) ? exact : 0;
+        // a low half that passed 65535 carried into its neighbour's half (exact >> 16 times): take that back,
+        // unless the neighbour is a heavy column itself (its half is discarded below)
+        if (mine && !(sl & 1) && sl + 1 < ns && (exact >> 16)) {
+          bool nb_heavy = false;
+          for (int h = 0; h < H; ++h) nb_heavy |= p.heavy_ids[h] == j + 1;
+          if (!nb_heavy) atomicSub(&cnt[sl >> 1], (unsigned)(exact >> 16) << 16);
+        }
+      }
+      __syncthreads();
+      if (tid < H) {
+        const int sl = p.heavy_ids[tid] - r0;
+        if (sl >= 0 && sl < ns) atomicAnd(&cnt[sl >> 1], (sl & 1) ? 0x0000ffffu : 0xffff0000u);
       }
       nex = H;
       __syncthreads();

@@ -505,3 +505,63 @@ def test_fit_items_seen_by_more_than_65535_users(engine, flags, dense_users):
         engine.fit_config(-1)
         engine.debug_flags(0)
     _assert_fit_equal(got, orc.canon_fit(X, K=K))
+
+
+@pytest.mark.parametrize("flags,dense_users", [(0, 0), (0, 64), (4, 0)])
+def test_fit_wrapped_counter_does_not_leak_into_neighbour(engine, flags, dense_users):
+    """A packed 16-bit counter in an even slot that passes 65,535 carries into the odd slot next to it; the
+    carried amount (known from the exact pair count) is taken back, so the ordinary neighbour column keeps
+    its exact count."""
+    rng = np.random.default_rng(11)
+    U, I, K = 70_000, 40, 39  # K = I - 1: every count of a row is compared
+    p = rng.random(I) * 0.5 + 0.02
+    p[[0, 2, 6, 9]] = [0.99, 0.97, 0.96, 0.95]   # heavy columns in even slots 0, 2, 6 with ordinary neighbours
+    X = csr_matrix((rng.random((U, I)) < p[None, :]).astype(np.int32))
+    n = np.bincount(X.indices, minlength=I)
+    assert (n >= 65536).sum() == 4 and n[1] < 65536 and n[3] < 65536 and n[7] < 65536
+    engine.debug_flags(flags)
+    engine.fit_config(dense_users)
+    try:
+        got = _fit_lists(engine, X, K)
+    finally:
+        engine.fit_config(-1)
+        engine.debug_flags(0)
+    _assert_fit_equal(got, orc.canon_fit(X, K=K))
+
+
+def test_fit_result_stays_on_device_until_used():
+    """fit keeps the top-K lists on the device: similarity_matrix_ is built on first access, an assigned matrix
+    replaces the device copy, pickles carry the host matrix only, and metrics read the device-resident lists."""
+    import pickle
+
+    from recpack_b200 import ItemKNN, NDCGK
+    from recpack_b200.synth import synth_interactions
+
+    X = synth_interactions(300, 180, 5000, seed=4)
+    Y = synth_interactions(300, 180, 1500, seed=5)
+    algo = ItemKNN(K=25, predict_topK=10, remove_history=True).fit(X)
+    assert algo.__dict__["_similarity_host"] is None and algo.__dict__["_fit_dev"] is not None
+    pred = algo.predict(X)                       # model straight from the device lists
+    assert algo.__dict__["_similarity_host"] is None
+    assert hasattr(pred, "_rpk_topn_dev")
+    m = NDCGK(10)
+    m.calculate(Y, pred)
+    m_host = NDCGK(10)
+    m_host.calculate(Y, csr_matrix(pred))        # plain CSR: ranked again from the host copy
+    assert m.value == m_host.value
+    S = algo.similarity_matrix_                  # first access builds the CSR
+    assert S.shape == (180, 180) and S is algo.similarity_matrix_
+    want = orc.canon_fit(X, K=25)
+    ref = orc.topk_to_csr(want["idx"], want["val"], want["len"], 180)
+    got = S.copy()
+    got.sort_indices()
+    assert np.array_equal(got.indices, ref.indices) and np.array_equal(got.data, ref.data)
+    clone = pickle.loads(pickle.dumps(algo))
+    assert clone.__dict__["_fit_dev"] is None
+    assert np.array_equal(clone.predict(X)._rpk_topn[0], pred._rpk_topn[0])
+    # assigning a matrix replaces the fit result (the reference lets users do this)
+    S2 = S.copy()
+    S2.data[:] = 1.0
+    algo.similarity_matrix_ = S2
+    assert algo.__dict__["_fit_dev"] is None
+    assert not np.array_equal(algo.predict(X).data, pred.data)
