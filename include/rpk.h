@@ -70,7 +70,8 @@ RPK_EXPORT int rpk_sync(rpk_ctx* ctx);
 RPK_EXPORT int64_t rpk_launch_count(const rpk_ctx* ctx);
 /* Test hook: force a code path.  bit 0: wide (64-bit CAS) score accumulators in predict;
  * bit 1: tiny candidate-list capacity in the selection routine (exercises its refinement and
- * tie paths on small inputs); bit 2: more than one item-range pass in fit/predict. */
+ * tie paths on small inputs); bit 2: more than one item-range pass in fit/predict;
+ * bit 3: the fit cuts its heaviest rows into pieces even on small inputs. */
 RPK_EXPORT int rpk_debug_flags(rpk_ctx* ctx, int flags);
 
 /*

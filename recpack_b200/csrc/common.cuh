@@ -39,6 +39,7 @@ enum {
   DBG_WIDE_ACC = 1,    // predict: 64-bit CAS accumulators for every user
   DBG_TINY_LIST = 2,   // selection: smallest legal candidate list
   DBG_MULTI_PASS = 4,  // fit / predict: at least two item-range passes
+  DBG_SPLIT_ROWS = 8,  // fit: cut the heaviest rows into pieces even when they are small
 };
 
 }  // namespace rpk

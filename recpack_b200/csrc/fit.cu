@@ -474,6 +474,9 @@ struct FitParams {
   const u64* work;        // per-item total of history lengths
   const unsigned short* g16;  // dense-leg counts [I x ldg] (null: none)
   int64_t ldg;
+  const int* pre;         // per item: slot of its pre-accumulated counters in `hbuf`, -1 = none (null: none at all)
+  const unsigned* hbuf;   // [slots x hstride] packed 16-bit counters written by k_fit_heavy_partial
+  int64_t hstride;
   SimKey sk;
   const int* order;       // rows of this launch, heaviest first
   const int* nrows_dev;   // number of rows in `order` (device side: no host round trip)
@@ -494,6 +497,163 @@ struct FitParams {
   int* scr_cnt;
   int* scr_len;    // [rows] survivors in scratch, -1 = row already final in out_*
 };
+
+// Adds the histories of the users of item i whose work prefix lies in [lo, hi) to the counters (one warp;
+// the window is a piece of the row's total work = sum of its users' history lengths).
+template <bool PACK16>
+__device__ __forceinline__ void accumulate_window(const FitParams& p, unsigned* cnt, int64_t ub, int nu, int r0,
+                                                  unsigned lo, unsigned hi) {
+  const int lane = threadIdx.x & 31;
+  const unsigned* pf_row = p.pref + ub;
+  int a = 0, b = nu;  // 32-ary search: last user whose prefix is <= lo
+  while (b - a > 1) {
+    const int step = (b - a + 31) / 32;
+    const int k = a + lane * step;
+    const bool ok = k < b && pf_row[k] <= lo;
+    const unsigned mk = __ballot_sync(0xffffffffu, ok) | 1u;
+    const int last = 31 - __clz(mk);
+    const int na = a + last * step;
+    b = min(b, na + step);
+    a = na;
+  }
+  for (int kbase = a; kbase < nu; kbase += 32) {
+    const int kk = kbase + lane;
+    unsigned pf = 0xffffffffu;
+    int64_t beg = 0;
+    int len = 0;
+    if (kk < nu) {
+      const int u = p.csc_users[ub + kk];
+      pf = pf_row[kk];
+      beg = p.indptr[u];
+      len = (int)(p.indptr[u + 1] - beg);
+    }
+    if (__shfl_sync(0xffffffffu, pf, 0) >= hi) break;
+    // software pipeline over the users of the batch: the first 128 indices of user l+1 are loaded
+    // while the counters of user l are updated
+    int jn[4] = {-1, -1, -1, -1};
+    int64_t bn = 0;
+    int sn = 0, en = 0;
+    auto fetch = [&](int l) {  // clip user l to [lo, hi) and issue its first loads
+      sn = 0;
+      en = 0;
+      if (l < 32) {
+        const unsigned pfl = __shfl_sync(0xffffffffu, pf, l);
+        const int n = __shfl_sync(0xffffffffu, len, l);
+        bn = __shfl_sync(0xffffffffu, beg, l);
+        if (pfl < hi) {
+          sn = lo > pfl ? (int)(lo - pfl) : 0;
+          en = (int)min((unsigned)n, hi - pfl);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int e = sn + lane + 32 * q;
+        jn[q] = e < en ? p.indices[bn + e] - r0 : -1;
+      }
+    };
+    fetch(0);
+    for (int l = 0; l < 32; ++l) {
+      if (__shfl_sync(0xffffffffu, pf, l) >= hi) break;
+      int jj[4] = {jn[0], jn[1], jn[2], jn[3]};
+      const int64_t bb = bn;
+      const int s0 = sn, e1 = en;
+      fetch(l + 1);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (jj[q] >= 0) {
+          if (PACK16) atomicAdd(&cnt[jj[q] >> 1], 1u << ((jj[q] & 1) * 16));
+          else atomicAdd(&cnt[jj[q]], 1u);
+        }
+      // long histories: the rest, four loads in flight per lane
+      for (int e = s0 + 128 + lane; e < e1; e += 128) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) jj[q] = e + 32 * q < e1 ? p.indices[bb + e + 32 * q] - r0 : -1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (jj[q] >= 0) {
+            if (PACK16) atomicAdd(&cnt[jj[q] >> 1], 1u << ((jj[q] & 1) * 16));
+            else atomicAdd(&cnt[jj[q]], 1u);
+          }
+      }
+    }
+  }
+}
+
+// ---- very heavy rows: one CTA per row bounds the fit by the heaviest row once the rows of a shard are few
+// (multi-GPU).  The work of such a row is cut into S pieces that separate CTAs accumulate in shared memory
+// and add into a global counter row; k_fit_rows then starts from those counters and only runs the epilogue.
+constexpr int HEAVY_ROWS = 64;    // candidate rows (the first of the heaviest-first order)
+constexpr int HEAVY_SPLITS = 16;  // pieces per row at most
+
+// plan[r] = {item, pieces, slot, 0} for the first HEAVY_ROWS rows of `order`; pre[item] = slot when pieces > 1.
+__global__ void __launch_bounds__(1024) k_heavy_plan(const int* __restrict__ order, const int* __restrict__ nrows_dev,
+                                                     const u64* __restrict__ work, int sm_count, u64 min_target,
+                                                     int4* __restrict__ plan, int* __restrict__ pre) {
+  __shared__ u64 s_tot;
+  __shared__ int s_slots;
+  const int tid = threadIdx.x, nrows = nrows_dev[0];
+  if (tid == 0) {
+    s_tot = 0;
+    s_slots = 0;
+  }
+  __syncthreads();
+  u64 t = 0;
+  for (int k = tid; k < nrows; k += blockDim.x) t += work[order[k]];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if ((tid & 31) == 0 && t) atomicAdd(&s_tot, t);
+  __syncthreads();
+  // a piece should be about half of an SM's fair share of this launch (never tiny)
+  u64 target = s_tot / (u64)(2 * sm_count);
+  if (target < min_target) target = min_target;
+  if (tid < HEAVY_ROWS) {
+    int4 pl = make_int4(-1, 0, -1, 0);
+    if (tid < nrows) {
+      const int i = order[tid];
+      const u64 w = work[i];
+      int S = (int)((w + target - 1) / target);
+      S = S > HEAVY_SPLITS ? HEAVY_SPLITS : S;
+      if (S >= 2 && w < (1ull << 32)) {
+        const int slot = atomicAdd(&s_slots, 1);
+        pl = make_int4(i, S, slot, 0);
+        pre[i] = slot;
+      }
+    }
+    plan[tid] = pl;
+  }
+}
+
+__global__ void __launch_bounds__(1024, 1) k_fit_heavy_partial(FitParams p, const int4* __restrict__ plan,
+                                                               unsigned* __restrict__ hbuf) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  unsigned* cnt = reinterpret_cast<unsigned*>(smem);
+  const int4 pl = plan[blockIdx.x / HEAVY_SPLITS];
+  const int piece = blockIdx.x % HEAVY_SPLITS;
+  if (pl.x < 0 || piece >= pl.y) return;
+  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, nwarps = nt >> 5;
+  const int i = pl.x;
+  const int nwords = (p.I + 1) >> 1;
+  for (int s = tid; s < nwords; s += nt) cnt[s] = 0u;
+  __syncthreads();
+  const int64_t ub = p.cscptr[i];
+  const int nu = (int)(p.cscptr[i + 1] - ub);
+  const unsigned T = (unsigned)p.work[i];
+  const unsigned pieces = (unsigned)pl.y * (unsigned)nwarps;
+  unsigned share = (T + pieces - 1) / pieces;
+  share = (share + 31u) & ~31u;
+  const u64 lo64 = (u64)((unsigned)piece * (unsigned)nwarps + (unsigned)warp) * share;
+  if (lo64 < T) {
+    const unsigned lo = (unsigned)lo64;
+    const unsigned hi = (unsigned)min((u64)T, lo64 + share);
+    accumulate_window<true>(p, cnt, ub, nu, 0, lo, hi);
+  }
+  __syncthreads();
+  unsigned* dst = hbuf + (int64_t)pl.z * p.hstride;
+  for (int s = tid; s < nwords; s += nt) {
+    const unsigned v = cnt[s];
+    if (v) atomicAdd(dst + s, v);
+  }
+}
 
 template <bool PACK16>
 __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
@@ -566,8 +726,14 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       for (int s = tid; s < nwords; s += nt) cnt[s] = 0u;
     }
     __syncthreads();
+    const int pre_slot = (PACK16 && p.pre) ? p.pre[i] : -1;
+    if (pre_slot >= 0) {  // the row's users were already counted by k_fit_heavy_partial (P == 1 there)
+      const unsigned* hb = p.hbuf + (int64_t)pre_slot * p.hstride;
+      for (int s = tid; s < nwords; s += nt) cnt[s] += hb[s];
+    }
     const int64_t nu64 = ue - ub;
-    if (!p.usplit) {
+    if (pre_slot >= 0) {
+    } else if (!p.usplit) {
       // ---- accumulate, single pass: the row's work (sum of its users' history lengths) is cut into equal
       //      pieces, one per warp, so that a single long history cannot stall the row on one warp
       const int nu = (int)nu64;
@@ -577,79 +743,7 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       const unsigned lo = (unsigned)warp * share;
       const unsigned hi = min(T, lo + share);
       if (lo < hi) {
-        const unsigned* pf_row = p.pref + ub;
-        int a = 0, b = nu;  // 32-ary search: last user whose prefix is <= lo
-        while (b - a > 1) {
-          const int step = (b - a + 31) / 32;
-          const int k = a + lane * step;
-          const bool ok = k < b && pf_row[k] <= lo;
-          const unsigned mk = __ballot_sync(0xffffffffu, ok) | 1u;
-          const int last = 31 - __clz(mk);
-          const int na = a + last * step;
-          b = min(b, na + step);
-          a = na;
-        }
-        for (int kbase = a; kbase < nu; kbase += 32) {
-          const int kk = kbase + lane;
-          unsigned pf = 0xffffffffu;
-          int64_t beg = 0;
-          int len = 0;
-          if (kk < nu) {
-            const int u = p.csc_users[ub + kk];
-            pf = pf_row[kk];
-            beg = p.indptr[u];
-            len = (int)(p.indptr[u + 1] - beg);
-          }
-          if (__shfl_sync(0xffffffffu, pf, 0) >= hi) break;
-          // software pipeline over the users of the batch: the first 128 indices of user l+1 are loaded
-          // while the counters of user l are updated
-          int jn[4] = {-1, -1, -1, -1};
-          int64_t bn = 0;
-          int sn = 0, en = 0;
-          auto fetch = [&](int l) {  // clip user l to [lo, hi) and issue its first loads
-            sn = 0;
-            en = 0;
-            if (l < 32) {
-              const unsigned pfl = __shfl_sync(0xffffffffu, pf, l);
-              const int n = __shfl_sync(0xffffffffu, len, l);
-              bn = __shfl_sync(0xffffffffu, beg, l);
-              if (pfl < hi) {
-                sn = lo > pfl ? (int)(lo - pfl) : 0;
-                en = (int)min((unsigned)n, hi - pfl);
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int e = sn + lane + 32 * q;
-              jn[q] = e < en ? p.indices[bn + e] - r0 : -1;
-            }
-          };
-          fetch(0);
-          for (int l = 0; l < 32; ++l) {
-            if (__shfl_sync(0xffffffffu, pf, l) >= hi) break;
-            int jj[4] = {jn[0], jn[1], jn[2], jn[3]};
-            const int64_t bb = bn;
-            const int s0 = sn, e1 = en;
-            fetch(l + 1);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (jj[q] >= 0) {
-                if (PACK16) atomicAdd(&cnt[jj[q] >> 1], 1u << ((jj[q] & 1) * 16));
-                else atomicAdd(&cnt[jj[q]], 1u);
-              }
-            // long histories: the rest, four loads in flight per lane
-            for (int e = s0 + 128 + lane; e < e1; e += 128) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) jj[q] = e + 32 * q < e1 ? p.indices[bb + e + 32 * q] - r0 : -1;
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (jj[q] >= 0) {
-                  if (PACK16) atomicAdd(&cnt[jj[q] >> 1], 1u << ((jj[q] & 1) * 16));
-                  else atomicAdd(&cnt[jj[q]], 1u);
-                }
-            }
-          }
-        }
+        accumulate_window<PACK16>(p, cnt, ub, nu, r0, lo, hi);
       }
     } else {
       // ---- accumulate, several item ranges: users are dealt to the warps in chunks (<= 32 users, one per
@@ -1165,6 +1259,28 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
       fp.scr_cnt = scr_cnt;
       fp.scr_len = scr_len;
       any_deferred = any_deferred || fp.defer_max > 0;
+      fp.pre = nullptr;
+      fp.hbuf = nullptr;
+      fp.hstride = 0;
+      if (!wide && !force_wide && P == 1 && nrows > 0) {
+        // rows too heavy for one CTA next to the others: counted in pieces first (see k_fit_heavy_partial)
+        const int64_t hstride = (((I + 1) >> 1) + 3) & ~(int64_t)3;
+        int4* plan = c->buf<int4>("fit_heavy_plan", HEAVY_ROWS);
+        int* pre = c->buf<int>("fit_heavy_pre", (size_t)I);
+        unsigned* hbuf = c->buf<unsigned>("fit_heavy_buf", (size_t)HEAVY_ROWS * hstride);
+        RPK_CUDA(cudaMemsetAsync(pre, 0xff, sizeof(int) * (size_t)I, st));
+        RPK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(unsigned) * (size_t)HEAVY_ROWS * hstride, st));
+        const u64 min_target = (c->flags & DBG_SPLIT_ROWS) ? 64ull : (1ull << 20);
+        k_heavy_plan<<<1, 1024, 0, st>>>(fp.order, fp.nrows_dev, work, c->sm_count, min_target, plan, pre);
+        RPK_LAUNCH_CHECK(c);
+        fp.pre = pre;
+        fp.hbuf = hbuf;
+        fp.hstride = hstride;
+        const size_t hsm = (size_t)hstride * sizeof(unsigned);
+        RPK_CUDA(cudaFuncSetAttribute(k_fit_heavy_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+        k_fit_heavy_partial<<<HEAVY_ROWS * HEAVY_SPLITS, nt, hsm, st>>>(fp, plan, hbuf);
+        RPK_LAUNCH_CHECK(c);
+      }
       auto kern = wide ? k_fit_rows<false> : k_fit_rows<true>;
       RPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int occ = 0;

@@ -15,7 +15,7 @@ from ._lib import RpkError
 SIM_CODES = {"cosine": 0, "conditional_probability": 1}
 METRIC_CODES = {"ndcg": 0, "recall": 1, "dcg": 2, "calibrated_recall": 3}
 
-DBG_WIDE_ACC, DBG_TINY_LIST, DBG_MULTI_PASS = 1, 2, 4
+DBG_WIDE_ACC, DBG_TINY_LIST, DBG_MULTI_PASS, DBG_SPLIT_ROWS = 1, 2, 4, 8
 
 
 def _is_torch(x):

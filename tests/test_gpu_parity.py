@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 UNIT = ["unit_cosine", "unit_empty_col", "unit_condprob", "unit_condprob_pd1", "unit_condprob_pd0.2", "unit_condprob_pd0.5"]
 SMALL = ["small_cosine", "small_condprob", "small_condprob_pd"]
-FLAG_SETS = [0, 1, 2, 4, 5, 6]  # bit0: 32-bit counters (fit) / wide accumulators (predict); bit1: tiny lists; bit2: multi-pass
+FLAG_SETS = [0, 1, 2, 4, 5, 6, 8, 10]  # bit0: 32-bit counters (fit) / wide accumulators (predict); bit1: tiny lists; bit2: multi-pass; bit3: heavy rows counted in pieces
 
 
 @pytest.fixture(scope="module")
@@ -488,7 +488,7 @@ def test_model_load_from_padded_shards(engine):
         assert np.array_equal(a[key], b_[key])
 
 
-@pytest.mark.parametrize("flags,dense_users", [(0, 0), (0, 64), (4, 0), (1, 0)])
+@pytest.mark.parametrize("flags,dense_users", [(0, 0), (0, 64), (4, 0), (1, 0), (8, 0), (8, 64)])
 def test_fit_items_seen_by_more_than_65535_users(engine, flags, dense_users):
     """Counts between two items that both exceed 65,535 users do not fit the packed 16-bit counters: they come
     from the exact pair kernel (or, with flag 1, from the 32-bit counter path)."""
@@ -507,7 +507,7 @@ def test_fit_items_seen_by_more_than_65535_users(engine, flags, dense_users):
     _assert_fit_equal(got, orc.canon_fit(X, K=K))
 
 
-@pytest.mark.parametrize("flags,dense_users", [(0, 0), (0, 64), (4, 0)])
+@pytest.mark.parametrize("flags,dense_users", [(0, 0), (0, 64), (4, 0), (8, 0), (8, 64)])
 def test_fit_wrapped_counter_does_not_leak_into_neighbour(engine, flags, dense_users):
     """A packed 16-bit counter in an even slot that passes 65,535 carries into the odd slot next to it; the
     carried amount (known from the exact pair count) is taken back, so the ordinary neighbour column keeps
