@@ -270,8 +270,8 @@ def run_gpu(args):
         eng.fit_topk(U, I, t_ptr_full, t_idx_full, K_NEIGH, item_begin=ib, item_end=ie, out=fit_out)
         ev[1].record()
         if world > 1:
-            g_idx, g_val, g_len = exchange.gather_padded()
-            eng.model_load_topk_rows(I, K_NEIGH, g_idx.shape[0], g_idx, g_val, g_len, exchange.row_source())
+            g_ent, g_len = exchange.gather_packed(eng)  # rows travel in the model's packed format
+            eng.model_load_packed_rows(I, K_NEIGH, g_ent.shape[0], g_ent, g_len, exchange.row_source())
         else:
             eng.model_load_topk(I, K_NEIGH, fit_out["idx"], fit_out["val"], fit_out["len"])
         ev[2].record()

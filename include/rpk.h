@@ -113,6 +113,16 @@ RPK_EXPORT int rpk_model_load_topk(rpk_ctx* ctx, int64_t I, int K,
 RPK_EXPORT int rpk_model_load_topk_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in,
                              const int32_t* idx, const double* val, const int32_t* len,
                              const int64_t* row_src);
+/* Multi-GPU exchange in the model's own format (8 bytes per entry instead of 12, and no per-rank re-sort of
+ * every row after the all-gather).  rpk_model_pack_rows turns `rows` rank-ordered lists (as written by
+ * rpk_fit_topk; columns are item ids in [0, I)) into packed rows out_ent[r*K + t] = column << 40 | q,
+ * q = rint(val * 2^39) | 1, ascending column, unused places all-ones.  rpk_model_load_packed_rows builds the
+ * model from such rows: model row i = input row row_src[i] (int64[I], null = identity), len = entries per row.
+ * Replaces nothing in the reference (single process); it is the row exchange of SURVEY.md 8(e). */
+RPK_EXPORT int rpk_model_pack_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows,
+                        const int32_t* idx, const double* val, const int32_t* len, uint64_t* out_ent);
+RPK_EXPORT int rpk_model_load_packed_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in,
+                               const uint64_t* ent, const int32_t* len, const int64_t* row_src);
 /* Every rpk_fit_topk increments the context's fit token.  When the last fit covered all item rows and
  * produced values, its lists stay resident on the device and rpk_model_load_last_fit(token) builds the
  * model from them without any host round trip; it fails when `token` is not the current one. */

@@ -26,6 +26,8 @@ _SIGNATURES = {
     "rpk_fit_item_counts": (C.c_int, [C.c_void_p, _i32p, C.c_int64]),
     "rpk_model_load_topk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, _i32p, _f64p, _i32p]),
     "rpk_model_load_topk_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _i32p, _f64p, _i32p, _i64p]),
+    "rpk_model_pack_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _i32p, _f64p, _i32p, _vp]),
+    "rpk_model_load_packed_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _vp, _i32p, _i64p]),
     "rpk_fit_token": (C.c_int64, [C.c_void_p]),
     "rpk_model_load_last_fit": (C.c_int, [C.c_void_p, C.c_int64]),
     "rpk_model_load_csr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, _f64p]),

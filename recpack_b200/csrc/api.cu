@@ -124,6 +124,20 @@ int rpk_model_load_topk_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in, co
   RPK_API_END(ctx)
 }
 
+int rpk_model_pack_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows, const int32_t* idx, const double* val,
+                        const int32_t* len, uint64_t* out_ent) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_model_pack_rows(ctx, I, K, rows, idx, val, len, out_ent);
+  RPK_API_END(ctx)
+}
+
+int rpk_model_load_packed_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in, const uint64_t* ent, const int32_t* len,
+                               const int64_t* row_src) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_model_load_packed_rows(ctx, I, K, rows_in, ent, len, row_src);
+  RPK_API_END(ctx)
+}
+
 int64_t rpk_fit_token(const rpk_ctx* ctx) { return ctx ? ctx->lf_token : 0; }
 
 int rpk_model_load_last_fit(rpk_ctx* ctx, int64_t token) {

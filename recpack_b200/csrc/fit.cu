@@ -19,15 +19,16 @@ namespace rpk {
 // ------------------------------------------------------------------------------------------
 // CSR preparation: item popularities, CSC transpose, per-row work estimate
 // ------------------------------------------------------------------------------------------
-// Per-item number of users that stay on the sparse path (one warp per user).
+// Per-item number of users that stay on the sparse path: n_light starts as a copy of the item popularities
+// and the (few) dense users' interactions are taken off it (one warp per user).
 __global__ void k_item_counts_light(const int64_t* __restrict__ indptr, const int* __restrict__ indices, int64_t U,
                                     const int* __restrict__ dense_slot, int* __restrict__ n_light) {
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t u = warp; u < U; u += nwarps) {
-    if (dense_slot[u] >= 0) continue;
-    for (int64_t k = indptr[u] + lane; k < indptr[u + 1]; k += 32) atomicAdd(&n_light[indices[k]], 1);
+    if (dense_slot[u] < 0) continue;
+    for (int64_t k = indptr[u] + lane; k < indptr[u + 1]; k += 32) atomicSub(&n_light[indices[k]], 1);
   }
 }
 
@@ -475,8 +476,13 @@ struct FitParams {
   const unsigned short* g16;  // dense-leg counts [I x ldg] (null: none)
   int64_t ldg;
   const int* pre;         // per item: slot of its pre-accumulated counters in `hbuf`, -1 = none (null: none at all)
-  const unsigned* hbuf;   // [slots x hstride] packed 16-bit counters written by k_fit_heavy_partial
+  unsigned* hbuf;         // [slots x hstride] packed 16-bit counters summed over the pieces of a split row
   int64_t hstride;
+  const int4* piece_tab;  // {item, piece, pieces, slot} of every piece, heaviest rows first
+  const int* hcount;      // [0] number of pieces, [1] number of split rows
+  const int* split_rows;  // the split rows (they are finished after everything else)
+  int* hdone;             // per slot: pieces completed
+  const int* hneed;       // per slot: pieces in all
   SimKey sk;
   const int* order;       // rows of this launch, heaviest first
   const int* nrows_dev;   // number of rows in `order` (device side: no host round trip)
@@ -580,22 +586,21 @@ __device__ __forceinline__ void accumulate_window(const FitParams& p, unsigned* 
 }
 
 // ---- very heavy rows: one CTA per row bounds the fit by the heaviest row once the rows of a shard are few
-// (multi-GPU).  The work of such a row is cut into S pieces that separate CTAs accumulate in shared memory
-// and add into a global counter row; k_fit_rows then starts from those counters and only runs the epilogue.
+// (multi-GPU).  The work of such a row is cut into pieces.  Pieces are ordinary work items at the head of
+// k_fit_rows' queue: a CTA counts its piece in shared memory and adds the counters into a global row; the
+// split rows themselves come last in the queue, start from those counters and only run the epilogue.
 constexpr int HEAVY_ROWS = 64;    // candidate rows (the first of the heaviest-first order)
 constexpr int HEAVY_SPLITS = 16;  // pieces per row at most
 
-// plan[r] = {item, pieces, slot, 0} for the first HEAVY_ROWS rows of `order`; pre[item] = slot when pieces > 1.
 __global__ void __launch_bounds__(1024) k_heavy_plan(const int* __restrict__ order, const int* __restrict__ nrows_dev,
                                                      const u64* __restrict__ work, int sm_count, u64 min_target,
-                                                     int4* __restrict__ plan, int* __restrict__ pre) {
+                                                     int4* __restrict__ piece_tab, int* __restrict__ hcount,
+                                                     int* __restrict__ split_rows, int* __restrict__ hneed,
+                                                     int* __restrict__ pre) {
   __shared__ u64 s_tot;
-  __shared__ int s_slots;
+  __shared__ int s_S[HEAVY_ROWS];
   const int tid = threadIdx.x, nrows = nrows_dev[0];
-  if (tid == 0) {
-    s_tot = 0;
-    s_slots = 0;
-  }
+  if (tid == 0) s_tot = 0;
   __syncthreads();
   u64 t = 0;
   for (int k = tid; k < nrows; k += blockDim.x) t += work[order[k]];
@@ -603,55 +608,35 @@ __global__ void __launch_bounds__(1024) k_heavy_plan(const int* __restrict__ ord
   for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   if ((tid & 31) == 0 && t) atomicAdd(&s_tot, t);
   __syncthreads();
-  // a piece should be about half of an SM's fair share of this launch (never tiny)
+  // a piece is about half of an SM's fair share of this launch; rows within 3/4 of the fair share stay whole
   u64 target = s_tot / (u64)(2 * sm_count);
   if (target < min_target) target = min_target;
   if (tid < HEAVY_ROWS) {
-    int4 pl = make_int4(-1, 0, -1, 0);
+    int S = 1;
     if (tid < nrows) {
-      const int i = order[tid];
-      const u64 w = work[i];
-      int S = (int)((w + target - 1) / target);
-      S = S > HEAVY_SPLITS ? HEAVY_SPLITS : S;
-      if (S >= 2 && w < (1ull << 32)) {
-        const int slot = atomicAdd(&s_slots, 1);
-        pl = make_int4(i, S, slot, 0);
-        pre[i] = slot;
+      const u64 w = work[order[tid]];
+      if (2 * w > 3 * target && w < (1ull << 32)) {
+        const u64 q = (w + target - 1) / target;
+        S = q > (u64)HEAVY_SPLITS ? HEAVY_SPLITS : (int)q;
       }
     }
-    plan[tid] = pl;
-  }
-}
-
-__global__ void __launch_bounds__(1024, 1) k_fit_heavy_partial(FitParams p, const int4* __restrict__ plan,
-                                                               unsigned* __restrict__ hbuf) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  unsigned* cnt = reinterpret_cast<unsigned*>(smem);
-  const int4 pl = plan[blockIdx.x / HEAVY_SPLITS];
-  const int piece = blockIdx.x % HEAVY_SPLITS;
-  if (pl.x < 0 || piece >= pl.y) return;
-  const int tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, nwarps = nt >> 5;
-  const int i = pl.x;
-  const int nwords = (p.I + 1) >> 1;
-  for (int s = tid; s < nwords; s += nt) cnt[s] = 0u;
-  __syncthreads();
-  const int64_t ub = p.cscptr[i];
-  const int nu = (int)(p.cscptr[i + 1] - ub);
-  const unsigned T = (unsigned)p.work[i];
-  const unsigned pieces = (unsigned)pl.y * (unsigned)nwarps;
-  unsigned share = (T + pieces - 1) / pieces;
-  share = (share + 31u) & ~31u;
-  const u64 lo64 = (u64)((unsigned)piece * (unsigned)nwarps + (unsigned)warp) * share;
-  if (lo64 < T) {
-    const unsigned lo = (unsigned)lo64;
-    const unsigned hi = (unsigned)min((u64)T, lo64 + share);
-    accumulate_window<true>(p, cnt, ub, nu, 0, lo, hi);
+    s_S[tid] = S;
   }
   __syncthreads();
-  unsigned* dst = hbuf + (int64_t)pl.z * p.hstride;
-  for (int s = tid; s < nwords; s += nt) {
-    const unsigned v = cnt[s];
-    if (v) atomicAdd(dst + s, v);
+  if (tid == 0) {
+    int np = 0, ns = 0;
+    for (int r = 0; r < HEAVY_ROWS && r < nrows; ++r) {
+      const int S = s_S[r];
+      if (S < 2) continue;
+      const int i = order[r];
+      for (int q = 0; q < S; ++q) piece_tab[np++] = make_int4(i, q, S, ns);
+      split_rows[ns] = i;
+      hneed[ns] = S;
+      pre[i] = ns;
+      ++ns;
+    }
+    hcount[0] = np;
+    hcount[1] = ns;
   }
 }
 
@@ -667,7 +652,9 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
   __shared__ int s_ex_idx[HEAVY_CAP], s_ex_cnt[HEAVY_CAP];
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  const int total = p.nrows_dev[0] * p.P;
+  const int nrow_items = p.nrows_dev[0] * p.P;
+  const int n_pieces = (PACK16 && p.pre) ? p.hcount[0] : 0;
+  const int total = n_pieces + nrow_items + ((PACK16 && p.pre) ? p.hcount[1] : 0);
   // coded item popularities for the selection keys: one byte per item behind the counters, loaded once
   if (p.pop_code) {
     unsigned char* code_s = reinterpret_cast<unsigned char*>(cnt) + (size_t)p.R * (PACK16 ? 2 : 4);
@@ -683,9 +670,46 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
     const int w = s_work;
     __syncthreads();
     if (w >= total) break;
-    const int pos = w / p.P;
-    const int i = p.order[pos];
-    const int pass = w % p.P;
+    if (PACK16 && w < n_pieces) {
+      // ---- a piece of a split row: count it, add the counters into the row's global copy
+      const int4 pc = p.piece_tab[w];
+      const int nw_all = (p.I + 1) >> 1;
+      for (int s = tid; s < nw_all; s += nt) cnt[s] = 0u;
+      __syncthreads();
+      const int64_t pub = p.cscptr[pc.x];
+      const int pnu = (int)(p.cscptr[pc.x + 1] - pub);
+      const unsigned T = (unsigned)p.work[pc.x];
+      const unsigned pieces = (unsigned)pc.z * (unsigned)nwarps;
+      unsigned share = (T + pieces - 1) / pieces;
+      share = (share + 31u) & ~31u;
+      const u64 lo64 = (u64)((unsigned)pc.y * (unsigned)nwarps + (unsigned)warp) * share;
+      if (lo64 < T) accumulate_window<PACK16>(p, cnt, pub, pnu, 0, (unsigned)lo64, (unsigned)min((u64)T, lo64 + share));
+      __syncthreads();
+      unsigned* dst = p.hbuf + (int64_t)pc.w * p.hstride;
+      for (int s = tid; s < nw_all; s += nt) {
+        const unsigned v = cnt[s];
+        if (v) atomicAdd(dst + s, v);
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) atomicAdd(&p.hdone[pc.w], 1);
+      continue;
+    }
+    int pos = 0, i, pass = 0;
+    int pre_slot = -1;
+    if (w < n_pieces + nrow_items) {
+      pos = (w - n_pieces) / p.P;
+      pass = (w - n_pieces) % p.P;
+      i = p.order[pos];
+      if (PACK16 && p.pre && p.pre[i] >= 0) continue;  // a split row: finished at the end of the queue
+    } else {
+      i = p.split_rows[w - n_pieces - nrow_items];
+      pre_slot = p.pre[i];
+      if (tid == 0) {  // its pieces were handed out long ago; wait for the last of them
+        while (atomicAdd(&p.hdone[pre_slot], 0) < p.hneed[pre_slot]) __nanosleep(256);
+      }
+      __syncthreads();
+    }
     const int r0 = pass * p.R;
     const int ns = min(p.R, p.I - r0);
     const int64_t ub = p.cscptr[i], ue = p.cscptr[i + 1];
@@ -726,10 +750,9 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       for (int s = tid; s < nwords; s += nt) cnt[s] = 0u;
     }
     __syncthreads();
-    const int pre_slot = (PACK16 && p.pre) ? p.pre[i] : -1;
-    if (pre_slot >= 0) {  // the row's users were already counted by k_fit_heavy_partial (P == 1 there)
+    if (pre_slot >= 0) {  // the row's users were counted in pieces (P == 1 there): start from their sum
       const unsigned* hb = p.hbuf + (int64_t)pre_slot * p.hstride;
-      for (int s = tid; s < nwords; s += nt) cnt[s] += hb[s];
+      for (int s = tid; s < nwords; s += nt) cnt[s] += __ldcg(hb + s);
     }
     const int64_t nu64 = ue - ub;
     if (pre_slot >= 0) {
@@ -1081,7 +1104,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     unsigned short* G = c->buf<unsigned short>("fit_dense_G", (size_t)(item_end - g_row0 + 1) * rows_pad);
     const int thr_init[2] = {dense_tau, 0};
     RPK_CUDA(cudaMemcpyAsync(thr_cnt, thr_init, sizeof(thr_init), cudaMemcpyHostToDevice, st));
-    RPK_CUDA(cudaMemsetAsync(n_light, 0, sizeof(int) * (size_t)I, st));
+    RPK_CUDA(cudaMemcpyAsync(n_light, n, sizeof(int) * (size_t)I, cudaMemcpyDeviceToDevice, st));
     RPK_CUDA(cudaMemsetAsync(A, 0, (size_t)rows_pad * kd_pad, st));
     k_assign_dense_slots<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, thr_cnt, hmax, slot);
     RPK_LAUNCH_CHECK(c);
@@ -1262,24 +1285,33 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
       fp.pre = nullptr;
       fp.hbuf = nullptr;
       fp.hstride = 0;
+      fp.piece_tab = nullptr;
+      fp.hcount = nullptr;
+      fp.split_rows = nullptr;
+      fp.hdone = nullptr;
+      fp.hneed = nullptr;
       if (!wide && !force_wide && P == 1 && nrows > 0) {
-        // rows too heavy for one CTA next to the others: counted in pieces first (see k_fit_heavy_partial)
+        // rows too heavy for one CTA next to the others are counted in pieces (see k_heavy_plan)
         const int64_t hstride = (((I + 1) >> 1) + 3) & ~(int64_t)3;
-        int4* plan = c->buf<int4>("fit_heavy_plan", HEAVY_ROWS);
+        int4* piece_tab = c->buf<int4>("fit_heavy_pieces", HEAVY_ROWS * HEAVY_SPLITS);
+        int* hmeta = c->buf<int>("fit_heavy_meta", 2 + 3 * HEAVY_ROWS);  // counts | split rows | done | need
         int* pre = c->buf<int>("fit_heavy_pre", (size_t)I);
         unsigned* hbuf = c->buf<unsigned>("fit_heavy_buf", (size_t)HEAVY_ROWS * hstride);
         RPK_CUDA(cudaMemsetAsync(pre, 0xff, sizeof(int) * (size_t)I, st));
+        RPK_CUDA(cudaMemsetAsync(hmeta, 0, sizeof(int) * (2 + 3 * HEAVY_ROWS), st));
         RPK_CUDA(cudaMemsetAsync(hbuf, 0, sizeof(unsigned) * (size_t)HEAVY_ROWS * hstride, st));
         const u64 min_target = (c->flags & DBG_SPLIT_ROWS) ? 64ull : (1ull << 20);
-        k_heavy_plan<<<1, 1024, 0, st>>>(fp.order, fp.nrows_dev, work, c->sm_count, min_target, plan, pre);
+        k_heavy_plan<<<1, 1024, 0, st>>>(fp.order, fp.nrows_dev, work, c->sm_count, min_target, piece_tab, hmeta, hmeta + 2,
+                                         hmeta + 2 + 2 * HEAVY_ROWS, pre);
         RPK_LAUNCH_CHECK(c);
         fp.pre = pre;
         fp.hbuf = hbuf;
         fp.hstride = hstride;
-        const size_t hsm = (size_t)hstride * sizeof(unsigned);
-        RPK_CUDA(cudaFuncSetAttribute(k_fit_heavy_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-        k_fit_heavy_partial<<<HEAVY_ROWS * HEAVY_SPLITS, nt, hsm, st>>>(fp, plan, hbuf);
-        RPK_LAUNCH_CHECK(c);
+        fp.piece_tab = piece_tab;
+        fp.hcount = hmeta;
+        fp.split_rows = hmeta + 2;
+        fp.hdone = hmeta + 2 + HEAVY_ROWS;
+        fp.hneed = hmeta + 2 + 2 * HEAVY_ROWS;
       }
       auto kern = wide ? k_fit_rows<false> : k_fit_rows<true>;
       RPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

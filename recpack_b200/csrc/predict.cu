@@ -41,7 +41,7 @@ __device__ __forceinline__ bool quantize(double v, u64& q) {
 // One CTA per row: pack (idx, q), sort by idx, write the row.
 __global__ void __launch_bounds__(256) k_model_from_topk(const int* __restrict__ idx, const double* __restrict__ val,
                                                          const int* __restrict__ len, const int64_t* __restrict__ row_src,
-                                                         int K, int I,
+                                                         int K, int I, int nrows,
                                                          const int64_t* __restrict__ m_ptr, u64* __restrict__ m_ent,
                                                          unsigned* __restrict__ m_rowmax, int* __restrict__ flag) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(256) k_model_from_topk(const int* __restrict__
   const int tid = threadIdx.x, nt = blockDim.x;
   int n2 = 2;
   while (n2 < K) n2 <<= 1;
-  for (int i = blockIdx.x; i < I; i += gridDim.x) {
+  for (int i = blockIdx.x; i < nrows; i += gridDim.x) {
     const int64_t src = row_src ? row_src[i] : (int64_t)i;  // where row i lives in the (gathered) input
     int m = len[src];
     if (m > K) m = K;
@@ -87,12 +87,15 @@ __global__ void __launch_bounds__(256) k_model_from_topk(const int* __restrict__
         }
         __syncthreads();
       }
-    const int64_t base = m_ptr[i];
-    for (int t = tid; t < m; t += nt) {
-      m_ent[base + t] = buf[t];
-      if (t > 0 && (buf[t] >> 40) == (buf[t - 1] >> 40)) atomicOr(flag, 2);  // duplicate column
+    if (m_ptr) {
+      const int64_t base = m_ptr[i];
+      for (int t = tid; t < m; t += nt) m_ent[base + t] = buf[t];
+      if (tid == 0) m_rowmax[i] = s_max;
+    } else {  // packed rows of K places each, all-ones after the row's entries (they sort last)
+      for (int t = tid; t < K; t += nt) m_ent[(int64_t)i * K + t] = buf[t];
     }
-    if (tid == 0) m_rowmax[i] = s_max;
+    for (int t = tid + 1; t < m; t += nt)
+      if ((buf[t] >> 40) == (buf[t - 1] >> 40)) atomicOr(flag, 2);  // duplicate column
     __syncthreads();
   }
 }
@@ -251,8 +254,101 @@ void run_model_load_topk_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, con
     int n2 = 2;
     while (n2 < K) n2 <<= 1;
     const int grid = (int)std::min<int64_t>(I, (int64_t)c->sm_count * 16);
-    k_model_from_topk<<<grid, 128, (size_t)n2 * sizeof(u64), st>>>(idx, val, len, row_src, K, (int)I, m_ptr, m_ent, m_rowmax,
+    k_model_from_topk<<<grid, 128, (size_t)n2 * sizeof(u64), st>>>(idx, val, len, row_src, K, (int)I, (int)I, m_ptr, m_ent, m_rowmax,
                                                                   c->get<int>("m_flag"));
+    RPK_LAUNCH_CHECK(c);
+  }
+  int64_t total = 0;
+  RPK_CUDA(cudaMemcpyAsync(&total, m_ptr + I, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  model_check_flag(c);
+  RPK_REQUIRE(total >= 0 && total <= I * (int64_t)K, "similarity model: row lengths exceed K");
+  c->m_nnz = total;
+  c->m_max_len = K;
+}
+
+// One warp per model row: copy its entries out of the packed input rows, check them, record the row maximum.
+__global__ void k_model_from_packed(const u64* __restrict__ ent, const int64_t* __restrict__ row_src, int K, int64_t I,
+                                    const int64_t* __restrict__ m_ptr, const int* __restrict__ m_len,
+                                    u64* __restrict__ m_ent, unsigned* __restrict__ m_rowmax, int* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < I; i += nwarps) {
+    const int64_t src = row_src ? row_src[i] : i;
+    const u64* row = ent + src * K;
+    const int64_t base = m_ptr[i];
+    const int n = m_len[i];
+    unsigned lmax = 0;
+    for (int t = lane; t < n; t += 32) {
+      const u64 e = row[t];
+      const u64 col = e >> 40, q = e & Q_MASK40;
+      if (col >= (u64)I || !(q & 1ull)) atomicOr(flag, 1);
+      if (t > 0 && (row[t - 1] >> 40) >= col) atomicOr(flag, 2);
+      m_ent[base + t] = e;
+      lmax = max(lmax, (unsigned)(q >> LIMB_BITS) + 1u);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    if (lane == 0) m_rowmax[i] = lmax;
+  }
+}
+
+void run_model_pack_rows(rpk_ctx* c, int64_t I, int K, int64_t rows, const int32_t* idx_u, const double* val_u,
+                         const int32_t* len_u, uint64_t* out_u) {
+  RPK_REQUIRE(K >= 1 && K <= 4096, "K must be in [1, 4096]");
+  RPK_REQUIRE(I >= 0 && I < ((int64_t)1 << 24), "item count must be below 2^24");
+  RPK_REQUIRE(rows >= 0, "negative row count");
+  RPK_REQUIRE(out_u != nullptr, "out_ent must not be null");
+  cudaStream_t st = c->stream;
+  const int32_t* idx = stage_in(c, idx_u, (size_t)rows * K, "pk_in_idx");
+  const double* val = stage_in(c, val_u, (size_t)rows * K, "pk_in_val");
+  const int32_t* len = stage_in(c, len_u, (size_t)rows, "pk_in_len");
+  Out<u64> o;
+  o.init(c, reinterpret_cast<u64*>(out_u), (size_t)rows * K, "pk_out");
+  int* flag = c->buf<int>("pk_flag", 1);
+  RPK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  if (rows > 0) {
+    int n2 = 2;
+    while (n2 < K) n2 <<= 1;
+    const int grid = (int)std::min<int64_t>(rows, (int64_t)c->sm_count * 16);
+    k_model_from_topk<<<grid, 128, (size_t)n2 * sizeof(u64), st>>>(idx, val, len, nullptr, K, (int)I, (int)rows, nullptr, o.dev, nullptr, flag);
+    RPK_LAUNCH_CHECK(c);
+  }
+  int h = 0;
+  RPK_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  RPK_CUDA(cudaStreamSynchronize(st));
+  RPK_REQUIRE(!(h & 1), "similarity lists: values must lie in [0, 2) and columns in [0, I)");
+  RPK_REQUIRE(!(h & 2), "similarity lists: column indices must be unique within a row");
+  o.finish(c);
+  finish_call(c);
+}
+
+void run_model_load_packed_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, const uint64_t* ent_u, const int32_t* len_u,
+                                const int64_t* row_src_u) {
+  RPK_REQUIRE(K >= 1 && K <= 4096, "K must be in [1, 4096]");
+  RPK_REQUIRE(rows_in >= I || row_src_u, "fewer input rows than items");
+  model_common_begin(c, I);
+  cudaStream_t st = c->stream;
+  const u64* ent = stage_in(c, reinterpret_cast<const u64*>(ent_u), (size_t)rows_in * K, "m_in_ent");
+  const int32_t* len = stage_in(c, len_u, (size_t)rows_in, "m_in_len");
+  const int64_t* row_src = row_src_u ? stage_in(c, row_src_u, (size_t)I, "m_in_rowsrc") : nullptr;
+  int64_t* m_ptr = c->buf<int64_t>("m_ptr", (size_t)I + 1);
+  int* m_len = c->buf<int>("m_len", (size_t)I);
+  if (I > 0) {
+    if (row_src) {
+      k_gather_len<<<ceil_div(I, 256), 256, 0, st>>>(len, row_src, I, m_len);
+      RPK_LAUNCH_CHECK(c);
+    } else {
+      RPK_CUDA(cudaMemcpyAsync(m_len, len, sizeof(int) * (size_t)I, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  k_scan_i32_i64<<<1, 1024, 0, st>>>(m_len, m_ptr, I);
+  RPK_LAUNCH_CHECK(c);
+  u64* m_ent = c->buf<u64>("m_ent", (size_t)I * K);
+  unsigned* m_rowmax = c->buf<unsigned>("m_rowmax", (size_t)I);
+  if (I > 0) {
+    const int grid = (int)std::min<int64_t>((I * 32 + 255) / 256, (int64_t)c->sm_count * 16);
+    k_model_from_packed<<<grid, 256, 0, st>>>(ent, row_src, K, I, m_ptr, m_len, m_ent, m_rowmax, c->get<int>("m_flag"));
     RPK_LAUNCH_CHECK(c);
   }
   int64_t total = 0;

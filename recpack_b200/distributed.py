@@ -47,6 +47,8 @@ class ShardExchange:
         self.g_idx = mk((self.world, self.maxrows, K), torch.int32, -1)
         self.g_val = mk((self.world, self.maxrows, K), torch.float64, 0)
         self.g_len = mk((self.world, self.maxrows), torch.int32, 0)
+        self.p_ent = mk((self.maxrows, K), torch.int64, -1)  # packed model rows (uint64 bit patterns), all-ones = unused
+        self.g_ent = mk((self.world, self.maxrows, K), torch.int64, -1)
         self.all_idx = mk((I, K), torch.int32, -1)
         self.all_val = mk((I, K), torch.float64, 0)
         self.all_len = mk((I,), torch.int32, 0)
@@ -75,6 +77,19 @@ class ShardExchange:
         self.dist.all_gather_into_tensor(self.g_val.view(-1, self.K), self.p_val)
         self.dist.all_gather_into_tensor(self.g_len.view(-1), self.p_len)
         return self.g_idx.view(-1, self.K), self.g_val.view(-1, self.K), self.g_len.view(-1)
+
+    def gather_packed(self, engine=None):
+        """Exchange in the model's own format: this rank's lists (filled through local_out()) are packed into
+        model rows (rpk_model_pack_rows; 8 bytes per entry, already in column order) and all-gathered together with
+        the row lengths.  Returns ([world * maxrows, K] int64, [world * maxrows] int32) for
+        rpk_model_load_packed_rows + row_source().  With engine=None the caller has filled p_ent itself."""
+        rows = self.cuts[self.rank + 1] - self.cuts[self.rank]
+        if engine is not None:
+            engine.model_pack_rows(self.cuts[-1], self.K, self.p_idx[:rows], self.p_val[:rows], self.p_len[:rows],
+                                   out=self.p_ent[:rows])
+        self.dist.all_gather_into_tensor(self.g_ent.view(-1, self.K), self.p_ent)
+        self.dist.all_gather_into_tensor(self.g_len.view(-1), self.p_len)
+        return self.g_ent.view(-1, self.K), self.g_len.view(-1)
 
     def gather(self, idx, val, ln):
         """idx/val/ln: this rank's rows (cuts[rank]..cuts[rank+1]).  Returns the full, unpadded arrays."""

@@ -149,6 +149,20 @@ class Engine:
         self._check(self._lib.rpk_model_load_topk_rows(self._h, int(I), int(K), int(rows_in), _addr(idx, np.int32),
                                                        _addr(val, np.float64), _addr(ln, np.int32), _addr(row_src, np.int64)))
 
+    def model_pack_rows(self, I, K, idx, val, ln, out=None):
+        """rpk_model_pack_rows: rank-ordered lists -> packed model rows (uint64 bit patterns; torch tensors carry
+        them as int64).  `out`: [rows, K] buffer to fill."""
+        rows = int(idx.shape[0])
+        if out is None:
+            out = _empty_like_kind(idx, (rows, K), np.int64 if _is_torch(idx) else np.uint64)
+        self._check(self._lib.rpk_model_pack_rows(self._h, int(I), int(K), rows, _addr(idx, np.int32), _addr(val, np.float64),
+                                                  _addr(ln, np.int32), _addr(out)))
+        return out
+
+    def model_load_packed_rows(self, I, K, rows_in, ent, ln, row_src=None):
+        self._check(self._lib.rpk_model_load_packed_rows(self._h, int(I), int(K), int(rows_in), _addr(ent), _addr(ln, np.int32),
+                                                         _addr(row_src, np.int64, allow_none=True)))
+
     def fit_token(self) -> int:
         return int(self._lib.rpk_fit_token(self._h))
 

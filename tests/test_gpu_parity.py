@@ -484,8 +484,23 @@ def test_model_load_from_padded_shards(engine):
     a = engine.predict_topn(300, indptr, indices, N)
     engine.model_load_topk_rows(200, K, 3 * maxrows, g_idx, g_val, g_len, src)
     b_ = engine.predict_topn(300, indptr, indices, N)
+    # the same exchange in the packed format: rows packed per shard, loaded through the same row map
+    g_ent = np.full((3 * maxrows, K), ~np.uint64(0), dtype=np.uint64)
+    for r in range(3):
+        b, e = cuts[r], cuts[r + 1]
+        g_ent[r * maxrows : r * maxrows + e - b] = engine.model_pack_rows(200, K, want["idx"][b:e], want["val"][b:e], want["len"][b:e])
+    engine.model_load_packed_rows(200, K, 3 * maxrows, g_ent, g_len, src)
+    c_ = engine.predict_topn(300, indptr, indices, N)
     for key in ("idx", "val", "len"):
-        assert np.array_equal(a[key], b_[key])
+        assert np.array_equal(a[key], b_[key]) and np.array_equal(a[key], c_[key])
+    from recpack_b200.engine import RpkError
+
+    with pytest.raises(RpkError):  # rows must be in column order
+        bad = g_ent.copy()
+        r = int(src[np.flatnonzero(want["len"] >= 2)[0]])
+        bad[r, :2] = bad[r, 1::-1]
+        engine.model_load_packed_rows(200, K, 3 * maxrows, bad, g_len, src)
+    engine.model_load_topk(200, K, want["idx"], want["val"], want["len"])  # leave a valid model behind
 
 
 @pytest.mark.parametrize("flags,dense_users", [(0, 0), (0, 64), (4, 0), (1, 0), (8, 0), (8, 64)])

@@ -137,6 +137,13 @@ def _gloo_worker(rank, world, port, tmpdir):
         a_idx, a_val, a_len = ex.gather(torch.from_numpy(full_idx[b:e]), torch.from_numpy(full_val[b:e]), torch.from_numpy(full_len[b:e]))
         assert np.array_equal(a_idx.numpy(), full_idx) and np.array_equal(a_val.numpy(), full_val)
         assert np.array_equal(a_len.numpy(), full_len)
+        # packed exchange (the rows are packed by rpk_model_pack_rows on a GPU; here the send buffer is filled by hand)
+        full_ent = rng.integers(0, 2**62, size=(I, K), dtype=np.int64)
+        ex.p_ent[: e - b].copy_(torch.from_numpy(full_ent[b:e]))
+        ex.p_len[: e - b].copy_(torch.from_numpy(full_len[b:e]))
+        g_ent, g_len = ex.gather_packed()
+        src = ex.row_source().numpy()
+        assert np.array_equal(g_ent.numpy()[src], full_ent) and np.array_equal(g_len.numpy()[src], full_len)
         sums = torch.tensor([1.0 + rank, 2.0, 10.0 * (rank + 1)], dtype=torch.float64)
         dist.all_reduce(sums)
         assert sums.tolist() == [3.0, 4.0, 30.0]
