@@ -116,6 +116,10 @@ __global__ void k_heavy_pairs(const int64_t* __restrict__ indptr, const int* __r
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int target = h < H ? heavy_ids[h] : -1;
+  // pair counts of this block in shared memory, added to the global table once at the end
+  __shared__ int s_pair[HEAVY_CAP * HEAVY_CAP];
+  for (int t = threadIdx.x; t < HEAVY_CAP * HEAVY_CAP; t += blockDim.x) s_pair[t] = 0;
+  __syncthreads();
   for (int64_t u0 = warp * per_warp; u0 < U; u0 += nwarps * per_warp) {
     const int64_t u = u0 + grp;
     bool has = false;
@@ -136,14 +140,69 @@ __global__ void k_heavy_pairs(const int64_t* __restrict__ indptr, const int* __r
       while (others) {
         const int b = __ffs(others) - 1;
         others &= others - 1;
-        atomicAdd(&pair[h * HEAVY_CAP + b], 1);
+        atomicAdd(&s_pair[h * HEAVY_CAP + b], 1);
       }
     }
   }
+  __syncthreads();
+  for (int t = threadIdx.x; t < HEAVY_CAP * HEAVY_CAP; t += blockDim.x)
+    if (s_pair[t]) atomicAdd(&pair[t], s_pair[t]);
 }
 
 // pref[k] = sum of the history lengths of the users listed before position k of the same item
 // (exclusive, in CSC order): lets the fit kernel cut a row's work into equal pieces per warp.
+constexpr int CSC_PREFIX_LONG = 4096;  // items with more users than this are scanned by a whole block
+__global__ void __launch_bounds__(1024) k_csc_prefix_long(const int64_t* __restrict__ cscptr, const int* __restrict__ csc_users,
+                                                          const int64_t* __restrict__ indptr, int64_t item_begin,
+                                                          int64_t item_end, unsigned* __restrict__ pref) {
+  __shared__ unsigned s_warp[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t i = item_begin + blockIdx.x; i < item_end; i += gridDim.x) {
+    const int64_t b = cscptr[i], e = cscptr[i + 1];
+    if (e - b <= CSC_PREFIX_LONG) continue;
+    unsigned carry = 0;
+    for (int64_t base = b; base < e; base += 4096) {  // 4 users per thread
+      unsigned v[4], tot = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t k = base + 4 * tid + q;
+        v[q] = 0;
+        if (k < e) {
+          const int u = csc_users[k];
+          v[q] = (unsigned)(indptr[u + 1] - indptr[u]);
+        }
+        tot += v[q];
+      }
+      unsigned incl = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) s_warp[warp] = incl;
+      __syncthreads();
+      unsigned wv = s_warp[lane];  // blockDim.x == 1024: 32 warp totals
+      unsigned wincl = wv;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, wincl, o);
+        if (lane >= o) wincl += t;
+      }
+      const unsigned before = __shfl_sync(0xffffffffu, wincl - wv, warp);
+      const unsigned block_tot = __shfl_sync(0xffffffffu, wincl, 31);
+      unsigned run = carry + before + incl - tot;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int64_t k = base + 4 * tid + q;
+        if (k < e) pref[k] = run;
+        run += v[q];
+      }
+      carry += block_tot;
+      __syncthreads();
+    }
+  }
+}
+
 __global__ void k_csc_prefix(const int64_t* __restrict__ cscptr, const int* __restrict__ csc_users,
                              const int64_t* __restrict__ indptr, int64_t item_begin, int64_t item_end,
                              unsigned* __restrict__ pref) {
@@ -152,6 +211,7 @@ __global__ void k_csc_prefix(const int64_t* __restrict__ cscptr, const int* __re
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = item_begin + warp; i < item_end; i += nwarps) {
     const int64_t b = cscptr[i], e = cscptr[i + 1];
+    if (e - b > CSC_PREFIX_LONG) continue;  // long lists: k_csc_prefix_long (a whole block per item)
     unsigned carry = 0;
     for (int64_t base = b; base < e; base += 128) {  // 4 users per lane: four independent loads in flight
       unsigned v[4], tot = 0;
@@ -1133,6 +1193,9 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
   if (nnz > 0 && I > 0) {
     int blocks = (int)std::min<int64_t>((nrows * 32 + 255) / 256, (int64_t)c->sm_count * 32);
     k_csc_prefix<<<std::max(blocks, 1), 256, 0, st>>>(cscptr, csc_users, indptr, item_begin, item_end, pref);
+    RPK_LAUNCH_CHECK(c);
+    k_csc_prefix_long<<<(int)std::min<int64_t>(nrows, (int64_t)c->sm_count * 2), 1024, 0, st>>>(cscptr, csc_users, indptr, item_begin,
+                                                                                                  item_end, pref);
     RPK_LAUNCH_CHECK(c);
   }
   int* nmax = c->buf<int>("fit_nmax", 4);
