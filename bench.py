@@ -348,6 +348,13 @@ def run_gpu(args):
             kname, kms = "k_fit_rows", k_rows
             alg = stats["fit_bytes"] * (item_work[ib:ie].sum() / item_work.sum())
         ach = alg / (kms * 1e-3) / 1e9
+        notes = {
+            "k_predict_a32": "algorithmic bytes per launch / CUDA-event duration of the kernel; operands are L2-resident (measured DRAM "
+                             "traffic is far below the algorithmic bytes), the kernel is bound by the shared-memory data pipe (one 32-bit "
+                             "atomic per similarity entry, ~40 % of its wavefronts are bank-conflict replays) and instruction issue, not by HBM",
+            "k_fit_rows": "algorithmic bytes per launch / CUDA-event duration of the row kernels; X is L2-resident, the kernel is bound by "
+                          "instruction issue and shared-memory atomics (one packed 16-bit counter update per co-occurrence), not by HBM",
+        }
         tensor = None
         if k_gram > 0:
             bf16 = None
@@ -373,10 +380,7 @@ def run_gpu(args):
             "ndcg10": ndcg10, "recall20": recall20, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic.get(kname), "peak_source": peak_src, "kernel_ms": kms,
-                         "note": "algorithmic bytes per launch / CUDA-event duration of the kernel; operands are L2-resident "
-                                 "(measured DRAM traffic is far below the algorithmic bytes), the kernel is bound by the shared-memory "
-                                 "data pipe (one 32-bit atomic per similarity entry, ~40 % of its wavefronts are bank-conflict replays) "
-                                 "and instruction issue, not by HBM"},
+                         "note": notes[kname]},
             "roofline_tensor": tensor,
             "phases_ms": {"fit": fit_ms, "exchange": exch_ms, "score": score_ms},
             "kernels_ms": {"k_gram_i8_tc": k_gram, "k_fit_rows": k_rows, "k_predict_a32": k_pred},
