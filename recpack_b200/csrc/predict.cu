@@ -7,10 +7,13 @@
 //   recpack/metrics/base.py:189            get_top_K_ranks(y_pred, K) on the prediction rows
 //
 // Scores are exact integers: every similarity value is stored as q = rint(v * 2^39) | 1 (40 bits), a
-// score is the integer sum of q over the history.  The sum is accumulated in two 32-bit limbs
-// (q & 0xFFFFF, q >> 20) with native shared-memory integer atomics (ATOMS.ADD); a 64-bit
-// compare-and-swap accumulator is the fallback when a limb could overflow.  Integer sums make the
-// result independent of the order in which the atomics land, so the top-N lists are deterministic.
+// score is the integer sum of q over the history.  Integer sums make the result independent of the order
+// in which the atomics land, so the top-N lists are deterministic.  Two kernels:
+//   k_predict_a32  top-N: 32-bit approximate sums with one native shared-memory atomic (ATOMS.ADD) per
+//                  entry pick the few items that can be in the top N, a second sweep adds their exact q;
+//   k_predict      full CSR output, and the exact path for users k_predict_a32 hands over: the sum is kept
+//                  in two 32-bit limbs (q & 0xFFFFF, q >> 20), 64-bit compare-and-swap accumulators when a
+//                  limb could overflow.
 #include <stdlib.h>
 
 #include <type_traits>
@@ -21,7 +24,6 @@
 #include "select.cuh"
 
 namespace rpk {
-
 
 constexpr u64 Q_MASK40 = (((u64)1) << 40) - 1;
 constexpr int LIMB_BITS = 20;
@@ -1280,23 +1282,19 @@ static PredGeom predict_geometry(rpk_ctx* c, int N) {
   return g;
 }
 
-// Segment tables (offset of each item range inside every model row); one for each scoring kernel.
-static const int* ensure_segments(rpk_ctx* c, int P, int R, int which = 0) {
-  int& cP = which ? c->m_P2 : c->m_P;
-  int& cR = which ? c->m_R2 : c->m_R;
-  const char* name = which ? "m_seg2" : "m_seg";
+// Segment table of the two-limb kernel: offset of each item range inside every model row.
+static void ensure_segments(rpk_ctx* c, const PredGeom& g) {
+  if (c->m_P == g.P && c->m_R == g.R) return;
   const int64_t I = c->m_I;
-  if (cP == P && cR == R) return c->get<int>(name);
-  int* seg = c->buf<int>(name, (size_t)I * (P + 1));
+  int* seg = c->buf<int>("m_seg", (size_t)I * (g.P + 1));
   if (I > 0) {
-    k_model_seg<<<ceil_div(I * (P + 1), 256), 256, 0, c->stream>>>(c->get<int64_t>("m_ptr"), c->get<u64>("m_ent"), I, P, R, seg);
+    k_model_seg<<<ceil_div(I * (g.P + 1), 256), 256, 0, c->stream>>>(c->get<int64_t>("m_ptr"), c->get<u64>("m_ent"), I, g.P,
+                                                                      g.R, seg);
     RPK_LAUNCH_CHECK(c);
   }
-  cP = P;
-  cR = R;
-  return seg;
+  c->m_P = g.P;
+  c->m_R = g.R;
 }
-static void ensure_segments(rpk_ctx* c, const PredGeom& g) { ensure_segments(c, g.P, g.R, 0); }
 
 // Padded block layout of the model (once per model) and the block table of a geometry.
 static void ensure_blocks(rpk_ctx* c, int P, int R) {
