@@ -53,7 +53,9 @@ extern "C" {
 typedef struct rpk_ctx rpk_ctx;
 
 enum { RPK_SIM_COSINE = 0, RPK_SIM_CONDPROB = 1 };
-enum { RPK_METRIC_NDCG = 0, RPK_METRIC_RECALL = 1, RPK_METRIC_DCG = 2, RPK_METRIC_CALIBRATED_RECALL = 3 };
+enum { RPK_METRIC_NDCG = 0, RPK_METRIC_RECALL = 1, RPK_METRIC_DCG = 2, RPK_METRIC_CALIBRATED_RECALL = 3,
+       RPK_METRIC_PRECISION = 4,        /* hits / K (recpack/metrics/precision.py:41-50) */
+       RPK_METRIC_RECIPROCAL_RANK = 5   /* 1 / rank of the first hit, 0 without one (metrics/reciprocal_rank.py:37-40) */ };
 
 RPK_EXPORT int rpk_abi_version(void);
 

@@ -405,7 +405,7 @@ def discount_tables(K):
 
 
 def canon_metrics_from_lists(top_idx, top_len, y_true, metrics):
-    """NDCG@K / Recall@K / DCG@K / CalibratedRecall@K from rank-ordered lists.
+    """NDCG@K / Recall@K / DCG@K / CalibratedRecall@K / Precision@K / ReciprocalRank@K from rank-ordered lists.
 
     ``metrics`` is a list of (kind, K).  Users with an empty y_true row are dropped
     (metrics/base.py:106-123); a user with true items but no recommendations scores 0.
@@ -428,6 +428,11 @@ def canon_metrics_from_lists(top_idx, top_len, y_true, metrics):
                 per_user[t] = hit.sum() / len(truth)
             elif kind == "calibrated_recall":
                 per_user[t] = hit.sum() / min(len(truth), K)
+            elif kind == "precision":  # metrics/precision.py:41-50: divided by K even when fewer were recommended
+                per_user[t] = hit.sum() / K
+            elif kind == "reciprocal_rank":  # metrics/reciprocal_rank.py:37-40
+                where = np.flatnonzero(hit)
+                per_user[t] = 1.0 / (where[0] + 1) if len(where) else 0.0
             else:
                 raise ValueError(kind)
         out[(kind, K)] = (per_user.mean() if len(users) else float("nan"), per_user, users)

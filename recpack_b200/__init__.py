@@ -5,7 +5,7 @@ hand-written sm_100a CUDA kernels through the C ABI in include/rpk.h.  There is 
 without ``recpack_b200/librpk.so`` and a B200 every compute call raises."""
 from .base import Algorithm, ItemSimilarityMatrixAlgorithm, TopKItemSimilarityMatrixAlgorithm  # noqa: F401
 from .matrix import UnsupportedTypeError, to_csr_matrix  # noqa: F401
-from .metrics import NDCGK, DCGK, RecallK, CalibratedRecallK  # noqa: F401
+from .metrics import NDCGK, DCGK, RecallK, CalibratedRecallK, PrecisionK, ReciprocalRankK  # noqa: F401
 from .nearest_neighbour import ItemKNN  # noqa: F401
 from .util import get_top_K_ranks, get_top_K_values  # noqa: F401
 

@@ -127,7 +127,7 @@ __global__ void k_metrics(const int* __restrict__ top_idx, const int* __restrict
     const int kind = kinds[m];
     const int lim = len < K ? len : K;
     double dcg = 0.0;
-    int hits = 0;
+    int hits = 0, first_hit = 0;  // first_hit: 1-based rank of the best-ranked hit
     for (int r = 0; r < lim; ++r) {
       const int item = top_idx[u * N + r];
       int lo = 0, hi = nt;
@@ -137,6 +137,7 @@ __global__ void k_metrics(const int* __restrict__ top_idx, const int* __restrict
         else hi = mid;
       }
       if (lo < nt && tidx[tb + lo] == item) {
+        if (!hits) first_hit = r + 1;
         hits++;
         dcg = __dadd_rn(dcg, discount[r]);
       }
@@ -145,6 +146,8 @@ __global__ void k_metrics(const int* __restrict__ top_idx, const int* __restrict
     if (kind == RPK_METRIC_NDCG) v = __ddiv_rn(dcg, idcg[nt < K ? nt : K]);
     else if (kind == RPK_METRIC_DCG) v = dcg;
     else if (kind == RPK_METRIC_RECALL) v = __ddiv_rn((double)hits, (double)nt);
+    else if (kind == RPK_METRIC_PRECISION) v = __ddiv_rn((double)hits, (double)K);
+    else if (kind == RPK_METRIC_RECIPROCAL_RANK) v = first_hit ? __ddiv_rn(1.0, (double)first_hit) : 0.0;
     else v = __ddiv_rn((double)hits, (double)(nt < K ? nt : K));
     per_user[(int64_t)m * U + u] = v;
   }
@@ -189,7 +192,7 @@ void run_metrics_topn(rpk_ctx* c, int64_t U, int N, const int32_t* top_idx_u, co
   RPK_REQUIRE(sums_u && n_users_u, "sums / n_users must not be null");
   for (int m = 0; m < n_metrics; ++m) {
     // kinds / Ks are tiny and always host-side in practice; validate when they are
-    if (!is_device_ptr(kinds_u)) RPK_REQUIRE(kinds_u[m] >= 0 && kinds_u[m] <= 3, "unknown metric kind");
+    if (!is_device_ptr(kinds_u)) RPK_REQUIRE(kinds_u[m] >= 0 && kinds_u[m] <= 5, "unknown metric kind");
     if (!is_device_ptr(Ks_u)) RPK_REQUIRE(Ks_u[m] >= 1 && Ks_u[m] <= maxK, "metric K exceeds the discount table");
   }
   cudaStream_t st = c->stream;

@@ -13,7 +13,7 @@ from . import _lib
 from ._lib import RpkError
 
 SIM_CODES = {"cosine": 0, "conditional_probability": 1}
-METRIC_CODES = {"ndcg": 0, "recall": 1, "dcg": 2, "calibrated_recall": 3}
+METRIC_CODES = {"ndcg": 0, "recall": 1, "dcg": 2, "calibrated_recall": 3, "precision": 4, "reciprocal_rank": 5}
 
 DBG_WIDE_ACC, DBG_TINY_LIST, DBG_MULTI_PASS, DBG_SPLIT_ROWS = 1, 2, 4, 8
 

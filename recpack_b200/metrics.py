@@ -116,6 +116,18 @@ class CalibratedRecallK(ListwiseMetricK):
     _kind = "calibrated_recall"
 
 
+class PrecisionK(ListwiseMetricK):
+    """metrics/precision.py:12-50: hits / K (fewer than K recommendations count as misses)."""
+
+    _kind = "precision"
+
+
+class ReciprocalRankK(ListwiseMetricK):
+    """metrics/reciprocal_rank.py:13-40: 1 / rank of the first hit, 0 without one."""
+
+    _kind = "reciprocal_rank"
+
+
 def ndcg_k(y_true, y_pred, k=50):
     r = NDCGK(K=k)
     r.calculate(y_true, y_pred)
@@ -136,5 +148,17 @@ def recall_k(y_true, y_pred, k=50):
 
 def calibrated_recall_k(y_true, y_pred, k):
     r = CalibratedRecallK(K=k)
+    r.calculate(y_true, y_pred)
+    return r.value
+
+
+def precision_k(y_true, y_pred, k=10):
+    r = PrecisionK(K=k)
+    r.calculate(y_true, y_pred)
+    return r.value
+
+
+def reciprocal_rank_k(y_true, y_pred, k=10):
+    r = ReciprocalRankK(K=k)
     r.calculate(y_true, y_pred)
     return r.value

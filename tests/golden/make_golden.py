@@ -139,8 +139,47 @@ def main():
                 out[f"{tname}_{tag}{k}_scores"] = m.results["score"].to_numpy().astype(np.float64)
                 out[f"{tname}_{tag}{k}_users"] = m.results["user_id"].to_numpy().astype(np.int64)
     np.savez_compressed(os.path.join(HERE, "metrics_unit.npz"), **out)
+    more_metrics(X_pred, truths)
     print("done")
 
 
-if __name__ == "__main__":
+def more_metrics(X_pred=None, truths=None):
+    """5. PrecisionK / ReciprocalRankK on the same fixtures (tests/test_metrics/test_precision.py,
+    test_reciprocal_rank.py use them) and on a seeded prediction matrix without score ties."""
+    from recpack.metrics.precision import PrecisionK
+    from recpack.metrics.reciprocal_rank import ReciprocalRankK
+
+    if X_pred is None:
+        X_pred = csr_matrix(([0.3, 0.2, 0.1, 0.23, 0.3, 0.5], ([0, 0, 0, 2, 2, 2], [0, 2, 3, 1, 3, 4])), shape=(10, 5))
+        truths = {
+            "true": csr_matrix(([1] * 5, ([0, 0, 2, 2, 2], [0, 2, 0, 1, 3])), shape=(10, 5)),
+            "simplified": csr_matrix(([1] * 2, ([0, 2], [2, 4])), shape=(10, 5)),
+            "unrecommended": csr_matrix(([1] * 6, ([0, 0, 2, 2, 2, 3], [0, 2, 0, 1, 3, 1])), shape=(10, 5)),
+        }
+    rng = np.random.default_rng(3)
+    dense = rng.permutation(60 * 40).reshape(60, 40).astype(np.float64) + 1.0  # distinct scores: no tie picks
+    dense[rng.random((60, 40)) < 0.7] = 0.0
+    big_pred = csr_matrix(dense)
+    big_true = csr_matrix((rng.random((60, 40)) < 0.15).astype(np.int64))
+    out = {}
+    pack("pred", X_pred, out)
+    pack("big_pred", big_pred, out)
+    pack("big_true", big_true, out)
+    cases = [(t, yt, X_pred, (1, 2, 3)) for t, yt in truths.items()] + [("big", big_true, big_pred, (1, 5, 10))]
+    for tname, yt, pr, ks in cases:
+        if tname != "big":
+            pack("true_" + tname, yt, out)
+        for cls, tag in ((PrecisionK, "precision"), (ReciprocalRankK, "reciprocal_rank")):
+            for k in ks:
+                m = cls(k)
+                m.calculate(yt, pr)
+                out[f"{tname}_{tag}{k}_value"] = np.array(m.value)
+                out[f"{tname}_{tag}{k}_scores"] = m.results["score"].to_numpy().astype(np.float64)
+                out[f"{tname}_{tag}{k}_users"] = m.results["user_id"].to_numpy().astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, "metrics_more.npz"), **out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "more":
+    more_metrics()  # only the fixture added later; the others are left as committed
+elif __name__ == "__main__":
     main()

@@ -580,3 +580,42 @@ def test_fit_result_stays_on_device_until_used():
     algo.similarity_matrix_ = S2
     assert algo.__dict__["_fit_dev"] is None
     assert not np.array_equal(algo.predict(X).data, pred.data)
+
+
+def test_precision_and_reciprocal_rank_through_public_api():
+    """PrecisionK / ReciprocalRankK (recpack/metrics/precision.py:41-50, reciprocal_rank.py:37-40) from the same
+    top-N lists: reference values on its own fixtures, reference per-user scores on a tie-free matrix, and the
+    oracle on lists produced by predict."""
+    from recpack_b200 import ItemKNN, PrecisionK, ReciprocalRankK
+    from recpack_b200.metrics import precision_k, reciprocal_rank_k
+    from recpack_b200.synth import synth_interactions
+
+    g = load_golden("metrics_more")
+    cases = [(t, unpack(g, "true_" + t), unpack(g, "pred"), (1, 2, 3)) for t in ("true", "simplified", "unrecommended")]
+    cases.append(("big", unpack(g, "big_true"), unpack(g, "big_pred"), (1, 5, 10)))
+    for tname, yt, pred, ks in cases:
+        for k in ks:
+            for cls, kind in ((PrecisionK, "precision"), (ReciprocalRankK, "reciprocal_rank")):
+                m = cls(k)
+                m.calculate(yt, pred)
+                assert m.name == f"{cls.__name__}_{k}"
+                np.testing.assert_allclose(m.value, float(g[f"{tname}_{kind}{k}_value"]), rtol=1e-12)
+                res = m.results
+                order = np.argsort(g[f"{tname}_{kind}{k}_users"])
+                assert np.array_equal(res["user_id"].to_numpy(), g[f"{tname}_{kind}{k}_users"][order])
+                if tname == "big":
+                    np.testing.assert_allclose(res["score"].to_numpy(), g[f"{tname}_{kind}{k}_scores"][order], rtol=1e-12, atol=0)
+    np.testing.assert_almost_equal(precision_k(unpack(g, "true_true"), unpack(g, "pred"), 2), 0.75)
+    np.testing.assert_almost_equal(reciprocal_rank_k(unpack(g, "true_true"), unpack(g, "pred"), 2), 0.75)
+    # device-resident lists from predict
+    X = synth_interactions(250, 90, 2500, seed=6)
+    Y = synth_interactions(250, 90, 900, seed=8)
+    pred = ItemKNN(K=15, predict_topK=12, remove_history=True).fit(X).predict(X)
+    idx, ln = pred._rpk_topn
+    want = orc.canon_metrics_from_lists(idx, ln, Y, [("precision", 10), ("reciprocal_rank", 10)])
+    for cls, kind in ((PrecisionK, "precision"), (ReciprocalRankK, "reciprocal_rank")):
+        m = cls(10)
+        m.calculate(Y, pred)
+        value, per_user, users = want[(kind, 10)]
+        np.testing.assert_allclose(m.value, value, rtol=1e-12)
+        np.testing.assert_allclose(m.results["score"].to_numpy(), per_user, rtol=1e-12, atol=0)

@@ -182,3 +182,38 @@ def test_top_k_ranks_fixture():
     got = orc.canon_top_k_ranks(mat, 20)
     assert (got != ref).nnz == 0  # no ties in this fixture -> identical
     assert _same_csr(orc.ref_top_k_ranks(mat, 20), ref)
+
+
+def _lists_from_ranks(pred, k):
+    ranks = orc.canon_top_k_ranks(pred, k)
+    U = pred.shape[0]
+    idx = np.full((U, k), -1, dtype=np.int32)
+    ln = np.zeros(U, dtype=np.int32)
+    for u in range(U):
+        row = ranks[u]
+        for c, r in zip(row.indices, row.data):
+            idx[u, int(r) - 1] = c
+        ln[u] = row.nnz
+    return idx, ln
+
+
+def test_precision_and_reciprocal_rank_vs_reference():
+    """recpack/metrics/precision.py:41-50, reciprocal_rank.py:37-40: values and per-user scores produced by the
+    reference (tests/golden/make_golden.py more) on its own metric fixtures and on a tie-free random matrix."""
+    g = load_golden("metrics_more")
+    cases = [(t, unpack(g, "true_" + t), unpack(g, "pred"), (1, 2, 3)) for t in ("true", "simplified", "unrecommended")]
+    cases.append(("big", unpack(g, "big_true"), unpack(g, "big_pred"), (1, 5, 10)))
+    for tname, yt, pred, ks in cases:
+        for k in ks:
+            idx, ln = _lists_from_ranks(pred, k)
+            res = orc.canon_metrics_from_lists(idx, ln, yt, [("precision", k), ("reciprocal_rank", k)])
+            for (kind, kk), (value, per_user, users) in res.items():
+                np.testing.assert_allclose(value, float(g[f"{tname}_{kind}{kk}_value"]), rtol=1e-12)
+                order = np.argsort(g[f"{tname}_{kind}{kk}_users"])
+                assert np.array_equal(g[f"{tname}_{kind}{kk}_users"][order], users)
+                if tname == "big":  # no score ties: the per-user numbers are the reference's
+                    np.testing.assert_allclose(per_user, g[f"{tname}_{kind}{kk}_scores"][order], rtol=1e-12, atol=0)
+    # closed forms quoted in the reference tests (recpack/tests/test_metrics/test_precision.py:16-21,
+    # test_reciprocal_rank.py:14-19)
+    np.testing.assert_almost_equal(float(g["true_precision2_value"]), 0.75)
+    np.testing.assert_almost_equal(float(g["true_reciprocal_rank2_value"]), 0.75)
