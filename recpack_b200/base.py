@@ -125,6 +125,7 @@ class ItemSimilarityMatrixAlgorithm(Algorithm):
     def _set_device_fit(self, out, I, device):
         """Keep the rank-ordered top-K lists of a fit on the device (torch tensors owned by this object)."""
         d = self.__dict__
+        get_engine(device).sync()  # the lists are complete before torch touches them (streams may differ)
         d["_similarity_host"] = None
         d["_fit_dev"] = {"idx": out["idx"], "val": out["val"], "len": out["len"], "I": int(I), "device": int(device),
                          "empty_rows": int((out["len"] == 0).sum().item())}
@@ -191,6 +192,7 @@ class ItemSimilarityMatrixAlgorithm(Algorithm):
         N = int(self.predict_topK)
         X, _, _, ptr_d, idx_d = device_structure(X, engine.device)
         top = engine.predict_topn(U, ptr_d, idx_d, N, mask_history=bool(self.remove_history))
+        engine.sync()
         idx, val, ln = to_host(top["idx"], top["val"], top["len"])
         M = lists_to_csr(idx, val, ln, I, attach=True)
         M._rpk_topn_dev = (top["idx"], top["len"], engine.device)  # the metrics read the lists where they are

@@ -80,6 +80,8 @@ def device_structure(X: csr_matrix, device: int):
         warnings.simplefilter("ignore")
         ptr_d = torch.from_numpy(indptr).to(dev, non_blocking=True)
         idx_d = torch.from_numpy(indices).to(dev, non_blocking=True)
+    # the library runs on its own stream: the uploads must have landed before it reads them
+    torch.cuda.current_stream(dev).synchronize()
     if sig is not None:
         try:
             X._rpk_dev = (sig, device, ptr_d, idx_d)

@@ -68,6 +68,7 @@ class ListwiseMetricK:
         U, I = yt.shape
         sums, n_users, per_user = engine.metrics_topn(U, idx.shape[1], top_idx, top_len, t_ptr_d, t_idx_d, [(self._kind, K)])
         if not isinstance(per_user, np.ndarray):
+            engine.sync()
             (per_user,) = to_host(per_user)
         users = np.flatnonzero(np.diff(t_ptr) > 0)  # metrics/base.py:106-123
         self.user_id_map_ = users
