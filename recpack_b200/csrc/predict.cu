@@ -1497,7 +1497,9 @@ void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr_
     pp.part_sq = c->buf<u64>("p_part_sq", (size_t)U * g.P * N);
     pp.part_len = c->buf<int>("p_part_len", (size_t)U * g.P);
     const int fgrid = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
-    if (c->flags & DBG_WIDE_ACC) {  // debug: every user through the two-limb kernel (64-bit accumulators)
+    // the block table of the 32-bit kernel indexes 4-entry blocks with 32 bits
+    const bool blocks_fit = (c->m_nnz + 3 * c->m_I) / 4 < (int64_t)0x7fffffff;
+    if ((c->flags & DBG_WIDE_ACC) || !blocks_fit) {  // debug flag / giant models: every user through the two-limb kernel
       launch_predict(c, pp, g, U, indptr);
       k_predict_finalize<<<fgrid, 256, 0, st>>>(pp.part_idx, pp.part_sq, pp.part_len, U, g.P, N, o_idx.dev, o_val.dev,
                                                 o_len.dev, nullptr, nullptr, nullptr, nullptr, 0);
