@@ -158,3 +158,30 @@ def test_shard_exchange_on_gloo_world_size_2(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def test_approximate_score_margin_property():
+    """The arithmetic behind k_predict_a32, emulated in numpy: a_j = sum((q >> s) | 1) with
+    s = 9 + ceil(log2 d) never overflows 32 bits, stays within d of score_j / 2^s, and every item of the exact
+    top N has a_j >= (N-th largest a) - 2d -- so the survivors of the approximate pass always contain it."""
+    rng = np.random.default_rng(17)
+    for d, n_items, N in ((1, 50, 5), (3, 200, 20), (84, 3000, 20), (700, 3000, 10), (5000, 4000, 20)):
+        s = 9 + (int(np.ceil(np.log2(d))) if d > 1 else 0)
+        # worst-case magnitudes included: values close to 2 (q just below 2^40) and tiny ones (q = 1)
+        v = rng.random((d, n_items)) ** 4 * 1.999
+        v[rng.random((d, n_items)) < 0.6] = 0.0            # K-sparse rows: most pairs absent
+        q = (np.rint(v * 2.0**39).astype(np.int64) | 1) * (v > 0)
+        q[0, :3] = (1 << 40) - 1                             # largest legal q
+        q[-1, 3:6] = 1                                       # smallest legal q
+        a_terms = np.where(q > 0, (q >> s) | 1, 0)
+        score = q.sum(axis=0)
+        a = a_terms.sum(axis=0)
+        assert a.max() < 2**32
+        cnt = (q > 0).sum(axis=0)
+        assert np.all(np.abs(a - score / 2.0**s) <= cnt + 1e-9) and cnt.max() <= d
+        cand = np.flatnonzero(score > 0)
+        exact_top = cand[np.lexsort((cand, -score[cand]))][:N]
+        a_sorted = np.sort(a[cand])[::-1]
+        thr = a_sorted[min(N, len(cand)) - 1] - 2 * d
+        survivors = set(cand[a[cand] >= thr].tolist())
+        assert set(exact_top.tolist()) <= survivors
