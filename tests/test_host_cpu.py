@@ -185,3 +185,24 @@ def test_approximate_score_margin_property():
         thr = a_sorted[min(N, len(cand)) - 1] - 2 * d
         survivors = set(cand[a[cand] >= thr].tolist())
         assert set(exact_top.tolist()) <= survivors
+
+
+def test_packed_counter_carry_property():
+    """The arithmetic behind the fit's packed 16-bit counters, emulated in numpy: two counts share
+    a 32-bit word that is only ever incremented by 1 or 1 << 16 (in any order, also summed over several partial
+    copies of the row); when the low count passes 65,535 it carries into the high half exactly (low total >> 16)
+    times, so subtracting that restores the neighbour's exact count."""
+    rng = np.random.default_rng(23)
+    for low_total, high_total, copies in ((70_000, 1234, 1), (131_072 + 5, 65_535 - 3, 4), (65_536, 0, 3), (100, 200, 2)):
+        # split both totals over `copies` partial words, each built by increments mod 2^32, then add the words
+        lo_parts = rng.multinomial(low_total, np.ones(copies) / copies)
+        hi_parts = rng.multinomial(high_total, np.ones(copies) / copies)
+        word = 0
+        for lp, hp in zip(lo_parts, hi_parts):
+            part = (int(lp) + (int(hp) << 16)) & 0xFFFFFFFF      # lp increments of 1, hp increments of 1 << 16
+            word = (word + part) & 0xFFFFFFFF                     # atomicAdd of the partial word
+        carries = low_total >> 16
+        if high_total + carries < 65_536:                         # the high half itself did not overflow
+            fixed = (word - (carries << 16)) & 0xFFFFFFFF
+            assert fixed >> 16 == high_total
+            assert fixed & 0xFFFF == low_total & 0xFFFF
