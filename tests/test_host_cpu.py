@@ -206,3 +206,54 @@ def test_packed_counter_carry_property():
             fixed = (word - (carries << 16)) & 0xFFFFFFFF
             assert fixed >> 16 == high_total
             assert fixed & 0xFFFF == low_total & 0xFFFF
+
+
+def test_registers_in_the_reference_registries():
+    """the drop-in classes register in recpack's own ALGORITHM_REGISTRY / METRIC_REGISTRY
+    (recpack/pipelines/registries.py:50-75) under new keys and PipelineBuilder accepts them.  Needs the reference
+    checkout (absent on the GPU box: skipped there); hyperopt is not installed, a six-name stub stands in."""
+    import sys
+    import types
+
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "recpack")):
+        pytest.skip("reference checkout not present")
+    added_path = ref not in sys.path
+    if added_path:
+        sys.path.insert(0, ref)
+    stub = None
+    if "hyperopt" not in sys.modules:
+        stub = types.ModuleType("hyperopt")
+        for name in ("Trials", "fmin", "tpe", "space_eval", "STATUS_OK", "hp"):
+            setattr(stub, name, object())
+        sys.modules["hyperopt"] = stub
+    try:
+        from recpack.pipelines import ALGORITHM_REGISTRY, METRIC_REGISTRY, PipelineBuilder
+
+        import recpack_b200
+
+        class ItemKNNB200(recpack_b200.ItemKNN):
+            pass
+
+        class NDCGKB200(recpack_b200.NDCGK):
+            pass
+
+        ALGORITHM_REGISTRY.register("ItemKNNB200", ItemKNNB200)
+        METRIC_REGISTRY.register("NDCGKB200", NDCGKB200)
+        assert ALGORITHM_REGISTRY.get("ItemKNNB200") is ItemKNNB200 and "ItemKNNB200" in ALGORITHM_REGISTRY
+        assert METRIC_REGISTRY.get("NDCGKB200") is NDCGKB200
+        with pytest.raises(KeyError):  # built-in names cannot be taken over (registries.py:63-75)
+            ALGORITHM_REGISTRY.register("ItemKNN", ItemKNNB200)
+        builder = PipelineBuilder()
+        builder.add_algorithm("ItemKNNB200", params={"K": 200, "predict_topK": 20, "remove_history": True})
+        builder.add_metric("NDCGKB200", K=[10])
+        algo = ALGORITHM_REGISTRY.get("ItemKNNB200")(K=200, predict_topK=20, remove_history=True)
+        assert algo.identifier.startswith("ItemKNNB200(K=200,") and algo.name == "ItemKNNB200"
+        assert NDCGKB200(10).name == "NDCGKB200_10"
+    finally:
+        if stub is not None:
+            sys.modules.pop("hyperopt", None)
+        if added_path:
+            sys.path.remove(ref)
+        for m in [k for k in sys.modules if k == "recpack" or k.startswith("recpack.")]:
+            sys.modules.pop(m, None)
