@@ -35,7 +35,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--shape", default="ml25m")
+    ap.add_argument("--shape", default="ml25m", help="ml100k | ml1m | ml25m | netflix | msd | large (recpack_b200/synth.py SHAPES)")
+    ap.add_argument("--similarity", default="cosine", choices=["cosine", "conditional_probability"])
+    ap.add_argument("--K", type=int, default=200, help="neighbours kept per item")
+    ap.add_argument("--generator", default="auto", choices=["auto", "numpy", "cuda"], help="synthetic data generator (synth.make_dataset)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-fit-rows", type=int, default=2048, help="item rows in the CPU baseline's fit sample")
@@ -44,13 +47,21 @@ def parse():
     return ap.parse_args()
 
 
-def make_data(shape):
-    from recpack_b200.synth import SHAPES, synth_interactions, weak_generalization_split
+def make_data(args):
+    """(train, test_out) of the named shape; the generator used is recorded in args.generator_used."""
+    from recpack_b200.synth import make_dataset
 
-    U, I, nnz = SHAPES[shape]
-    X = synth_interactions(U, I, nnz, seed=0)
-    train, test_out = weak_generalization_split(X, 0.8, seed=42)
+    train, test_out, gen = make_dataset(args.shape, seed=0, split_seed=42, generator=args.generator)
+    args.generator_used = gen
     return train, test_out
+
+
+def workload_name(args, train, n_eval=None):
+    U, I = train.shape
+    sim = "cosine" if args.similarity == "cosine" else "conditional-probability"
+    tail = f" over {n_eval} users" if n_eval is not None else ""
+    return (f"ItemKNN {sim} K={args.K}, {args.shape} shape {U}x{I}, {train.nnz} train interactions (80% WeakGeneralization split), "
+            f"top-{N_LIST} with history masked, NDCG@10 + Recall@20{tail}")
 
 
 def workload_stats(train, K, N, test_out):
@@ -175,7 +186,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    train, test_out = make_data(args.shape)
+    train, test_out = make_data(args)
     U, I = train.shape
     from oracle import recpack_oracle as orc
 
@@ -248,7 +259,7 @@ def run_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    train, test_out = make_data(args.shape)
+    train, test_out = make_data(args)
     U, I = train.shape
     stats = workload_stats(train, K_NEIGH, N_LIST, test_out)
     eng = get_engine(local_rank)

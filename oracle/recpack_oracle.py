@@ -213,9 +213,26 @@ def item_counts(Xb: csr_matrix) -> np.ndarray:
     return np.bincount(Xb.indices, minlength=Xb.shape[1]).astype(np.int64)
 
 
-def cooccurrence_rows(Xb: csr_matrix, rows) -> np.ndarray:
+class Prepared:
+    """Binarised matrix, its transpose and the item popularities, computed once (the sampled-row checks
+    at the 100 M / 500 M interaction shapes would otherwise redo the transpose per row block)."""
+
+    def __init__(self, X):
+        self.Xb = binarize(X)
+        self.Xt = self.Xb.T.tocsr()
+        self.n = item_counts(self.Xb)
+        self.shape = self.Xb.shape
+
+
+def prepare(X) -> "Prepared":
+    return X if isinstance(X, Prepared) else Prepared(X)
+
+
+def cooccurrence_rows(Xb, rows) -> np.ndarray:
     """Exact integer co-occurrence counts c[i, :] for the given item rows
     (nearest_neighbour.py:48: ``to_binary(X).T @ X`` restricted to rows)."""
+    if isinstance(Xb, Prepared):
+        return np.asarray((Xb.Xt[rows] @ Xb.Xb).todense())
     Xt = Xb.T.tocsr().astype(np.int64)
     return np.asarray((Xt[rows] @ Xb.astype(np.int64)).todense())
 
@@ -295,8 +312,8 @@ def canon_values(similarity, pop_discount, c, n_i, n_j, pw_j):
 def canon_fit(X, K=200, similarity="cosine", pop_discount=None, rows=None, block=256):
     """Canonical ItemKNN fit.  Returns dict(idx, cnt, val, len) with rows in rank order
     (best first), ``idx`` padded with -1.  ``rows`` restricts to a subset of item rows."""
-    Xb = binarize(X)
-    n = item_counts(Xb)
+    Xb = prepare(X)  # a Prepared object may be passed instead of a matrix
+    n = Xb.n
     I = Xb.shape[1]
     row_ids = np.arange(I) if rows is None else np.asarray(rows, dtype=np.int64)
     pw = _pow_table(n, pop_discount) if pop_discount else None

@@ -1,91 +1,38 @@
-"""Algorithm base classes with the reference's fit / predict contract.
+"""Item-similarity algorithm bases whose scoring runs on the GPU.
 
-Mirror of recpack/algorithms/base.py:33-304 (Algorithm, ItemSimilarityMatrixAlgorithm,
-TopKItemSimilarityMatrixAlgorithm): same names, same wrappers, same log line and warnings.  The
-scoring of ItemSimilarityMatrixAlgorithm runs on the GPU (rpk_predict_*), there is no CPU path."""
+With ``recpack`` importable the classes here subclass the reference's own
+``recpack.algorithms.base.ItemSimilarityMatrixAlgorithm`` / ``TopKItemSimilarityMatrixAlgorithm``
+(base.py:220-304): ``fit`` / ``predict`` wrappers, ``name``, ``identifier`` and the constructor are inherited,
+and only what computes is replaced -- ``_predict`` (rpk_predict_*), the input coercion (structure only,
+memoised per matrix) and the two O(nnz) Python-set checks (same warnings, computed from row pointers).
+Without ``recpack`` a small mirror of those wrappers stands in (``_mirror.py``).  There is no CPU path."""
 from __future__ import annotations
 
-import logging
-import time
 import warnings
 
 import numpy as np
 from scipy.sparse import csr_matrix
-from sklearn.base import BaseEstimator
 from sklearn.utils.validation import check_is_fitted
 
+from . import _ref
 from .engine import get_engine
 from .matrix import binary_structure, device_structure, to_csr_matrix, to_host
 
-logger = logging.getLogger("recpack")
+if _ref.HAVE_RECPACK:
+    Algorithm = _ref.ref_base.Algorithm
+    _SimilarityBase = _ref.ref_base.ItemSimilarityMatrixAlgorithm
+    _TopKBase = _ref.ref_base.TopKItemSimilarityMatrixAlgorithm
+else:
+    from . import _mirror
+
+    Algorithm = _mirror.Algorithm
+    _SimilarityBase = _mirror.ItemSimilarityMatrixAlgorithm
+    _TopKBase = _mirror.TopKItemSimilarityMatrixAlgorithm
 
 
-class Algorithm(BaseEstimator):
-    """recpack/algorithms/base.py:33-217."""
-
-    def __init__(self):
-        super().__init__()
-
-    @property
-    def name(self):
-        return self.__class__.__name__
-
-    @property
-    def identifier(self):
-        paramstring = ",".join((f"{k}={v}" for k, v in self.get_params().items()))
-        return self.name + "(" + paramstring + ")"
-
-    def __str__(self):
-        return self.name
-
-    def set_params(self, **params):
-        super().set_params(**params)
-
-    def _fit(self, X: csr_matrix):
-        raise NotImplementedError("Please implement _fit")
-
-    def _predict(self, X: csr_matrix) -> csr_matrix:
-        raise NotImplementedError("Please implement _predict")
-
-    def _check_fit_complete(self):
-        check_is_fitted(self)
-
-    def _check_prediction(self, X_pred: csr_matrix, X: csr_matrix) -> None:
-        """Warn when a user with history got no recommendation (base.py:108-127); computed from the
-        row pointers instead of Python sets over nonzero()."""
-        has_hist = np.diff(X.indptr) > 0
-        has_pred = np.diff(X_pred.indptr) > 0
-        if X_pred.nnz and not np.all(X_pred.data):  # explicit zeros do not count as recommendations
-            has_pred = np.asarray((X_pred != 0).sum(axis=1)).ravel() > 0
-        missing = int(np.count_nonzero(has_hist & ~has_pred))
-        if missing > 0:
-            warnings.warn(f"{self.name} failed to recommend any items for {missing} users")
-
-    def _transform_fit_input(self, X):
-        return to_csr_matrix(X, binary=True)
-
-    def _transform_predict_input(self, X):
-        return to_csr_matrix(X, binary=True)
-
-    def fit(self, X):
-        start = time.time()
-        X = self._transform_fit_input(X)
-        self._fit(X)
-        self._check_fit_complete()
-        end = time.time()
-        logger.info(f"Fitting {self.name} complete - Took {end - start :.3}s")
-        return self
-
-    def predict(self, X) -> csr_matrix:
-        self._check_fit_complete()
-        X = self._transform_predict_input(X)
-        X_pred = self._predict(X)
-        self._check_prediction(X_pred, X)
-        return X_pred
-
-
-class ItemSimilarityMatrixAlgorithm(Algorithm):
-    """recpack/algorithms/base.py:220-279: predict = X @ similarity_matrix_, on the GPU.
+class GpuSimilarityMixin:
+    """GPU implementation of the ``ItemSimilarityMatrixAlgorithm`` contract (base.py:220-279): predict =
+    X @ similarity_matrix_.
 
     Two additions follow the reference's own precedent ``predict_topK`` ("Use when the user x item
     output matrix would become too large for RAM", base.py:427-430):
@@ -94,7 +41,11 @@ class ItemSimilarityMatrixAlgorithm(Algorithm):
     * ``remove_history``: drop the user's own history items inside predict -- before the truncation,
       which is where the pipeline removes them (pipelines/pipeline.py:174-175).
 
-    With both unset the full score matrix of the reference is returned."""
+    With both unset ``predict`` returns every non-zero score like the reference.  Scores are exact sums
+    of the similarities in fixed point relative to the largest similarity of the model
+    (``q = rint(v / vmax * (2^39 - 1))``): they agree with the reference's float64 sums to
+    ``d_u * vmax * 2^-40`` and do not depend on summation order.  Similarity values must be finite and
+    non-negative (a signed model, e.g. EASE, uses ``recpack_b200.EASE``'s dense scorer)."""
 
     predict_topK = None
     remove_history = False
@@ -112,8 +63,10 @@ class ItemSimilarityMatrixAlgorithm(Algorithm):
 
     @similarity_matrix_.setter
     def similarity_matrix_(self, S):
-        self.__dict__["_similarity_host"] = S
-        self.__dict__["_fit_dev"] = None  # an assigned matrix replaces the device-resident fit result
+        d = self.__dict__
+        d["_similarity_host"] = S
+        d["_fit_dev"] = None  # an assigned matrix replaces the device-resident fit result
+        d["_model_version"] = d.get("_model_version", 0) + 1
 
     def _materialize_similarity(self):
         dev = self.__dict__["_fit_dev"]
@@ -127,6 +80,7 @@ class ItemSimilarityMatrixAlgorithm(Algorithm):
         d = self.__dict__
         get_engine(device).sync()  # the lists are complete before torch touches them (streams may differ)
         d["_similarity_host"] = None
+        d["_model_version"] = d.get("_model_version", 0) + 1
         d["_fit_dev"] = {"idx": out["idx"], "val": out["val"], "len": out["len"], "I": int(I), "device": int(device),
                          "empty_rows": int((out["len"] == 0).sum().item())}
 
@@ -142,37 +96,38 @@ class ItemSimilarityMatrixAlgorithm(Algorithm):
         return state
 
     # -- device model management ---------------------------------------------------------------
-    def _device_model_key(self):
-        S = self.similarity_matrix_
-        return (id(S), S.shape, S.nnz, S.data.ctypes.data, S.indices.ctypes.data)
-
     def _ensure_device_model(self, engine):
-        dev = self.__dict__.get("_fit_dev")
-        if dev is not None and dev["device"] == engine.device:
-            key = ("dev", engine.device, id(dev["idx"]))
-            if getattr(engine, "_model_key", None) != key:
+        """Loads this estimator's similarity model into the engine unless it is the resident one.  The key is
+        (estimator, version): the version is bumped whenever ``similarity_matrix_`` is assigned or a fit finishes;
+        arrays edited in place afterwards need ``invalidate_device_model()``."""
+        d = self.__dict__
+        key = (id(self), d.get("_model_version", 0))
+        with engine.model_lock:
+            if engine._model_key == key:
+                return
+            engine._model_key = None  # a failed load leaves no model behind (the C side drops it too)
+            dev = d.get("_fit_dev")
+            if dev is not None and dev["device"] == engine.device:
                 engine.model_load_topk(dev["I"], dev["idx"].shape[1], dev["idx"], dev["val"], dev["len"])
-                engine._model_key = key
-                engine._model_owner = dev["idx"]  # keeps the id unique while it is the loaded model
-            return
-        S = self.similarity_matrix_
-        if not isinstance(S, csr_matrix):
-            S = csr_matrix(S)
-            self.similarity_matrix_ = S
-        key = (engine.device,) + self._device_model_key()
-        if getattr(engine, "_model_key", None) == key:
-            return
-        if not S.has_canonical_format:
-            S = S.copy()
-            S.sum_duplicates()
-        if S.nnz and not np.all(S.data):
-            S = S.copy()
-            S.eliminate_zeros()
-        engine.model_load_csr(S.shape[0], np.ascontiguousarray(S.indptr, dtype=np.int64),
-                              np.ascontiguousarray(S.indices, dtype=np.int32),
-                              np.ascontiguousarray(S.data, dtype=np.float64))
-        engine._model_key = key
-        engine._model_owner = self.__dict__.get("_similarity_host")
+            else:
+                S = self.similarity_matrix_
+                if not isinstance(S, csr_matrix):
+                    S = csr_matrix(S)
+                if not S.has_canonical_format:
+                    S = S.copy()
+                    S.sum_duplicates()
+                if S.nnz and not np.all(S.data):
+                    S = S.copy()
+                    S.eliminate_zeros()
+                engine.model_load_csr(S.shape[0], np.ascontiguousarray(S.indptr, dtype=np.int64),
+                                      np.ascontiguousarray(S.indices, dtype=np.int32),
+                                      np.ascontiguousarray(S.data, dtype=np.float64))
+            engine._model_key = key
+            engine._model_owner = self  # keeps id(self) unique while it is the resident model
+
+    def invalidate_device_model(self):
+        """Call after editing ``similarity_matrix_`` in place: the next predict uploads it again."""
+        self.__dict__["_model_version"] = self.__dict__.get("_model_version", 0) + 1
 
     def _n_items(self):
         dev = self.__dict__.get("_fit_dev")
@@ -183,24 +138,46 @@ class ItemSimilarityMatrixAlgorithm(Algorithm):
         I = self._n_items()
         if X.shape[1] != I:
             raise ValueError("matmul: dimension mismatch with signature (n?,k),(k,m?)->(n?,m?)")
-        self._ensure_device_model(engine)
         U = X.shape[0]
-        if self.predict_topK is None:
-            X, indptr, indices = binary_structure(X)
-            o_ptr, o_idx, o_val = engine.predict_csr(U, indptr, indices, mask_history=bool(self.remove_history))
-            return csr_matrix((o_val, o_idx, o_ptr), shape=(U, I))
-        N = int(self.predict_topK)
-        X, _, _, ptr_d, idx_d = device_structure(X, engine.device)
-        top = engine.predict_topn(U, ptr_d, idx_d, N, mask_history=bool(self.remove_history))
-        engine.sync()
+        with engine.model_lock:  # load + score as one step: the engine holds one model at a time
+            self._ensure_device_model(engine)
+            if self.predict_topK is None:
+                X, indptr, indices = binary_structure(X)
+                o_ptr, o_idx, o_val = engine.predict_csr(U, indptr, indices, mask_history=bool(self.remove_history))
+                return csr_matrix((o_val, o_idx, o_ptr), shape=(U, I))
+            N = int(self.predict_topK)
+            X, _, _, ptr_d, idx_d = device_structure(X, engine.device)
+            top = engine.predict_topn(U, ptr_d, idx_d, N, mask_history=bool(self.remove_history))
+            engine.sync()
         idx, val, ln = to_host(top["idx"], top["val"], top["len"])
         M = lists_to_csr(idx, val, ln, I, attach=True)
-        M._rpk_topn_dev = (top["idx"], top["len"], engine.device)  # the metrics read the lists where they are
+        # the metrics read the lists where they are, as long as the matrix still is what predict returned
+        M._rpk_topn_dev = (top["idx"], top["len"], engine.device)
+        M._rpk_topn_sig = matrix_signature(M)
         return M
 
+    # -- the reference's checks, without Python sets over nonzero() -------------------------------------
+    def _transform_fit_input(self, X):
+        return to_csr_matrix(X, binary=True)
+
+    def _transform_predict_input(self, X):
+        return to_csr_matrix(X, binary=True)
+
+    def _check_prediction(self, X_pred: csr_matrix, X: csr_matrix) -> None:
+        """Warn when a user with history got no recommendation (base.py:108-127)."""
+        has_hist = np.diff(X.indptr) > 0
+        has_pred = np.diff(X_pred.indptr) > 0
+        if X_pred.nnz and not np.all(X_pred.data):  # explicit zeros do not count as recommendations
+            has_pred = np.asarray((X_pred != 0).sum(axis=1)).ravel() > 0
+        missing = int(np.count_nonzero(has_hist & ~has_pred))
+        if missing > 0:
+            warnings.warn(f"{self.name} failed to recommend any items for {missing} users")
+
     def _check_fit_complete(self):
-        super()._check_fit_complete()
-        assert self.__sklearn_is_fitted__()  # hasattr(self, "similarity_matrix_") without building the matrix
+        """check_is_fitted + "missing similar items" (base.py:257-279); the device-resident fit result answers
+        from its row lengths without building the host matrix."""
+        check_is_fitted(self)
+        assert self.__sklearn_is_fitted__()
         dev = self.__dict__.get("_fit_dev")
         if dev is not None:
             missing = dev["empty_rows"]
@@ -214,12 +191,20 @@ class ItemSimilarityMatrixAlgorithm(Algorithm):
             warnings.warn(f"{self.name} missing similar items for {missing} items.")
 
 
-class TopKItemSimilarityMatrixAlgorithm(ItemSimilarityMatrixAlgorithm):
+class ItemSimilarityMatrixAlgorithm(GpuSimilarityMixin, _SimilarityBase):
+    """recpack/algorithms/base.py:220-279 with ``_predict`` on the GPU: any algorithm that sets a sparse,
+    non-negative ``similarity_matrix_`` in ``_fit`` scores through rpk_predict_*."""
+
+
+class TopKItemSimilarityMatrixAlgorithm(GpuSimilarityMixin, _TopKBase):
     """recpack/algorithms/base.py:282-304."""
 
-    def __init__(self, K):
-        super().__init__()
-        self.K = K
+
+def matrix_signature(M: csr_matrix):
+    """Cheap identity of a CSR's content as predict returned it (array addresses, nnz and a checksum of the
+    values): an in-place edit of ``data`` / ``indices`` or a re-assignment changes it."""
+    return (M.data.ctypes.data, M.indices.ctypes.data, M.indptr.ctypes.data, M.nnz, M.shape,
+            float(M.data.sum()) if M.nnz else 0.0)
 
 
 def lists_to_csr(idx, val, ln, n_cols, attach=False) -> csr_matrix:

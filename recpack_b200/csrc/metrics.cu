@@ -148,6 +148,7 @@ __global__ void k_metrics(const int* __restrict__ top_idx, const int* __restrict
     else if (kind == RPK_METRIC_RECALL) v = __ddiv_rn((double)hits, (double)nt);
     else if (kind == RPK_METRIC_PRECISION) v = __ddiv_rn((double)hits, (double)K);
     else if (kind == RPK_METRIC_RECIPROCAL_RANK) v = first_hit ? __ddiv_rn(1.0, (double)first_hit) : 0.0;
+    else if (kind == RPK_METRIC_HITS) v = (double)hits;
     else v = __ddiv_rn((double)hits, (double)(nt < K ? nt : K));
     per_user[(int64_t)m * U + u] = v;
   }
@@ -192,7 +193,7 @@ void run_metrics_topn(rpk_ctx* c, int64_t U, int N, const int32_t* top_idx_u, co
   RPK_REQUIRE(sums_u && n_users_u, "sums / n_users must not be null");
   for (int m = 0; m < n_metrics; ++m) {
     // kinds / Ks are tiny and always host-side in practice; validate when they are
-    if (!is_device_ptr(kinds_u)) RPK_REQUIRE(kinds_u[m] >= 0 && kinds_u[m] <= 5, "unknown metric kind");
+    if (!is_device_ptr(kinds_u)) RPK_REQUIRE(kinds_u[m] >= 0 && kinds_u[m] <= RPK_METRIC_HITS, "unknown metric kind");
     if (!is_device_ptr(Ks_u)) RPK_REQUIRE(Ks_u[m] >= 1 && Ks_u[m] <= maxK, "metric K exceeds the discount table");
   }
   cudaStream_t st = c->stream;
@@ -224,6 +225,66 @@ void run_metrics_topn(rpk_ctx* c, int64_t U, int N, const int32_t* top_idx_u, co
   o_pu.finish(c);
   o_sums.finish(c);
   o_n.finish(c);
+  finish_call(c);
+}
+
+// ---- CoverageK (recpack/metrics/coverage.py:13-40): items that appear among the first K places of the list of
+// any user with a non-empty y_true row (metrics/base.py:106-123 drops the other users first).
+__global__ void k_coverage_mark(const int* __restrict__ top_idx, const int* __restrict__ top_len, int64_t U, int N, int K,
+                                const int64_t* __restrict__ tptr, unsigned char* __restrict__ flags) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= U * K) return;
+  const int64_t u = t / K;
+  const int r = (int)(t % K);
+  if (tptr[u + 1] == tptr[u]) return;
+  int len = top_len[u];
+  if (len > N) len = N;
+  if (r < len) flags[top_idx[u * N + r]] = 1;
+}
+
+__global__ void __launch_bounds__(1024) k_coverage_count(const unsigned char* __restrict__ flags, int64_t I,
+                                                         long long* __restrict__ out) {
+  __shared__ long long s_cnt[32];
+  long long c = 0;
+  for (int64_t j = threadIdx.x; j < I; j += blockDim.x) c += flags[j] != 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tot = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_cnt[w];
+    *out = tot;
+  }
+}
+
+void run_coverage_topn(rpk_ctx* c, int64_t U, int N, int K, int64_t I, const int32_t* top_idx_u, const int32_t* top_len_u,
+                       const int64_t* true_indptr_u, int64_t* out_count_u, uint8_t* out_flags_u) {
+  RPK_REQUIRE(U >= 0 && N >= 1 && K >= 1 && K <= N && I >= 0, "bad coverage arguments");
+  RPK_REQUIRE(out_count_u, "out_count must not be null");
+  cudaStream_t st = c->stream;
+  const int32_t* top_idx = stage_in(c, top_idx_u, (size_t)U * N, "x_top_idx");
+  const int32_t* top_len = stage_in(c, top_len_u, (size_t)U, "x_top_len");
+  const int64_t* tptr = stage_in(c, true_indptr_u, (size_t)U + 1, "x_tptr");
+  Out<int64_t> o_n;
+  Out<uint8_t> o_f;
+  o_n.init(c, out_count_u, 1, "x_cov_n");
+  unsigned char* flags;
+  if (out_flags_u) {
+    o_f.init(c, out_flags_u, (size_t)I, "x_cov_flags");
+    flags = o_f.dev;
+  } else {
+    flags = c->buf<unsigned char>("x_cov_flags", (size_t)I + 1);
+  }
+  RPK_CUDA(cudaMemsetAsync(flags, 0, (size_t)I, st));
+  if (U > 0) {
+    k_coverage_mark<<<ceil_div(U * K, 256), 256, 0, st>>>(top_idx, top_len, U, N, K, tptr, flags);
+    RPK_LAUNCH_CHECK(c);
+  }
+  k_coverage_count<<<1, 1024, 0, st>>>(flags, I, reinterpret_cast<long long*>(o_n.dev));
+  RPK_LAUNCH_CHECK(c);
+  o_n.finish(c);
+  o_f.finish(c);
   finish_call(c);
 }
 

@@ -63,6 +63,9 @@ class Engine:
         import secrets
 
         self.nonce = secrets.randbits(62)  # identifies this context in (picklable) fit tokens
+        self.model_lock = threading.RLock()  # the context holds ONE similarity model: load + score under this lock
+        self._model_key = None
+        self._model_owner = None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -99,8 +102,12 @@ class Engine:
 
     # -- fit ------------------------------------------------------------------------------
     def fit_topk(self, U, I, indptr, indices, K, similarity="cosine", item_pow=None, item_begin=0, item_end=None,
-                 want_cnt=True, want_val=True, out=None):
+                 want_cnt=True, want_val=True, out=None, normalize_X=False):
         """rpk_fit_topk.  Returns dict(idx, cnt, val, len); rows in rank order."""
+        if normalize_X:
+            # l1-normalised rows make X real-valued; the GPU Gram is defined on exact integer counts
+            # (SURVEY.md 8f-2).  No silent CPU path: say so.
+            raise NotImplementedError("normalize_X=True is not implemented on the B200 path yet")
         item_end = I if item_end is None else item_end
         rows = item_end - item_begin
         nnz = int(indices.shape[0])

@@ -1,21 +1,28 @@
 """ItemKNN on the GPU -- drop-in for recpack.algorithms.ItemKNN.
 
-Mirror of recpack/algorithms/nearest_neighbour.py:114-224: same constructor arguments, validation
-and attributes; ``_fit`` calls rpk_fit_topk instead of sklearn/scipy/numpy."""
+With ``recpack`` importable this class subclasses the reference's own ``ItemKNN``
+(recpack/algorithms/nearest_neighbour.py:114-224): constructor validation, warnings and attributes are inherited,
+``_fit`` calls rpk_fit_topk instead of sklearn / scipy / numpy, ``_predict`` is the GPU scorer of
+``GpuSimilarityMixin``."""
 from __future__ import annotations
 
-import warnings
 from typing import Optional
 
 import numpy as np
 from scipy.sparse import csr_matrix
 
-from .base import TopKItemSimilarityMatrixAlgorithm, lists_to_csr
+from . import _ref
+from .base import GpuSimilarityMixin, lists_to_csr
 from .engine import get_engine
 from .matrix import device_structure, to_host
 
+if _ref.HAVE_RECPACK:
+    _ItemKNNBase = _ref.ref_nn.ItemKNN
+else:
+    from ._mirror import ItemKNNArgs as _ItemKNNBase
 
-class ItemKNN(TopKItemSimilarityMatrixAlgorithm):
+
+class ItemKNN(GpuSimilarityMixin, _ItemKNNBase):
     """Item K Nearest Neighbours (Deshpande & Karypis 2004), cosine or conditional-probability
     similarity, K most similar items per item.  See the reference docstring
     (nearest_neighbour.py:114-167) for the model; arguments are identical.
@@ -23,8 +30,6 @@ class ItemKNN(TopKItemSimilarityMatrixAlgorithm):
     :param predict_topK: optional, keep only this many scores per user in ``predict``.
     :param remove_history: optional, drop history items inside ``predict``.
     """
-
-    SUPPORTED_SIMILARITIES = ["cosine", "conditional_probability"]
 
     def __init__(
         self,
@@ -36,31 +41,12 @@ class ItemKNN(TopKItemSimilarityMatrixAlgorithm):
         predict_topK: Optional[int] = None,
         remove_history: bool = False,
     ):
-        super().__init__(K)
-        if similarity not in self.SUPPORTED_SIMILARITIES:
-            raise ValueError(f"similarity {similarity} not supported")
-        self.similarity = similarity
-        if self.similarity != "conditional_probability" and pop_discount:
-            warnings.warn(
-                "Argument pop_discount is incompatible with all similarity \
-                functions except conditional probability. \
-                This argument will be ignored, \
-                popularity discounting won't be applied.",
-                UserWarning,
-            )
-        if type(pop_discount) == float and (pop_discount < 0 or pop_discount > 1):
-            raise ValueError("Invalid value for pop_discount. Value should be between 0 and 1.")
-        self.pop_discount = pop_discount
-        self.normalize_X = normalize_X
-        self.normalize_sim = normalize_sim
+        super().__init__(K=K, similarity=similarity, pop_discount=pop_discount, normalize_X=normalize_X,
+                         normalize_sim=normalize_sim)
         self.predict_topK = predict_topK
         self.remove_history = remove_history
 
     def _fit(self, X: csr_matrix) -> None:
-        if self.normalize_X:
-            # l1-normalised rows make X real-valued; the GPU Gram is defined on exact integer counts
-            # (SURVEY.md 8f-2).  No silent CPU path: say so.
-            raise NotImplementedError("normalize_X=True is not implemented on the B200 path yet")
         engine = get_engine()
         X, indptr, indices, ptr_d, idx_d = device_structure(X, engine.device)
         U, I = X.shape
@@ -74,7 +60,8 @@ class ItemKNN(TopKItemSimilarityMatrixAlgorithm):
         K = int(self.K)
         # the rank-ordered lists stay on the device (torch tensors owned by this estimator); similarity_matrix_
         # is built from them on first use
-        out = engine.fit_topk(U, I, ptr_d, idx_d, K, similarity=self.similarity, item_pow=item_pow, want_cnt=False)
+        out = engine.fit_topk(U, I, ptr_d, idx_d, K, similarity=self.similarity, item_pow=item_pow, want_cnt=False,
+                              normalize_X=bool(self.normalize_X))
         if self.normalize_sim:
             # Normalizer(norm="l1") over the kept entries of each row (nearest_neighbour.py:220-222), on the host
             idx, val, ln = to_host(out["idx"], out["val"], out["len"])
