@@ -26,7 +26,7 @@ if ROOT not in sys.path:
 
 METRIC = "ItemKNN fit + predict + NDCG@10/Recall@20 throughput (evaluated users / second per full pass)"
 UNIT = "users/s"
-K_NEIGH, N_LIST = 200, 20
+N_LIST = 20
 
 
 def parse():
@@ -41,9 +41,8 @@ def parse():
     ap.add_argument("--generator", default="auto", choices=["auto", "numpy", "cuda"], help="synthetic data generator (synth.make_dataset)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-fit-rows", type=int, default=2048, help="item rows in the CPU baseline's fit sample")
-    ap.add_argument("--cpu-users", type=int, default=1536, help="users in the CPU baseline's scoring sample")
-    ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes of --impl reference (0 = one per host core)")
+    ap.add_argument("--ref-fraction", type=float, default=0.02, help="fraction of a full pass one step of the reference arm / CPU baseline does")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="worker processes of --impl reference's setup (0 = one per host core, at most 64)")
     return ap.parse_args()
 
 
@@ -136,102 +135,106 @@ def measured_peaks():
 
 
 # ----------------------------------------------------------------------------------------------
-# CPU baseline: the reference's own calls (oracle restatement), bounded sample
+# CPU arm: the reference's own implementation (baseline/_ref, unmodified), row-blocked -- baseline/ref_runner.py
 # ----------------------------------------------------------------------------------------------
-def cpu_baseline(train, test_out, S_host, fit_rows, n_users, seed=0):
-    """Times ref_fit_row_blocked on `fit_rows` item rows and predict + history removal + NDCG@10 +
-    Recall@20 on `n_users` users; extrapolates linearly to the full pass.  Single-threaded like the
-    reference (scipy SpGEMM, sklearn normalise and the Python top-K loops are not threaded)."""
-    from oracle import recpack_oracle as orc
+def bench_config(args, train, test_out):
+    """The `config` object: identical for the GPU arm and the reference arm of the same command line."""
+    n_eval = int(np.count_nonzero(np.diff(test_out.indptr)))
+    return {"workload": workload_name(args, train, n_eval),
+            "l2": "256 MB buffer written between timed iterations (L2 flush)", "seeds": {"data": 0, "split": 42},
+            "generator": args.generator_used,
+            "parallelism": f"item rows x{args.gpus} (fit), users x{args.gpus} (scoring)"}
 
-    rng = np.random.default_rng(seed)
+
+def cpu_baseline(args, train, test_out, S_host, fraction, steps=1, seed0=0):
+    """One (or a few) bounded steps of the reference on ONE host thread -- the reference's sparse path is
+    single-threaded (scipy SpGEMM, sklearn normalise, the Python top-K loops).  A step fits a random `fraction` of
+    the item rows and scores + evaluates the same fraction of the users against the real fitted S, so its time is
+    that fraction of a full pass and users-in-the-sample / seconds estimates the full-pass throughput."""
+    from baseline.ref_runner import RefRunner
+
+    r = RefRunner(train, test_out, args.K, args.similarity)
+    r.set_model(S_host)
+    outs = [r.step(fraction, seed0 + k) for k in range(steps)]
     U, I = train.shape
-    rows = np.sort(rng.choice(I, size=min(fit_rows, I), replace=False))
-    t0 = time.perf_counter()
-    orc.ref_fit_row_blocked(train, K=K_NEIGH, block=2048, rows=rows)
-    t_fit_sample = time.perf_counter() - t0
-    fit_s = t_fit_sample * I / len(rows)
-    users = np.sort(rng.choice(U, size=min(n_users, U), replace=False))
-    Xs, Ys = train[users], test_out[users]
-    t0 = time.perf_counter()
-    pred = orc.ref_predict(Xs, S_host)
-    pred = orc.ref_remove_history(pred, Xs)
-    ndcg = orc.ref_ndcg(Ys, pred, 10)[0]
-    rec = orc.ref_recall(Ys, pred, 20)[0]
-    t_score_sample = time.perf_counter() - t0
-    score_rate = len(users) / t_score_sample
-    total = fit_s + U / score_rate
+    v = float(np.mean([o["users"] / o["seconds"] for o in outs]))
+    o = outs[-1]
     return {
-        "value": U / total, "unit": UNIT, "cores": 1, "kind": "port",
-        "sample": f"fit: {len(rows)} of {I} item rows ({t_fit_sample:.1f} s, x{I / len(rows):.0f} -> {fit_s:.0f} s); "
-                  f"scoring: {len(users)} of {U} users ({t_score_sample:.1f} s -> {score_rate:.0f} users/s); oracle/recpack_oracle.py ref_* "
-                  f"(same sklearn/scipy/numpy calls as recpack), 1 thread of {os.cpu_count()} host cores",
-        "fit_seconds_extrapolated": fit_s, "scoring_users_per_s": score_rate,
-        "ndcg10_sample": float(ndcg), "recall20_sample": float(rec),
+        "value": v, "unit": UNIT, "cores": 1, "kind": r.kind,
+        "sample": f"{steps} step(s) of {o['rows']} of {I} item rows fitted + {o['users']} of {U} users scored and evaluated "
+                  f"({100 * fraction:.1f} % of a full pass: fit {o['fit_seconds']:.1f} s + scoring {o['score_seconds']:.1f} s); "
+                  + ("recpack's own get_top_K_values / ItemKNN._predict / NDCGK / RecallK from baseline/_ref on sklearn cosine_similarity row blocks"
+                     if r.kind == "reference" else "oracle/recpack_oracle.py ref_* (recpack not importable)")
+                  + f", 1 thread of {os.cpu_count()} host cores",
+        "step_seconds": [round(x["seconds"], 3) for x in outs],
+        "fit_seconds_full_pass_estimate": float(np.mean([x["fit_seconds"] for x in outs])) / fraction,
+        "scoring_users_per_s": float(np.mean([x["users"] / x["score_seconds"] for x in outs])),
+        "ndcg10_sample": float(o["ndcg10"]), "recall20_sample": float(o["recall20"]),
     }
 
 
-_REF_STATE = None
-
-
-def _ref_worker(seed):
-    """One worker of the reference arm (forked: the matrices are shared copy-on-write)."""
-    os.environ["OMP_NUM_THREADS"] = "1"
-    train, test_out, S_host, fit_rows, n_users = _REF_STATE
-    return cpu_baseline(train, test_out, S_host, fit_rows, n_users, seed=seed)
-
-
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation of the path.  Setup (untimed): the data and the
+    complete similarity matrix, fitted by the reference's calls on all host cores (row blocks are independent).
+    Timed: `steps` bounded steps on one thread, each a random `--ref-fraction` of a full pass (see cpu_baseline)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from baseline.ref_runner import RefRunner, parallel_steps
+
+    t_start = time.perf_counter()
     train, test_out = make_data(args)
     U, I = train.shape
-    from oracle import recpack_oracle as orc
+    r = RefRunner(train, test_out, args.K, args.similarity)
+    procs = max(1, min(args.cpu_procs or (os.cpu_count() or 1), os.cpu_count() or 1, 64))
+    t0 = time.perf_counter()
+    d = np.diff(train.indptr).astype(np.float64)
+    full_fit = float((d * d).sum()) <= 6e10  # ML-25M / Netflix shapes: minutes of CPU in all; beyond that a stand-in
+    if full_fit:
+        S = r.fit_all(procs)
+        s_note = f"the reference's own row-blocked fit of all {I} rows on {procs} worker processes ({time.perf_counter() - t0:.0f} s, untimed setup)"
+    else:
+        rng = np.random.default_rng(1)
+        from scipy.sparse import csr_matrix
 
-    # a similarity matrix for the scoring leg: reference fit of a row sample would not give a full S, so
-    # score against the reference's row-blocked fit of the rows the sampled users' items need most: use a
-    # cheap full-size stand-in with the right sparsity (K neighbours per item, values in (0,1]).
-    rng = np.random.default_rng(1)
-    from scipy.sparse import csr_matrix
-
-    # neighbours drawn in proportion to sqrt(popularity): real top-K lists concentrate on popular items,
-    # which is what decides how many distinct scores X @ S produces per user
-    pop = np.sqrt(np.bincount(train.indices, minlength=I).astype(np.float64) + 1.0)
-    idx = rng.choice(I, size=(I, K_NEIGH), p=pop / pop.sum()).astype(np.int32)
-    S_host = csr_matrix((rng.random(I * K_NEIGH) * 0.5 + 1e-3, idx.ravel(), np.arange(I + 1, dtype=np.int64) * K_NEIGH), shape=(I, I))
-    S_host.sum_duplicates()
-    # The reference's calls are single-threaded (scipy SpGEMM, sklearn normalise, Python top-K loops), but item
-    # row blocks and user blocks are independent: one worker process per host core, each timing its own sample
-    # while all of them run; the rates add up.
-    import multiprocessing as mp
-
-    procs = max(1, min(args.cpu_procs or (os.cpu_count() or 1), os.cpu_count() or 1))
-    global _REF_STATE
-    _REF_STATE = (train, test_out, S_host, args.cpu_fit_rows, args.cpu_users)
-    vals = []
-    with mp.get_context("fork").Pool(procs) as pool:
-        for s in range(args.warmup + args.steps):
-            outs = pool.map(_ref_worker, [1000 * s + w for w in range(procs)])
-            if s >= args.warmup:
-                fit_rate = sum(I / o["fit_seconds_extrapolated"] for o in outs)      # item rows per second, all workers
-                score_rate = sum(o["scoring_users_per_s"] for o in outs)
-                total = I / fit_rate + U / score_rate
-                vals.append({"value": U / total, "fit_seconds_extrapolated": I / fit_rate, "scoring_users_per_s": score_rate,
-                             "sample": f"{procs} worker processes at once, each: " + outs[0]["sample"]})
-    v = float(np.mean([o["value"] for o in vals]))
-    last = vals[-1]
+        pop = np.sqrt(np.bincount(train.indices, minlength=I).astype(np.float64) + 1.0)
+        idx = rng.choice(I, size=(I, args.K), p=pop / pop.sum()).astype(np.int32)
+        S = csr_matrix((rng.random(I * args.K) * 0.5 + 1e-3, idx.ravel(), np.arange(I + 1, dtype=np.int64) * args.K), shape=(I, I))
+        S.sum_duplicates()
+        s_note = "a stand-in K-sparse S (neighbours ~ sqrt(popularity)): the complete reference fit of this shape takes hours of CPU"
+    r.set_model(S)
+    f = args.ref_fraction
+    outs = []
+    for s in range(args.warmup + args.steps):
+        o = r.step(f, 1000 + s)
+        if s >= args.warmup:
+            outs.append(o)
+    v = float(np.mean([o["users"] / o["seconds"] for o in outs]))
+    ms = 1000.0 * float(np.mean([o["seconds"] for o in outs]))
+    o = outs[-1]
+    # what all host cores deliver together on independent blocks (one more round, every worker one step)
+    par, wall = parallel_steps(r, f, [5000 + k for k in range(procs)])
+    v_all = float(sum(x["users"] for x in par) / wall)
+    sample = (f"each step: {o['rows']} of {I} item rows fitted + {o['users']} of {U} users scored and evaluated = {100 * f:.1f} % of a full pass, "
+              f"measured (fit {o['fit_seconds']:.1f} s + scoring {o['score_seconds']:.1f} s); scoring against {s_note}; "
+              + ("recpack's own get_top_K_values / ItemKNN._predict / NDCGK / RecallK from baseline/_ref on sklearn cosine_similarity row blocks"
+                 if r.kind == "reference" else "oracle/recpack_oracle.py ref_* (recpack not importable)")
+              + f"; 1 thread (the reference's sparse path is single-threaded) of {os.cpu_count()} host cores")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000.0 * U / v, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"ItemKNN cosine K={K_NEIGH}, {args.shape} shape {U}x{I}, {train.nnz} train interactions, top-{N_LIST}, NDCG@10/Recall@20",
-                   "note": "scoring leg uses a stand-in K-sparse S (neighbours ~ sqrt(popularity)); the fit leg is the reference's own"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": last["sample"]},
+        "config": bench_config(args, train, test_out),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": r.kind, "sample": sample,
+                         "all_cores": {"value": v_all, "cores": procs,
+                                       "sample": f"{procs} worker processes, one such step each, at once ({wall:.1f} s wall)"}},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "fit_seconds": float(np.mean([o["fit_seconds_extrapolated"] for o in vals])),
-        "scoring_users_per_s": float(np.mean([o["scoring_users_per_s"] for o in vals])),
+        "step_fraction_of_full_pass": f,
+        "full_pass_seconds_estimate": U / v,
+        "fit_seconds_full_pass_estimate": float(np.mean([x["fit_seconds"] for x in outs])) / f,
+        "scoring_users_per_s": float(np.mean([x["users"] / x["score_seconds"] for x in outs])),
+        "ndcg10_sample": float(o["ndcg10"]), "recall20_sample": float(o["recall20"]),
+        "setup_seconds": t0 - t_start, "model_seconds": time.perf_counter() - t0,
     }
     _emit(line)
 
@@ -261,6 +264,7 @@ def run_gpu(args):
 
     train, test_out = make_data(args)
     U, I = train.shape
+    K_NEIGH, SIM = args.K, args.similarity
     stats = workload_stats(train, K_NEIGH, N_LIST, test_out)
     eng = get_engine(local_rank)
     eng.use_torch_stream()
@@ -302,11 +306,11 @@ def run_gpu(args):
     def one_step(record):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-        eng.fit_topk(U, I, t_ptr_full, t_idx_full, K_NEIGH, item_begin=ib, item_end=ie, out=fit_out)
+        eng.fit_topk(U, I, t_ptr_full, t_idx_full, K_NEIGH, similarity=SIM, item_begin=ib, item_end=ie, out=fit_out)
         ev[1].record()
         if world > 1:
             g_ent, g_len = exchange.gather_packed(eng)  # rows travel in the model's packed format
-            eng.model_load_packed_rows(I, K_NEIGH, g_ent.shape[0], g_ent, g_len, exchange.row_source())
+            eng.model_load_packed_rows(I, K_NEIGH, g_ent.shape[0], g_ent, g_len, exchange.scale_exp, exchange.row_source())
         else:
             eng.model_load_topk(I, K_NEIGH, fit_out["idx"], fit_out["val"], fit_out["len"])
         ev[2].record()
@@ -364,7 +368,7 @@ def run_gpu(args):
     # ---- end to end through the public classes, host inputs (N = 1 rank-local: each rank does its shard)
     e2e = None
     if not args.no_e2e and world == 1:
-        e2e = run_e2e(train, test_out, eng, steps=max(3, min(args.steps, 5)))
+        e2e = run_e2e(args, train, test_out, eng, steps=max(3, min(args.steps, 5)))
     elif not args.no_e2e:
         # N > 1: the same sharded step through the C ABI with HOST input buffers (pinned), every copy inside the
         # timed region, wall clock bracketed by barriers, max over ranks
@@ -375,20 +379,24 @@ def run_gpu(args):
         hu_ptr, hu_idx = pin(my_ptr_h - my_lo), pin(train.indices[my_lo:my_hi].astype(np.int32))
         hy_ptr, hy_idx = pin(y_ptr_h - y_ptr_h[0]), pin(test_out.indices[int(y_ptr_h[0]):int(y_ptr_h[-1])].astype(np.int32))
         h2d_rank = sum(int(t.numel() * t.element_size()) for t in (hx_ptr, hx_idx, hu_ptr, hu_idx, hy_ptr, hy_idx))
+        h_top_idx = torch.empty((nU, N_LIST), dtype=torch.int32).pin_memory()
+        h_top_len = torch.empty((nU,), dtype=torch.int32).pin_memory()
         e_times = []
         e_red = None
         for s_ in range(max(3, min(args.steps, 5)) + 1):
             barrier()
             t0 = time.perf_counter()
-            eng.fit_topk(U, I, hx_ptr.numpy(), hx_idx.numpy(), K_NEIGH, item_begin=ib, item_end=ie, out=fit_out)
+            eng.fit_topk(U, I, hx_ptr.numpy(), hx_idx.numpy(), K_NEIGH, similarity=SIM, item_begin=ib, item_end=ie, out=fit_out)
             g_ent, g_len = exchange.gather_packed(eng)
-            eng.model_load_packed_rows(I, K_NEIGH, g_ent.shape[0], g_ent, g_len, exchange.row_source())
+            eng.model_load_packed_rows(I, K_NEIGH, g_ent.shape[0], g_ent, g_len, exchange.scale_exp, exchange.row_source())
             eng.predict_topn(nU, hu_ptr.numpy(), hu_idx.numpy(), N_LIST, mask_history=True, out=top_out)
             sums, n_users, _ = eng.metrics_topn(nU, N_LIST, top_out["idx"], top_out["len"], hy_ptr.numpy(), hy_idx.numpy(), metrics,
                                                 want_per_user=False)
             r_ = torch.tensor([sums[0], sums[1], float(n_users)], dtype=torch.float64, device=dev)
             dist.all_reduce(r_)
             e_red = r_.cpu().numpy()  # the step's result on the host
+            h_top_idx.copy_(top_out["idx"], non_blocking=True)  # ... and this rank's top-N lists
+            h_top_len.copy_(top_out["len"], non_blocking=True)
             torch.cuda.synchronize()
             dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -398,35 +406,41 @@ def run_gpu(args):
         dist.all_reduce(tot)
         te = float(np.median(e_times))
         e2e = {"value": U / te, "unit": UNIT, "seconds": te, "step_seconds": [round(x, 5) for x in e_times],
-               "h2d_bytes_per_step": int(tot.item()), "d2h_bytes_per_step": int(world * (2 * 8 + 8 + 24)),
+               "h2d_bytes_per_step": int(tot.item()), "d2h_bytes_per_step": int(U * (N_LIST * 4 + 4) + world * (2 * 8 + 8 + 24)),
                "ndcg10": float(e_red[0] / e_red[2]), "recall20": float(e_red[1] / e_red[2]),
-               "path": "C ABI per rank with pinned host inputs (X, the rank's user rows, y_true); outputs of fit / predict stay "
-                       "on the device, the metric sums come back"}
+               "path": "C ABI per rank with pinned host inputs (X, the rank's user rows, y_true); the rank's top-N lists and the "
+                       "metric sums come back to the host; the top-K similarity lists stay on the device"}
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         fit_frac_share = (ie - ib) / I
         k_gram, k_rows, k_pred = (float(np.mean(phase_ms[k])) for k in ("gram_tc", "fit_rows", "predict"))
+        # measured DRAM bytes per launch come from an `ncu --set full` capture of THIS shape / configuration when one is
+        # committed (profiles/r2_traffic.json, keyed "<shape>/<similarity>/K<k>/gpus<n>"); otherwise null
         traffic = {}
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tpath) and world == 1:
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f)
-        # dominant kernel = the longer of the two big kernels; algorithmic bytes per launch
-        if k_pred >= k_rows:
-            kname, kms = "k_predict_a32", k_pred
-            alg = stats["score_bytes"] * (d_u[ub:ue].sum() / d_u.sum())
-        else:
-            kname, kms = "k_fit_rows", k_rows
-            alg = stats["fit_bytes"] * (item_work[ib:ie].sum() / item_work.sum())
-        ach = alg / (kms * 1e-3) / 1e9
+                traffic = json.load(f).get(f"{args.shape}/{args.similarity}/K{args.K}/gpus{world}", {})
+        # both big kernels against the HBM roofline: algorithmic bytes per launch / CUDA-event time
+        alg_pred = stats["score_bytes"] * (d_u[ub:ue].sum() / d_u.sum())
+        alg_rows = stats["fit_bytes"] * (item_work[ib:ie].sum() / item_work.sum())
         notes = {
-            "k_predict_a32": "algorithmic bytes per launch / CUDA-event duration of the kernel; operands are L2-resident (measured DRAM "
-                             "traffic is far below the algorithmic bytes), the kernel is bound by the shared-memory data pipe (one 32-bit "
-                             "atomic per similarity entry, ~40 % of its wavefronts are bank-conflict replays) and instruction issue, not by HBM",
-            "k_fit_rows": "algorithmic bytes per launch / CUDA-event duration of the row kernels; X is L2-resident, the kernel is bound by "
-                          "instruction issue and shared-memory atomics (one packed 16-bit counter update per co-occurrence), not by HBM",
+            "k_predict_a32": "algorithmic bytes per launch (SURVEY 8d: d_u*(4+8K)+8+8N+4*d_out per user) / CUDA-event duration of the "
+                             "scoring kernels; S and X are L2-resident, so measured DRAM traffic is far below the algorithmic bytes: "
+                             "the kernel is bound by instruction issue and the shared-memory pipe (one 32-bit atomic per similarity "
+                             "entry), not by HBM",
+            "k_fit_rows": "algorithmic bytes per launch (4 B per co-occurrence update + CSC + output lists) / CUDA-event duration of the "
+                          "row kernels; X is L2-resident, the kernel is bound by instruction issue and shared-memory atomics, not by HBM",
         }
+        per_kernel = []
+        for nm_, ms_, alg_ in (("k_predict_a32", k_pred, alg_pred), ("k_fit_rows", k_rows, alg_rows)):
+            if ms_ > 0:
+                a_ = alg_ / (ms_ * 1e-3) / 1e9
+                per_kernel.append({"bound": "hbm", "kernel": nm_, "achieved": a_, "peak": peak, "unit": "GB/s", "frac": a_ / peak,
+                                   "traffic": traffic.get(nm_), "kernel_ms": ms_, "algorithmic_bytes": alg_, "note": notes[nm_]})
+        dom = max(per_kernel, key=lambda r_: r_["kernel_ms"])
+        kname, kms, ach = dom["kernel"], dom["kernel_ms"], dom["achieved"]
         tensor = None
         if k_gram > 0:
             bf16 = None
@@ -444,15 +458,13 @@ def run_gpu(args):
             "metric": METRIC, "value": U / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32 counts / u64 fixed-point scores / f64 values", "data": "synthetic",
-            "config": {"workload": f"ItemKNN cosine K={K_NEIGH}, {args.shape} shape {U}x{I}, {train.nnz} train interactions (80% WeakGeneralization split), "
-                                   f"top-{N_LIST} with history masked, NDCG@10 + Recall@20 over {n_eval} users",
-                       "l2": "256 MB buffer written between timed iterations (L2 flush)", "seeds": {"data": 0, "split": 42},
-                       "parallelism": f"item rows x{world} (fit), users x{world} (scoring)"},
+            "config": bench_config(args, train, test_out),
             "fit_seconds": fit_ms * 1e-3, "scoring_users_per_s": U / (score_ms * 1e-3), "exchange_ms": exch_ms,
             "ndcg10": ndcg10, "recall20": recall20, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": traffic.get(kname), "peak_source": peak_src, "kernel_ms": kms,
                          "note": notes[kname]},
+            "roofline_kernels": per_kernel,
             "roofline_tensor": tensor,
             "phases_ms": {"fit": fit_ms, "exchange": exch_ms, "score": score_ms},
             "kernels_ms": {"k_gram_i8_tc": k_gram, "k_fit_rows": k_rows, "k_predict_a32": k_pred},
@@ -466,13 +478,13 @@ def run_gpu(args):
 
             S_host = lists_to_csr(fit_out["idx"].cpu().numpy(), fit_out["val"].cpu().numpy(), fit_out["len"].cpu().numpy(), I)
             S_host.sort_indices()
-            line["cpu_baseline"] = cpu_baseline(train, test_out, S_host, args.cpu_fit_rows, args.cpu_users)
+            line["cpu_baseline"] = cpu_baseline(args, train, test_out, S_host, args.ref_fraction, steps=1)
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_e2e(train, test_out, eng, steps):
+def run_e2e(args, train, test_out, eng, steps):
     """fit(X) -> predict(X) -> NDCGK/RecallK.calculate through the drop-in classes, scipy CSR inputs whose
     arrays live in pinned host memory; every copy is inside the timed region."""
     import warnings
@@ -505,7 +517,7 @@ def run_e2e(train, test_out, eng, steps):
         t0 = time.perf_counter()
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            algo = ItemKNN(K=K_NEIGH, predict_topK=N_LIST, remove_history=True).fit(Xh)
+            algo = ItemKNN(K=args.K, similarity=args.similarity, predict_topK=N_LIST, remove_history=True).fit(Xh)
             pred = algo.predict(Xh)
         m1, m2 = NDCGK(10), RecallK(20)
         m1.calculate(Yh, pred)
@@ -522,7 +534,11 @@ def run_e2e(train, test_out, eng, steps):
     # top-K similarity lists stay on the device (similarity_matrix_ is built on first access, not here).
     d2h = U * N_LIST * 12 + U * 4 + 2 * (U * 8 + 16) + 8
     return {"value": U / t, "unit": UNIT, "seconds": t, "step_seconds": [round(x, 5) for x in times], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-            "ndcg10": float(v[0]), "recall20": float(v[1])}
+            "ndcg10": float(v[0]), "recall20": float(v[1]),
+            "path": "drop-in classes: ItemKNN(...).fit(X) -> predict(X) -> NDCGK(10) / RecallK(20).calculate with scipy CSR inputs in pinned "
+                    "host memory; the top-N prediction matrix (indices, scores) and the per-user metric values come back to the host",
+            "note": "similarity_matrix_ is not materialised inside the timed region: the top-K lists stay on the device until the "
+                    "attribute is first read (the reference's fit leaves S on the host; here that is 142 MB D2H + one CSR build on demand)"}
 
 
 def _emit(line):

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define RPK_ABI_VERSION 1
+#define RPK_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define RPK_EXPORT __attribute__((visibility("default")))
@@ -55,7 +55,8 @@ typedef struct rpk_ctx rpk_ctx;
 enum { RPK_SIM_COSINE = 0, RPK_SIM_CONDPROB = 1 };
 enum { RPK_METRIC_NDCG = 0, RPK_METRIC_RECALL = 1, RPK_METRIC_DCG = 2, RPK_METRIC_CALIBRATED_RECALL = 3,
        RPK_METRIC_PRECISION = 4,        /* hits / K (recpack/metrics/precision.py:41-50) */
-       RPK_METRIC_RECIPROCAL_RANK = 5   /* 1 / rank of the first hit, 0 without one (metrics/reciprocal_rank.py:37-40) */ };
+       RPK_METRIC_RECIPROCAL_RANK = 5,  /* 1 / rank of the first hit, 0 without one (metrics/reciprocal_rank.py:37-40) */
+       RPK_METRIC_HITS = 6              /* number of hits among the first K places = row sum of HitK's scores (metrics/hit.py:20-45) */ };
 
 RPK_EXPORT int rpk_abi_version(void);
 
@@ -73,7 +74,8 @@ RPK_EXPORT int64_t rpk_launch_count(const rpk_ctx* ctx);
 /* Test hook: force a code path.  bit 0: wide (64-bit CAS) score accumulators in predict;
  * bit 1: tiny candidate-list capacity in the selection routine (exercises its refinement and
  * tie paths on small inputs); bit 2: more than one item-range pass in fit/predict;
- * bit 3: the fit cuts its heaviest rows into pieces even on small inputs. */
+ * bit 3: the fit cuts its heaviest rows into pieces even on small inputs; bit 4: rpk_predict_topn computes exact
+ * scores for every list even when out_val is NULL (it otherwise proves most lists from approximate sums). */
 RPK_EXPORT int rpk_debug_flags(rpk_ctx* ctx, int flags);
 
 /*
@@ -105,7 +107,9 @@ RPK_EXPORT int rpk_fit_item_counts(rpk_ctx* ctx, int32_t* out_counts, int64_t I)
  * Load the similarity model used by the predict calls.
  *   _topk: from [I x K] lists as rpk_fit_topk writes them (any order inside a row).
  *   _csr:  from a CSR item x item matrix (indptr int64[I+1], column indices unique per row).
- * Values must lie in [0, 2); scoring is defined on q = rint(v * 2^39) | 1 (exact integer sums).
+ * Values must be finite and non-negative.  Scoring is defined in fixed point relative to the model's largest value
+ * vmax: q = max(rint(v * 2^e), 1) with e = 39 - floor(log2(vmax)) (so vmax * 2^e lies in [2^39, 2^40)); a score is
+ * the exact integer sum of q over the history, reported as sum * 2^-e.  |score - float64 sum| <= d_u * 2^-(e+1).
  */
 RPK_EXPORT int rpk_model_load_topk(rpk_ctx* ctx, int64_t I, int K,
                         const int32_t* idx, const double* val, const int32_t* len);
@@ -116,15 +120,19 @@ RPK_EXPORT int rpk_model_load_topk_rows(rpk_ctx* ctx, int64_t I, int K, int64_t 
                              const int32_t* idx, const double* val, const int32_t* len,
                              const int64_t* row_src);
 /* Multi-GPU exchange in the model's own format (8 bytes per entry instead of 12, and no per-rank re-sort of
- * every row after the all-gather).  rpk_model_pack_rows turns `rows` rank-ordered lists (as written by
- * rpk_fit_topk; columns are item ids in [0, I)) into packed rows out_ent[r*K + t] = column << 40 | q,
- * q = rint(val * 2^39) | 1, ascending column, unused places all-ones.  rpk_model_load_packed_rows builds the
- * model from such rows: model row i = input row row_src[i] (int64[I], null = identity), len = entries per row.
+ * every row after the all-gather).  rpk_model_scale_exp returns the exponent e these lists would get as a model
+ * of their own; the ranks agree on the smallest e (largest value anywhere) before packing.
+ * rpk_model_pack_rows turns `rows` rank-ordered lists (as written by rpk_fit_topk; columns are item ids in
+ * [0, I)) into packed rows out_ent[r*K + t] = column << 40 | q, q = max(rint(val * 2^scale_exp), 1), ascending
+ * column, unused places all-ones.  rpk_model_load_packed_rows builds the model from such rows: model row i =
+ * input row row_src[i] (int64[I], null = identity), len = entries per row, scale_exp as used for packing.
  * Replaces nothing in the reference (single process); it is the row exchange of SURVEY.md 8(e). */
+RPK_EXPORT int rpk_model_scale_exp(rpk_ctx* ctx, int K, int64_t rows, const double* val, const int32_t* len,
+                        int32_t* out_exp);
 RPK_EXPORT int rpk_model_pack_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows,
-                        const int32_t* idx, const double* val, const int32_t* len, uint64_t* out_ent);
+                        const int32_t* idx, const double* val, const int32_t* len, int scale_exp, uint64_t* out_ent);
 RPK_EXPORT int rpk_model_load_packed_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in,
-                               const uint64_t* ent, const int32_t* len, const int64_t* row_src);
+                               const uint64_t* ent, const int32_t* len, const int64_t* row_src, int scale_exp);
 /* Every rpk_fit_topk increments the context's fit token.  When the last fit covered all item rows and
  * produced values, its lists stay resident on the device and rpk_model_load_last_fit(token) builds the
  * model from them without any host round trip; it fails when `token` is not the current one. */
@@ -138,6 +146,9 @@ RPK_EXPORT int rpk_model_load_csr(rpk_ctx* ctx, int64_t I, int64_t nnz,
  * history items; keep the N best (score desc, item index asc).
  *   out_idx int32 [U x N] (-1 padded), out_val float64 [U x N] (score, 0 padded; may be NULL),
  *   out_len int32 [U].
+ * The lists are the same with and without out_val.  Without it the kernel stops at 32-bit approximate sums
+ * wherever those already prove the order (gaps larger than the error bound) and computes exact sums only for the
+ * remaining lists.
  */
 RPK_EXPORT int rpk_predict_topn(rpk_ctx* ctx, int64_t U, int64_t nnz,
                      const int64_t* indptr, const int32_t* indices,
@@ -174,6 +185,15 @@ RPK_EXPORT int rpk_metrics_topn(rpk_ctx* ctx, int64_t U, int N,
                      int n_metrics, const int32_t* kinds, const int32_t* Ks,
                      const double* discount, const double* idcg, int maxK,
                      double* per_user, double* sums, int64_t* n_users);
+
+/*
+ * CoverageK (recpack/metrics/coverage.py:13-40): *out_count = number of distinct items among the first K places of
+ * the lists of users with a non-empty y_true row (users without true items are dropped first,
+ * metrics/base.py:106-123); out_flags uint8[I] (may be NULL) marks those items.
+ */
+RPK_EXPORT int rpk_coverage_topn(rpk_ctx* ctx, int64_t U, int N, int K, int64_t I,
+                      const int32_t* top_idx, const int32_t* top_len, const int64_t* true_indptr,
+                      int64_t* out_count, uint8_t* out_flags);
 
 /*
  * Dense leg of the fit on the tensor cores (tcgen05 int8 MMA, int32 accumulation in TMEM):

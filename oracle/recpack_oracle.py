@@ -35,9 +35,18 @@ import numpy as np
 import scipy.sparse as sp
 from scipy.sparse import csr_matrix
 
-# Fixed-point scale of the canonical scoring definition (see canon_quantize).
+# Fixed-point scoring definition (see canon_quantize): the scale 2^e is chosen per model so that the largest
+# similarity lands in [2^39, 2^40).
 Q_BITS = 39
-Q_ONE = 1 << Q_BITS
+
+
+def scale_exp(values) -> int:
+    """e = 39 - floor(log2(vmax)); 39 for an empty / all-zero model."""
+    v = np.asarray(values, dtype=np.float64)
+    vmax = float(v.max()) if v.size else 0.0
+    if not vmax > 0.0:
+        return Q_BITS
+    return Q_BITS - int(np.floor(np.log2(vmax))) if np.isfinite(vmax) else Q_BITS
 
 
 # --------------------------------------------------------------------------
@@ -352,15 +361,21 @@ def topk_to_csr(idx, val, ln, n_cols) -> csr_matrix:
     return S
 
 
-def canon_quantize(values: np.ndarray) -> np.ndarray:
-    """Fixed-point image of a similarity value: q = rint(v * 2^39) | 1.
+def canon_quantize(values: np.ndarray, e: int = None) -> np.ndarray:
+    """Fixed-point image of the similarity values of ONE model: q = clip(rint(v * 2^e), 1, 2^40 - 1) with the
+    model's scale exponent e (scale_exp of all its values unless given).
 
-    Scores are exact integer sums of q, hence independent of summation order; the
-    forced low bit keeps every stored entry non-zero (|q*2^-39 - v| <= 2^-39)."""
-    q = np.rint(np.asarray(values, dtype=np.float64) * float(Q_ONE)).astype(np.int64)
-    if np.any(q < 0) or np.any(q >= (1 << 40)):
-        raise ValueError("similarity values outside [0, 2) are not representable")
-    return q | 1
+    Scores are exact integer sums of q, hence independent of summation order; a stored entry never
+    vanishes (|q * 2^-e - v| <= 2^-(e+1) unless v < 2^-(e+1))."""
+    v = np.asarray(values, dtype=np.float64)
+    if np.any(~(v >= 0)) or np.any(~np.isfinite(v)):
+        raise ValueError("similarity values must be finite and non-negative")
+    e = scale_exp(v) if e is None else e
+    sv = np.ldexp(v, e)
+    if np.any(sv >= float(1 << 40)):
+        raise ValueError("similarity values do not fit 40 bits at this scale")
+    # a stored entry never vanishes; a value within half a step of 2^40 would round up to it: clamped
+    return np.clip(np.rint(sv).astype(np.int64), 1, (1 << 40) - 1)
 
 
 def canon_scores_q(X, S: csr_matrix) -> csr_matrix:
@@ -373,6 +388,14 @@ def canon_scores_q(X, S: csr_matrix) -> csr_matrix:
     out = (Xb.astype(np.int64) @ Sq).tocsr()
     out.sort_indices()
     return out
+
+
+def canon_score_scale(S: csr_matrix) -> float:
+    """2^-e of the model: exact scores are score_q * this."""
+    Sq = csr_matrix(S, copy=True)
+    Sq.sum_duplicates()
+    Sq.eliminate_zeros()
+    return float(np.ldexp(1.0, -scale_exp(Sq.data)))
 
 
 def canon_predict_topn(X, S, N, remove_history=True):
@@ -400,14 +423,14 @@ def canon_predict_topn(X, S, N, remove_history=True):
         idx[u, :m] = cols[order]
         sq[u, :m] = vals[order]
         ln[u] = m
-    return {"idx": idx, "score_q": sq, "val": sq.astype(np.float64) / float(Q_ONE), "len": ln}
+    return {"idx": idx, "score_q": sq, "val": sq.astype(np.float64) * canon_score_scale(S), "len": ln}
 
 
 def canon_predict_csr(X, S, remove_history=False) -> csr_matrix:
     """Full canonical score matrix (float64 = score_q * 2^-39), reference layout of predict()."""
     Xb = binarize(X)
     sc = canon_scores_q(Xb, S)
-    out = csr_matrix((sc.data.astype(np.float64) / float(Q_ONE), sc.indices, sc.indptr), shape=sc.shape)
+    out = csr_matrix((sc.data.astype(np.float64) * canon_score_scale(S), sc.indices, sc.indptr), shape=sc.shape)
     if remove_history:
         out = csr_matrix(out - out.multiply(Xb))
         out.eliminate_zeros()

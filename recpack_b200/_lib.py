@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librpk.so")
+LIB_PATH = os.environ.get("RPK_LIB") or os.path.join(_HERE, "librpk.so")  # RPK_LIB: an instrumented build (profiles/)
 
 _lib = None
 
@@ -26,8 +26,9 @@ _SIGNATURES = {
     "rpk_fit_item_counts": (C.c_int, [C.c_void_p, _i32p, C.c_int64]),
     "rpk_model_load_topk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, _i32p, _f64p, _i32p]),
     "rpk_model_load_topk_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _i32p, _f64p, _i32p, _i64p]),
-    "rpk_model_pack_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _i32p, _f64p, _i32p, _vp]),
-    "rpk_model_load_packed_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _vp, _i32p, _i64p]),
+    "rpk_model_scale_exp": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _f64p, _i32p, C.POINTER(C.c_int32)]),
+    "rpk_model_pack_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _i32p, _f64p, _i32p, C.c_int, _vp]),
+    "rpk_model_load_packed_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _vp, _i32p, _i64p, C.c_int]),
     "rpk_fit_token": (C.c_int64, [C.c_void_p]),
     "rpk_model_load_last_fit": (C.c_int, [C.c_void_p, C.c_int64]),
     "rpk_model_load_csr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, _f64p]),
@@ -35,6 +36,7 @@ _SIGNATURES = {
     "rpk_predict_csr_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, C.c_int, _i64p]),
     "rpk_predict_csr_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, C.c_int, _i64p, _i32p, _f64p]),
     "rpk_topk_csr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, _f64p, C.c_int, _i32p, _i32p]),
+    "rpk_coverage_topn": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, _i32p, _i32p, _i64p, _i64p, _vp]),
     "rpk_gram_dense_u16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _vp, _vp]),
     "rpk_fit_config": (C.c_int, [C.c_void_p, C.c_int]),
     "rpk_last_timings": (C.c_int, [C.c_void_p, _vp]),
@@ -64,7 +66,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.rpk_abi_version() != 1:
+    if lib.rpk_abi_version() != 2:
         raise RpkError("librpk.so ABI version mismatch; rebuild it")
     _lib = lib
     return lib

@@ -124,17 +124,23 @@ int rpk_model_load_topk_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in, co
   RPK_API_END(ctx)
 }
 
-int rpk_model_pack_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows, const int32_t* idx, const double* val,
-                        const int32_t* len, uint64_t* out_ent) {
+int rpk_model_scale_exp(rpk_ctx* ctx, int K, int64_t rows, const double* val, const int32_t* len, int32_t* out_exp) {
   RPK_API_BEGIN(ctx)
-  rpk::run_model_pack_rows(ctx, I, K, rows, idx, val, len, out_ent);
+  rpk::run_model_scale_exp(ctx, K, rows, val, len, out_exp);
+  RPK_API_END(ctx)
+}
+
+int rpk_model_pack_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows, const int32_t* idx, const double* val,
+                        const int32_t* len, int scale_exp, uint64_t* out_ent) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_model_pack_rows(ctx, I, K, rows, idx, val, len, scale_exp, out_ent);
   RPK_API_END(ctx)
 }
 
 int rpk_model_load_packed_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in, const uint64_t* ent, const int32_t* len,
-                               const int64_t* row_src) {
+                               const int64_t* row_src, int scale_exp) {
   RPK_API_BEGIN(ctx)
-  rpk::run_model_load_packed_rows(ctx, I, K, rows_in, ent, len, row_src);
+  rpk::run_model_load_packed_rows(ctx, I, K, rows_in, ent, len, row_src, scale_exp);
   RPK_API_END(ctx)
 }
 
@@ -188,6 +194,13 @@ int rpk_metrics_topn(rpk_ctx* ctx, int64_t U, int N, const int32_t* top_idx, con
   RPK_API_BEGIN(ctx)
   rpk::run_metrics_topn(ctx, U, N, top_idx, top_len, true_indptr, true_indices, true_nnz, n_metrics, kinds, Ks, discount,
                         idcg, maxK, per_user, sums, n_users);
+  RPK_API_END(ctx)
+}
+
+int rpk_coverage_topn(rpk_ctx* ctx, int64_t U, int N, int K, int64_t I, const int32_t* top_idx, const int32_t* top_len,
+                      const int64_t* true_indptr, int64_t* out_count, uint8_t* out_flags) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_coverage_topn(ctx, U, N, K, I, top_idx, top_len, true_indptr, out_count, out_flags);
   RPK_API_END(ctx)
 }
 

@@ -40,6 +40,7 @@ enum {
   DBG_TINY_LIST = 2,   // selection: smallest legal candidate list
   DBG_MULTI_PASS = 4,  // fit / predict: at least two item-range passes
   DBG_SPLIT_ROWS = 8,  // fit: cut the heaviest rows into pieces even when they are small
+  DBG_EXACT_SCORES = 16,  // predict: exact sums for every list even when only the lists are asked for
 };
 
 }  // namespace rpk
@@ -88,6 +89,7 @@ struct rpk_ctx {
   int m_R2 = 0;
   bool m_pad = false;  // padded block layout of the model is current
   int m_max_len = 0;  // longest model row
+  int m_exp = 39;     // scale of the loaded model: q = rint(v * 2^m_exp)
 
   // ---- per-pass candidate counts of the last rpk_predict_csr_count
   int64_t pc_U = 0;

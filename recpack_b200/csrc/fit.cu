@@ -392,41 +392,40 @@ struct RowCountSrc {
   __device__ __forceinline__ u64 margin() const { return sk.margin(); }
   int cmin;  // set_floor(): counts below this cannot reach the requested key
   __device__ __forceinline__ void set_floor(u64 thr) { cmin = sk.min_count(thr); }
-  // Visit every candidate whose count reaches the floor.  Words of two packed counters are skipped as a
-  // whole when empty, which is what makes sparse rows cheap.
+  // Visit every candidate whose count reaches the floor.  The row's own slot (the diagonal) has been zeroed by the
+  // caller, so no slot needs a self test.  Packed counters are read 16 bytes (eight counters) at a time and a
+  // vector is skipped as a whole when none of its counters reaches the floor -- in the copy pass after a threshold
+  // guess that is almost every vector, which is what makes the epilogue cheap next to the accumulation.
+  // `nvec16`: number of 16-byte vectors of the counter array (the array is zero beyond the row's last counter).
+  int nvec16;
   template <class F>
-  __device__ __forceinline__ void visit(F f, int wstride, bool low_half_only) const {
+  __device__ __forceinline__ void visit(F f) const {
     const int tid = threadIdx.x, nt = blockDim.x;
     if (PACK16) {
-      const int nwords = (ns + 1) >> 1;
-      const int step = nt * wstride;
-      // four words (eight counters) per thread and iteration: all keys -- each needs a popularity load from
-      // L2 -- are computed before the first callback, so the loads overlap instead of queueing up
-      for (int wb = tid * wstride; wb < nwords; wb += 4 * step) {
-        unsigned v[4];
+      const uint4* c4 = reinterpret_cast<const uint4*>(cnt);
+      const unsigned cm = (unsigned)(cmin > 65535 ? 65535 : (cmin < 1 ? 1 : cmin));
+      const unsigned cm_hi = cm << 16;
+      const bool none = cmin > 65535;  // no 16-bit counter can reach the floor
+      for (int v = tid; v < nvec16; v += nt) {
+        const uint4 x = c4[v];
+        if ((x.x | x.y | x.z | x.w) == 0u || none) continue;
+        const unsigned xs[4] = {x.x, x.y, x.z, x.w};
+        bool any = false;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = wb + q * step < nwords ? cnt[wb + q * step] : 0u;
-        if ((v[0] | v[1] | v[2] | v[3]) == 0u) continue;
-        u64 k[8];
-        bool ok[8];
+        for (int q = 0; q < 4; ++q) any |= (xs[q] >= cm_hi) | ((xs[q] & 0xffffu) >= cm);
+        if (!any) continue;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int w = wb + q * step;
-          const int c0 = (int)(v[q] & 0xffffu), c1 = (int)(v[q] >> 16);
-          const int j0 = r0 + 2 * w;
-          ok[2 * q] = c0 >= cmin && j0 != self;
-          ok[2 * q + 1] = !low_half_only && c1 >= cmin && j0 + 1 != self;
-          k[2 * q] = ok[2 * q] ? sk.akey(c0, j0) : 0ull;
-          k[2 * q + 1] = ok[2 * q + 1] ? sk.akey(c1, j0 + 1) : 0ull;
+          const int c0 = (int)(xs[q] & 0xffffu), c1 = (int)(xs[q] >> 16);
+          const int slot = 8 * v + 2 * q;
+          if (c0 >= (int)cm) f(slot, sk.akey(c0, r0 + slot));
+          if (c1 >= (int)cm) f(slot + 1, sk.akey(c1, r0 + slot + 1));
         }
-#pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (ok[q]) f(2 * (wb + (q >> 1) * step) + (q & 1), k[q]);
       }
     } else {
-      for (int w = tid * wstride; w < ns; w += nt * wstride) {
+      for (int w = tid; w < ns; w += nt) {
         const int c0 = (int)cnt[w];
-        if (c0 >= cmin && r0 + w != self) f(w, sk.akey(c0, r0 + w));
+        if (c0 >= cmin && c0 > 0) f(w, sk.akey(c0, r0 + w));
       }
     }
   }
@@ -437,16 +436,28 @@ struct RowCountSrc {
   }
   template <class F>
   __device__ __forceinline__ void for_each(F f) const {
-    visit(f, 1, false);
+    visit(f);
     visit_extras(f);
   }
+  // one slot in SEL_SAMPLE: the low counter of every 8th word (packed) / every 16th counter
   template <class F>
   __device__ __forceinline__ void for_each_sampled(F f) const {
-    if (PACK16) visit(f, SEL_SAMPLE / 2, true);  // the low counter of every 8th word = 1 slot in 16
-    else visit(f, SEL_SAMPLE, false);
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (PACK16) {
+      const int nwords = (ns + 1) >> 1;
+      for (int w = tid * (SEL_SAMPLE / 2); w < nwords; w += nt * (SEL_SAMPLE / 2)) {
+        const int c0 = (int)(cnt[w] & 0xffffu);
+        if (c0 >= cmin && c0 > 0) f(2 * w, sk.akey(c0, r0 + 2 * w));
+      }
+    } else {
+      for (int w = tid * SEL_SAMPLE; w < ns; w += nt * SEL_SAMPLE) {
+        const int c0 = (int)cnt[w];
+        if (c0 >= cmin && c0 > 0) f(w, sk.akey(c0, r0 + w));
+      }
+    }
     visit_extras(f);
   }
-  // Integer-only pass over the packed counters: candidate count and the largest count; the key bounds
+  // Integer-only pass over the counters: candidate count and the largest count; the key bounds
   // follow from that (no popularity loads, no float math).
   __device__ void stats(SelShared* sh) const {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
@@ -455,35 +466,37 @@ struct RowCountSrc {
       sh->bstar = 0;
     }
     __syncthreads();
-    int cntc = 0, cmax = 0;
-    const int sslot = self - r0;
+    int cntc = 0;
+    unsigned cmax = 0;
     if (PACK16) {
-      const int nwords = (ns + 1) >> 1;
-      for (int w = tid; w < nwords; w += nt) {
-        const unsigned v = cnt[w];
-        int c0 = (int)(v & 0xffffu), c1 = (int)(v >> 16);
-        if (2 * w == sslot) c0 = 0;
-        if (2 * w + 1 == sslot) c1 = 0;
-        cntc += (c0 != 0) + (c1 != 0);
-        cmax = max(cmax, max(c0, c1));
+      const uint4* c4 = reinterpret_cast<const uint4*>(cnt);
+      for (int v = tid; v < nvec16; v += nt) {
+        const uint4 x = c4[v];
+        if ((x.x | x.y | x.z | x.w) == 0u) continue;
+        const unsigned xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned lo = xs[q] & 0xffffu, hi = xs[q] >> 16;
+          cntc += (lo != 0u) + (hi != 0u);
+          cmax = max(cmax, max(lo, hi));
+        }
       }
     } else {
       for (int w = tid; w < ns; w += nt) {
-        int c0 = (int)cnt[w];
-        if (w == sslot) c0 = 0;
-        cntc += c0 != 0;
+        const unsigned c0 = cnt[w];
+        cntc += c0 != 0u;
         cmax = max(cmax, c0);
       }
     }
     if (tid < nex && ex_cnt[tid] > 0 && ex_idx[tid] != self) {
       cntc++;
-      cmax = max(cmax, ex_cnt[tid]);
+      cmax = max(cmax, (unsigned)ex_cnt[tid]);
     }
     cntc = __reduce_add_sync(0xffffffffu, cntc);
     cmax = __reduce_max_sync(0xffffffffu, cmax);
     if (lane == 0 && cntc) {
       atomicAdd(&sh->count, cntc);
-      atomicMax(&sh->bstar, cmax);
+      atomicMax(&sh->bstar, (int)cmax);
     }
     __syncthreads();
     if (tid == 0) {
@@ -806,8 +819,12 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       } else {
         for (int s = tid; s < nwords; s += nt) cnt[s] = grow[s];
       }
+      // the selection passes read whole 16-byte vectors: the tail of the array must be zero
+      for (int s = nwords + tid; s < (PACK16 ? p.R >> 1 : p.R); s += nt) cnt[s] = 0u;
     } else {
-      for (int s = tid; s < nwords; s += nt) cnt[s] = 0u;
+      uint4* c4 = reinterpret_cast<uint4*>(cnt);
+      const int nv = PACK16 ? p.R >> 3 : p.R >> 2;  // R is a multiple of 8
+      for (int s = tid; s < nv; s += nt) c4[s] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
     if (pre_slot >= 0) {  // the row's users were counted in pieces (P == 1 there): start from their sum
@@ -886,7 +903,17 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       nex = H;
       __syncthreads();
     }
-    RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i, s_ex_idx, s_ex_cnt, nex, 1};
+    // the diagonal never survives (nearest_neighbour.py:64,81 + util.py:96): drop it here, once, instead of testing
+    // every slot for it in the selection passes
+    if (tid == 0) {
+      const int sl = i - r0;
+      if (sl >= 0 && sl < ns) {
+        if (PACK16) cnt[sl >> 1] &= (sl & 1) ? 0x0000ffffu : 0xffff0000u;
+        else cnt[sl] = 0u;
+      }
+    }
+    __syncthreads();
+    RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i, s_ex_idx, s_ex_cnt, nex, 1, p.R >> 3};
     bool sorted = true;
     const int m = block_select_topk(src, p.K, list, p.cap, p.direct_cap, hist, sh, p.defer_max, &sorted);
     if (!sorted) {

@@ -13,10 +13,11 @@ void run_fit_item_counts(rpk_ctx* c, int32_t* out_counts, int64_t I);
 
 void run_model_load_topk(rpk_ctx* c, int64_t I, int K, const int32_t* idx, const double* val, const int32_t* len);
 void run_model_load_last_fit(rpk_ctx* c, int64_t token);
+void run_model_scale_exp(rpk_ctx* c, int K, int64_t rows, const double* val, const int32_t* len, int32_t* out_exp);
 void run_model_pack_rows(rpk_ctx* c, int64_t I, int K, int64_t rows, const int32_t* idx, const double* val,
-                         const int32_t* len, uint64_t* out_ent);
+                         const int32_t* len, int scale_exp, uint64_t* out_ent);
 void run_model_load_packed_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, const uint64_t* ent, const int32_t* len,
-                                const int64_t* row_src);
+                                const int64_t* row_src, int scale_exp);
 void run_model_load_topk_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, const int32_t* idx, const double* val,
                               const int32_t* len, const int64_t* row_src);
 void run_model_load_csr(rpk_ctx* c, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices,
@@ -34,6 +35,9 @@ void run_metrics_topn(rpk_ctx* c, int64_t U, int N, const int32_t* top_idx, cons
                       const int64_t* true_indptr, const int32_t* true_indices, int64_t true_nnz, int n_metrics,
                       const int32_t* kinds, const int32_t* Ks, const double* discount, const double* idcg, int maxK,
                       double* per_user, double* sums, int64_t* n_users);
+
+void run_coverage_topn(rpk_ctx* c, int64_t U, int N, int K, int64_t I, const int32_t* top_idx, const int32_t* top_len,
+                       const int64_t* true_indptr, int64_t* out_count, uint8_t* out_flags);
 
 void run_gram_dense_u16(rpk_ctx* c, int64_t I, int64_t Kd, const unsigned char* A, unsigned short* G);
 void run_gram_dense_tc(rpk_ctx* c, const unsigned char* A, int64_t rows_pad, int64_t kd_pad, int64_t row_begin,

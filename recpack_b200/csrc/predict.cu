@@ -6,9 +6,11 @@
 //   recpack/pipelines/pipeline.py:174-175  history removal
 //   recpack/metrics/base.py:189            get_top_K_ranks(y_pred, K) on the prediction rows
 //
-// Scores are exact integers: every similarity value is stored as q = rint(v * 2^39) | 1 (40 bits), a
-// score is the integer sum of q over the history.  Integer sums make the result independent of the order
-// in which the atomics land, so the top-N lists are deterministic.  Two kernels:
+// Scores are exact integers: every similarity value is stored as q = max(rint(v * 2^e), 1) (40 bits), with the
+// power of two 2^e chosen per model so that the largest similarity lands in [2^39, 2^40) -- the resolution is
+// relative to the model's largest value (2^-40 of it), whatever its magnitude.  A score is the integer sum of q
+// over the history, reported as sum * 2^-e.  Integer sums make the result independent of the order in which the
+// atomics land, so the top-N lists are deterministic.  Two kernels:
 //   k_predict_a32  top-N: 32-bit approximate sums with one native shared-memory atomic (ATOMS.ADD) per
 //                  entry pick the few items that can be in the top N, a second sweep adds their exact q;
 //   k_predict      full CSR output, and the exact path for users k_predict_a32 hands over: the sum is kept
@@ -33,11 +35,68 @@ constexpr int LIMB_CHUNK = 4095;  // rows that can be added before the low limb 
 // ------------------------------------------------------------------------------------------
 // Model construction
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool quantize(double v, u64& q) {
-  if (!(v >= 0.0) || !(v < 2.0)) return false;
-  long long r = __double2ll_rn(v * 549755813888.0);  // 2^39, exact scaling; round half to even like np.rint
-  q = ((u64)r) | 1ull;
-  return q <= Q_MASK40;
+// Scale of the loaded model: q = rint(v * 2^e), scores come back as sum * inv (inv = 2^-e).
+struct ModelScale {
+  double inv;
+  int e;
+  int pad;
+};
+
+__device__ __forceinline__ bool quantize(double v, int e, u64& q) {
+  if (!(v >= 0.0) || !(v <= 1.7e308)) return false;  // negative, NaN or infinite
+  const double sv = scalbn(v, e);                   // exact power-of-two scaling
+  if (!(sv < 1099511627776.0)) return false;        // does not fit 40 bits (cannot happen with the model's own scale)
+  long long r = __double2ll_rn(sv);                 // round half to even like np.rint
+  q = r < 1 ? 1ull : (u64)r;                        // a stored entry never vanishes
+  if (q > Q_MASK40) q = Q_MASK40;                   // a value within half a step of 2^40 rounds up to it: clamp
+  return true;
+}
+
+// Largest value of the lists / CSR about to be loaded (bit pattern of a non-negative double orders like an integer).
+__global__ void k_model_vmax_lists(const double* __restrict__ val, const int* __restrict__ len, const int64_t* __restrict__ row_src,
+                                   int K, int64_t nrows, u64* __restrict__ vmax_bits, int* __restrict__ flag) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  u64 best = 0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nrows * K; t += stride) {
+    const int64_t src = row_src ? row_src[t / K] : t / K;
+    int m = len[src];
+    m = m > K ? K : m;
+    if ((int)(t % K) < m) {
+      const double v = val[src * K + t % K];
+      if (!(v >= 0.0) || !(v <= 1.7e308)) atomicOr(flag, 1);
+      else best = max(best, (u64)__double_as_longlong(v));
+    }
+  }
+  best = warp_max_u64(best);
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(vmax_bits, best);
+}
+
+__global__ void k_model_vmax_flat(const double* __restrict__ val, int64_t n, u64* __restrict__ vmax_bits, int* __restrict__ flag) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  u64 best = 0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    const double v = val[t];
+    if (!(v >= 0.0) || !(v <= 1.7e308)) atomicOr(flag, 1);
+    else best = max(best, (u64)__double_as_longlong(v));
+  }
+  best = warp_max_u64(best);
+  if ((threadIdx.x & 31) == 0 && best) atomicMax(vmax_bits, best);
+}
+
+// e = 39 - floor(log2(vmax)): vmax * 2^e lies in [2^39, 2^40).  An empty (or all-zero) model gets e = 39.
+__global__ void k_model_scale(const u64* __restrict__ vmax_bits, ModelScale* __restrict__ sc, int forced_e, int use_forced) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int e = 39;
+    if (use_forced) {
+      e = forced_e;
+    } else {
+      const double vmax = __longlong_as_double((long long)vmax_bits[0]);
+      if (vmax > 0.0) e = 39 - ilogb(vmax);
+    }
+    sc->e = e;
+    sc->inv = scalbn(1.0, -e);
+    sc->pad = 0;
+  }
 }
 
 // One CTA per row: pack (idx, q), sort by idx, write the row.
@@ -45,11 +104,13 @@ __global__ void __launch_bounds__(256) k_model_from_topk(const int* __restrict__
                                                          const int* __restrict__ len, const int64_t* __restrict__ row_src,
                                                          int K, int I, int nrows,
                                                          const int64_t* __restrict__ m_ptr, u64* __restrict__ m_ent,
-                                                         unsigned* __restrict__ m_rowmax, int* __restrict__ flag) {
+                                                         unsigned* __restrict__ m_rowmax, int* __restrict__ flag,
+                                                         const ModelScale* __restrict__ scale) {
   extern __shared__ __align__(16) unsigned char smem[];
   u64* buf = reinterpret_cast<u64*>(smem);
   __shared__ unsigned s_max;
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int sc_e = scale->e;
   int n2 = 2;
   while (n2 < K) n2 <<= 1;
   for (int i = blockIdx.x; i < nrows; i += gridDim.x) {
@@ -65,7 +126,7 @@ __global__ void __launch_bounds__(256) k_model_from_topk(const int* __restrict__
       if (t < m) {
         int j = idx[src * K + t];
         u64 q = 1;
-        bool ok = quantize(val[src * K + t], q);
+        bool ok = quantize(val[src * K + t], sc_e, q);
         if (!ok || j < 0 || j >= I) atomicOr(flag, 1);
         packed = ((u64)(unsigned)j << 40) | (q & Q_MASK40);
         lmax = max(lmax, (unsigned)(q >> LIMB_BITS) + 1u);
@@ -105,8 +166,10 @@ __global__ void __launch_bounds__(256) k_model_from_topk(const int* __restrict__
 // One warp per row of a CSR with ascending unique columns.
 __global__ void k_model_from_csr(const int64_t* __restrict__ indptr, const int* __restrict__ indices,
                                  const double* __restrict__ values, int64_t I, u64* __restrict__ m_ent,
-                                 unsigned* __restrict__ m_rowmax, int* __restrict__ m_len, int* __restrict__ flag) {
+                                 unsigned* __restrict__ m_rowmax, int* __restrict__ m_len, int* __restrict__ flag,
+                                 const ModelScale* __restrict__ scale) {
   const int lane = threadIdx.x & 31;
+  const int sc_e = scale->e;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = warp; i < I; i += nwarps) {
@@ -115,7 +178,7 @@ __global__ void k_model_from_csr(const int64_t* __restrict__ indptr, const int* 
     for (int64_t k = b + lane; k < e; k += 32) {
       int j = indices[k];
       u64 q = 1;
-      bool ok = quantize(values[k], q);
+      bool ok = quantize(values[k], sc_e, q);
       if (!ok || j < 0 || j >= I) atomicOr(flag, 1);
       if (k > b && indices[k - 1] >= j) atomicOr(flag, 2);
       m_ent[k] = ((u64)(unsigned)j << 40) | (q & Q_MASK40);
@@ -151,29 +214,14 @@ __global__ void k_model_seg(const int64_t* __restrict__ m_ptr, const u64* __rest
   seg[t] = (int)(lo - b);
 }
 
-// ---- block layout for the 32-bit scoring kernel: every row padded to a multiple of 4 entries (32 bytes, one
-// sector) with all-ones entries, whose column 0xFFFFFF lies outside every item range.
-__global__ void k_model_pad_len(const int64_t* __restrict__ m_ptr, int64_t I, int* __restrict__ len4) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < I) len4[i] = (int)((m_ptr[i + 1] - m_ptr[i] + 3) & ~(int64_t)3);
-}
-
-__global__ void k_model_pad(const int64_t* __restrict__ m_ptr, const u64* __restrict__ m_ent,
-                            const int64_t* __restrict__ ptr4, int64_t I, u64* __restrict__ ent4) {
-  const int lane = threadIdx.x & 31;
-  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = warp; i < I; i += nwarps) {
-    const int64_t b = m_ptr[i], n = m_ptr[i + 1] - b, o = ptr4[i], n4 = ptr4[i + 1] - o;
-    for (int64_t k = lane; k < n4; k += 32) ent4[o + k] = k < n ? m_ent[b + k] : ~0ull;
-  }
-}
-
-// blk[i*P + p] = {first 4-entry block, number of blocks} covering the entries of row i with column in
-// [p*R, (p+1)*R).  The blocks may also hold neighbours from the adjacent ranges of the same row (and
-// padding); the kernel drops those by their column.
-__global__ void k_model_blocks(const int64_t* __restrict__ m_ptr, const u64* __restrict__ m_ent,
-                               const int64_t* __restrict__ ptr4, int64_t I, int P, int R, int2* __restrict__ blk) {
+// ---- block layout for the 32-bit scoring kernel, built per geometry (P item ranges of R items).  The entries of
+// every (row, item range) segment are copied out on their own, padded to a multiple of 4 entries (32 bytes, one
+// sector), and re-packed as (q << 24) | slot with slot = column - p*R, the accumulator the kernel adds to: one AND
+// and one shift per entry, no range test.  Padding entries have q = 0 and slot = R + (position in the segment & 31):
+// they land in 32 scratch accumulators behind the range, a different bank for every lane of the warp that reads them.
+// seg[t] = {offset of the segment inside its model row, entries}, t = row * P + range
+__global__ void k_model_seg_len(const int64_t* __restrict__ m_ptr, const u64* __restrict__ m_ent, int64_t I, int P, int R,
+                                int2* __restrict__ seg, int* __restrict__ len4) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= I * P) return;
   const int64_t i = t / P;
@@ -189,12 +237,38 @@ __global__ void k_model_blocks(const int64_t* __restrict__ m_ptr, const u64* __r
     return lo - b;
   };
   const int64_t s0 = lower((u64)p * (u64)R), s1 = lower((u64)(p + 1) * (u64)R);
-  int2 r = make_int2(0, 0);
-  if (s1 > s0) {
-    const int64_t first = (ptr4[i] + s0) >> 2, last = (ptr4[i] + s1 + 3) >> 2;
-    r = make_int2((int)first, (int)(last - first));
+  seg[t] = make_int2((int)s0, (int)(s1 - s0));
+  len4[t] = (int)((s1 - s0 + 3) & ~(int64_t)3);
+}
+
+// One warp per segment: copy + re-pack + pad; blk[t] = {first 4-entry block, number of blocks, ceil(largest q / 2^20), 0}.
+// The third field bounds every term of the segment: the kernel sums it over a user's rows to choose the shift of
+// its 32-bit sums.
+__global__ void k_model_pad(const int64_t* __restrict__ m_ptr, const u64* __restrict__ m_ent, const int2* __restrict__ seg,
+                            const int64_t* __restrict__ ptr4, int64_t I, int P, int R, u64* __restrict__ ent4,
+                            int4* __restrict__ blk) {
+  const int lane = threadIdx.x & 31;
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = warp; t < I * P; t += nwarps) {
+    const int64_t i = t / P;
+    const int p = (int)(t % P);
+    const int2 sg = seg[t];
+    const int64_t src = m_ptr[i] + sg.x, o = ptr4[t], n4 = ptr4[t + 1] - o;
+    u64 qmax = 0;
+    for (int64_t k = lane; k < n4; k += 32) {
+      u64 v = (u64)(unsigned)(R + (int)(k & 31));  // padding: q = 0, a scratch slot of this lane's own
+      if (k < sg.y) {
+        const u64 e = m_ent[src + k];
+        const u64 q = e & Q_MASK40;
+        v = (q << 24) | (u64)((unsigned)(e >> 40) - (unsigned)p * (unsigned)R);
+        qmax = max(qmax, q);
+      }
+      ent4[o + k] = v;
+    }
+    qmax = warp_max_u64(qmax);
+    if (lane == 0) blk[t] = make_int4((int)(o >> 2), (int)(n4 >> 2), (int)(unsigned)((qmax + 0xfffffull) >> 20), 0);
   }
-  blk[t] = r;
 }
 
 __global__ void k_gather_len(const int* __restrict__ len, const int64_t* __restrict__ row_src, int64_t I, int* __restrict__ out) {
@@ -210,15 +284,28 @@ static void model_common_begin(rpk_ctx* c, int64_t I) {
   c->m_pad = false;
   int* flag = c->buf<int>("m_flag", 1);
   RPK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+  RPK_CUDA(cudaMemsetAsync(c->buf<u64>("m_vmax", 1), 0, sizeof(u64), c->stream));
+  c->buf<ModelScale>("m_scale", 1);
+}
+
+// Scale of the model about to be loaded: from the largest value (forced < 0 ... use_forced = false) or as given.
+static const ModelScale* model_set_scale(rpk_ctx* c, bool use_forced, int forced_e) {
+  ModelScale* sc = c->get<ModelScale>("m_scale");
+  k_model_scale<<<1, 32, 0, c->stream>>>(c->get<u64>("m_vmax"), sc, forced_e, use_forced ? 1 : 0);
+  RPK_LAUNCH_CHECK(c);
+  return sc;
 }
 
 static void model_check_flag(rpk_ctx* c) {
   int h = 0;
+  ModelScale hs;
   RPK_CUDA(cudaMemcpyAsync(&h, c->get<int>("m_flag"), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  RPK_CUDA(cudaMemcpyAsync(&hs, c->get<ModelScale>("m_scale"), sizeof(ModelScale), cudaMemcpyDeviceToHost, c->stream));
   RPK_CUDA(cudaStreamSynchronize(c->stream));
+  c->m_exp = hs.e;
   if (h & 1) {
     c->m_I = 0;
-    throw Error("similarity model: values must lie in [0, 2) and columns in [0, I)");
+    throw Error("similarity model: values must be finite and non-negative, columns in [0, I)");
   }
   if (h & 2) {
     c->m_I = 0;
@@ -253,11 +340,17 @@ void run_model_load_topk_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, con
   u64* m_ent = c->buf<u64>("m_ent", (size_t)I * K);
   unsigned* m_rowmax = c->buf<unsigned>("m_rowmax", (size_t)I);
   if (I > 0) {
+    k_model_vmax_lists<<<(int)std::min<int64_t>(ceil_div(I * K, 256), (int64_t)c->sm_count * 16), 256, 0, st>>>(
+        val, len, row_src, K, I, c->get<u64>("m_vmax"), c->get<int>("m_flag"));
+    RPK_LAUNCH_CHECK(c);
+  }
+  const ModelScale* scale = model_set_scale(c, false, 0);
+  if (I > 0) {
     int n2 = 2;
     while (n2 < K) n2 <<= 1;
     const int grid = (int)std::min<int64_t>(I, (int64_t)c->sm_count * 16);
     k_model_from_topk<<<grid, 128, (size_t)n2 * sizeof(u64), st>>>(idx, val, len, row_src, K, (int)I, (int)I, m_ptr, m_ent, m_rowmax,
-                                                                  c->get<int>("m_flag"));
+                                                                  c->get<int>("m_flag"), scale);
     RPK_LAUNCH_CHECK(c);
   }
   int64_t total = 0;
@@ -284,7 +377,7 @@ __global__ void k_model_from_packed(const u64* __restrict__ ent, const int64_t* 
     for (int t = lane; t < n; t += 32) {
       const u64 e = row[t];
       const u64 col = e >> 40, q = e & Q_MASK40;
-      if (col >= (u64)I || !(q & 1ull)) atomicOr(flag, 1);
+      if (col >= (u64)I || q == 0ull) atomicOr(flag, 1);
       if (t > 0 && (row[t - 1] >> 40) >= col) atomicOr(flag, 2);
       m_ent[base + t] = e;
       lmax = max(lmax, (unsigned)(q >> LIMB_BITS) + 1u);
@@ -295,8 +388,37 @@ __global__ void k_model_from_packed(const u64* __restrict__ ent, const int64_t* 
   }
 }
 
+// Exponent e of the scale 2^e these lists would get as a model of their own (39 - floor(log2(largest value))).
+void run_model_scale_exp(rpk_ctx* c, int K, int64_t rows, const double* val_u, const int32_t* len_u, int32_t* out_exp) {
+  RPK_REQUIRE(K >= 1 && K <= 4096, "K must be in [1, 4096]");
+  RPK_REQUIRE(rows >= 0 && out_exp, "bad arguments");
+  cudaStream_t st = c->stream;
+  const double* val = stage_in(c, val_u, (size_t)rows * K, "pk_in_val");
+  const int32_t* len = stage_in(c, len_u, (size_t)rows, "pk_in_len");
+  u64* vmax = c->buf<u64>("pk_vmax", 1);
+  int* flag = c->buf<int>("pk_flag", 1);
+  ModelScale* sc = c->buf<ModelScale>("pk_scale", 1);
+  RPK_CUDA(cudaMemsetAsync(vmax, 0, sizeof(u64), st));
+  RPK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  if (rows > 0) {
+    k_model_vmax_lists<<<(int)std::min<int64_t>(ceil_div(rows * K, 256), (int64_t)c->sm_count * 16), 256, 0, st>>>(val, len, nullptr, K, rows,
+                                                                                                                  vmax, flag);
+    RPK_LAUNCH_CHECK(c);
+  }
+  k_model_scale<<<1, 32, 0, st>>>(vmax, sc, 0, 0);
+  RPK_LAUNCH_CHECK(c);
+  ModelScale hs;
+  int h = 0;
+  RPK_CUDA(cudaMemcpyAsync(&hs, sc, sizeof(ModelScale), cudaMemcpyDeviceToHost, st));
+  RPK_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  RPK_CUDA(cudaStreamSynchronize(st));
+  RPK_REQUIRE(!(h & 1), "similarity lists: values must be finite and non-negative");
+  *out_exp = hs.e;
+}
+
 void run_model_pack_rows(rpk_ctx* c, int64_t I, int K, int64_t rows, const int32_t* idx_u, const double* val_u,
-                         const int32_t* len_u, uint64_t* out_u) {
+                         const int32_t* len_u, int scale_exp, uint64_t* out_u) {
+  RPK_REQUIRE(scale_exp > -1000 && scale_exp < 1100, "scale exponent out of range");
   RPK_REQUIRE(K >= 1 && K <= 4096, "K must be in [1, 4096]");
   RPK_REQUIRE(I >= 0 && I < ((int64_t)1 << 24), "item count must be below 2^24");
   RPK_REQUIRE(rows >= 0, "negative row count");
@@ -309,27 +431,32 @@ void run_model_pack_rows(rpk_ctx* c, int64_t I, int K, int64_t rows, const int32
   o.init(c, reinterpret_cast<u64*>(out_u), (size_t)rows * K, "pk_out");
   int* flag = c->buf<int>("pk_flag", 1);
   RPK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  ModelScale* sc = c->buf<ModelScale>("pk_scale", 1);
+  k_model_scale<<<1, 32, 0, st>>>(nullptr, sc, scale_exp, 1);
+  RPK_LAUNCH_CHECK(c);
   if (rows > 0) {
     int n2 = 2;
     while (n2 < K) n2 <<= 1;
     const int grid = (int)std::min<int64_t>(rows, (int64_t)c->sm_count * 16);
-    k_model_from_topk<<<grid, 128, (size_t)n2 * sizeof(u64), st>>>(idx, val, len, nullptr, K, (int)I, (int)rows, nullptr, o.dev, nullptr, flag);
+    k_model_from_topk<<<grid, 128, (size_t)n2 * sizeof(u64), st>>>(idx, val, len, nullptr, K, (int)I, (int)rows, nullptr, o.dev, nullptr, flag, sc);
     RPK_LAUNCH_CHECK(c);
   }
   int h = 0;
   RPK_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   RPK_CUDA(cudaStreamSynchronize(st));
-  RPK_REQUIRE(!(h & 1), "similarity lists: values must lie in [0, 2) and columns in [0, I)");
+  RPK_REQUIRE(!(h & 1), "similarity lists: values must be finite, non-negative and below 2^(40 - scale_exp); columns in [0, I)");
   RPK_REQUIRE(!(h & 2), "similarity lists: column indices must be unique within a row");
   o.finish(c);
   finish_call(c);
 }
 
 void run_model_load_packed_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, const uint64_t* ent_u, const int32_t* len_u,
-                                const int64_t* row_src_u) {
+                                const int64_t* row_src_u, int scale_exp) {
   RPK_REQUIRE(K >= 1 && K <= 4096, "K must be in [1, 4096]");
   RPK_REQUIRE(rows_in >= I || row_src_u, "fewer input rows than items");
+  RPK_REQUIRE(scale_exp > -1000 && scale_exp < 1100, "scale exponent out of range");
   model_common_begin(c, I);
+  model_set_scale(c, true, scale_exp);
   cudaStream_t st = c->stream;
   const u64* ent = stage_in(c, reinterpret_cast<const u64*>(ent_u), (size_t)rows_in * K, "m_in_ent");
   const int32_t* len = stage_in(c, len_u, (size_t)rows_in, "m_in_len");
@@ -382,9 +509,15 @@ void run_model_load_csr(rpk_ctx* c, int64_t I, int64_t nnz, const int64_t* indpt
   u64* m_ent = c->buf<u64>("m_ent", (size_t)nnz);
   unsigned* m_rowmax = c->buf<unsigned>("m_rowmax", (size_t)I);
   int* m_len = c->buf<int>("m_len", (size_t)I);
+  if (nnz > 0) {
+    k_model_vmax_flat<<<(int)std::min<int64_t>(ceil_div(nnz, 256), (int64_t)c->sm_count * 16), 256, 0, st>>>(
+        values, nnz, c->get<u64>("m_vmax"), c->get<int>("m_flag"));
+    RPK_LAUNCH_CHECK(c);
+  }
+  const ModelScale* scale = model_set_scale(c, false, 0);
   if (I > 0) {
     const int grid = (int)std::min<int64_t>((I * 32 + 255) / 256, (int64_t)c->sm_count * 16);
-    k_model_from_csr<<<grid, 256, 0, st>>>(indptr, indices, values, I, m_ent, m_rowmax, m_len, c->get<int>("m_flag"));
+    k_model_from_csr<<<grid, 256, 0, st>>>(indptr, indices, values, I, m_ent, m_rowmax, m_len, c->get<int>("m_flag"), scale);
     RPK_LAUNCH_CHECK(c);
   }
   int64_t ends[2] = {0, 0};
@@ -473,6 +606,7 @@ struct PredParams {
   const int64_t* out_indptr;
   int* out_indices;
   double* out_values;
+  const ModelScale* scale;   // scores are reported as sum * scale->inv
   unsigned long long* prof;  // RPK_PHASE_PROF builds: cycles of thread 0 per phase
 };
 
@@ -702,6 +836,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       if (tid == 0) p.pass_cnt[slot_out] = s_cnt;
     } else {
       int64_t out = p.out_indptr[u];
+      const double inv_scale = p.scale->inv;
       for (int q = 0; q < pass; ++q) out += p.pass_cnt[(int64_t)u * p.P + q];
       int running = 0;
       for (int base = 0; base < ns; base += nt) {
@@ -719,7 +854,7 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
         if (sc != 0) {
           const int pos = running + off + __popc(bal & ((1u << lane) - 1u));
           p.out_indices[out + pos] = r0 + s;
-          p.out_values[out + pos] = (double)sc * (1.0 / 549755813888.0);
+          p.out_values[out + pos] = (double)sc * inv_scale;
         }
         running += tot;
         __syncthreads();
@@ -746,60 +881,25 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
 
 
 // ------------------------------------------------------------------------------------------
-// Scoring kernel, top-N mode: 32-bit approximate accumulators + exact scores for the survivors
+// Scoring kernel, top-N mode: 32-bit approximate sums, exact scores only where the order needs them
 // ------------------------------------------------------------------------------------------
 // The two-limb kernel above pays two shared-memory atomics per similarity entry and 8 bytes per item slot.
-// For top-N only a handful of scores per user matter, so this kernel runs two sweeps over the user's rows:
-//   1. a_j += (q >> s) | 1 with ONE 32-bit atomic per entry (s = 9 + ceil(log2 d) keeps every sum below
-//      2^32).  Each term is within 1 of q / 2^s, so |a_j - score_j / 2^s| <= d: a_j orders two items
-//      correctly whenever their a differ by more than 2d.
-//   2. the selection keeps every item whose a_j is within 2d of the N-th largest (a few more than N); their
-//      slots are marked and the rows are streamed again, adding the exact q of marked slots only.
-// The survivors are then ordered by their exact scores.  4 bytes per slot let two CTAs share an SM, so one
-// CTA's latency-bound steps (work fetch, selection, output) hide behind the other's atomics.  A user whose
-// survivors do not fit the list (huge groups of near-equal scores) is handed to the two-limb kernel.
-struct ApproxSrc {
-  const unsigned* acc;
-  const int* touched;  // non-null: slot list (sparse mode)
-  int r0, ns;
-  u64 floor_;
-  u64 margin_;
-  u64 kmax_;
-  __device__ __forceinline__ int nslots() const { return ns; }
-  __device__ __forceinline__ u64 margin() const { return margin_; }
-  __device__ __forceinline__ void set_floor(u64 thr) { floor_ = thr; }
-  __device__ __forceinline__ void stats(SelShared* sh) const {
-    if (threadIdx.x == 0) {
-      sh->count = ns;
-      sh->kmin = 1ull;
-      sh->kmax = kmax_;
-    }
-    __syncthreads();
-  }
-  template <class F>
-  __device__ __forceinline__ void visit(F f, int stride) const {
-    for (int slot = threadIdx.x * stride; slot < ns; slot += blockDim.x * stride) {
-      const int j = touched ? touched[slot] : slot;
-      const u64 k = (u64)acc[j];
-      if (k != 0 && k >= floor_) f(slot, k);
-    }
-  }
-  template <class F>
-  __device__ __forceinline__ void for_each(F f) const { visit(f, 1); }
-  template <class F>
-  __device__ __forceinline__ void for_each_sampled(F f) const { visit(f, SEL_SAMPLE); }
-  __device__ __forceinline__ void entry(int slot, Entry& e) const {
-    const int j = touched ? touched[slot] : slot;
-    e.key = (u64)acc[j];
-    e.idx = r0 + j;
-    e.aux = 0;
-  }
-  __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const {  // unused (SURVIVORS_ONLY)
-    if (a.key != b.key) return a.key > b.key ? 1 : -1;
-    return 0;
-  }
-};
-
+// For top-N only a handful of scores per user matter, so this kernel works on approximations:
+//   1. sweep: a_j += (q >> s) | 1 with ONE fire-and-forget 32-bit atomic per entry.  s is the smallest shift that
+//      keeps every sum below 2^32, taken from a bound on the user's terms (sum over the history rows of the largest
+//      q of the row's segment).  Each term is within 1 of q / 2^s, so |a_j - score_j / 2^s| <= d (d = history
+//      length): a_x - a_y > 2d proves score_x > score_y.
+//   2. history items are zeroed, then two dense passes over the accumulators (16-byte loads, untouched vectors are
+//      skipped as a whole): a 2048-bin histogram finds the bin of the N-th largest sum, the second pass copies
+//      every item within 2d of that bin's lower edge to the survivor list and clears the accumulators.
+//   3. when the caller wants the lists only (no scores) and the survivors' sums are all more than 2d apart down to
+//      the (N+1)-th, their order is already proven: the sums themselves are written out.  Otherwise a second sweep
+//      over the rows adds the exact q of the survivors (two 20-bit limbs, native atomics) and they are ordered by
+//      their exact scores.
+// k_predict_merge orders the P per-range lists of a user; a user whose lists cannot be ordered with certainty
+// (approximate sums of different ranges too close) is scored again with exact sums.  4 bytes per slot let two CTAs
+// share an SM, so one CTA's latency-bound steps hide behind the other's atomics.  A user whose survivors do not fit
+// the list (huge groups of near-equal scores) is handed to the two-limb kernel.
 struct ExactOrder {
   __device__ __forceinline__ int cmp3(const Entry& a, const Entry& b) const {
     if (a.key != b.key) return a.key > b.key ? 1 : -1;
@@ -809,142 +909,189 @@ struct ExactOrder {
 
 struct Pred32Params {
   const int* indices;
-  const uint4* ent4;  // model rows in 4-entry blocks (two uint4 each)
-  const int2* blk;    // {first block, blocks} per (row, item range)
-  const int4* work_tab;
+  const u64* ent;        // model rows in 4-entry blocks, entries (q << 24) | column
+  const int4* blk;       // {first block, blocks, bound of q >> 20, 0} per (row, item range)
+  const int4* work_tab;  // {user, history length, row start lo, hi} in processing order
+  const int* n_work;     // non-null: number of work_tab records (device side), replaces U
   int U, P, R, I, N, mask;
-  int cap, direct_cap, tcap;
+  int exact;             // 1: exact scores for every list (scores requested / second pass over flagged users)
+  int cap;
   int* queue;
-  int* part_idx;
-  u64* part_sq;
-  int* part_len;
-  int* ovf_flag;   // per user: 1 = handed to the two-limb kernel
-  int* ovf_count;  // number of such users
-  int4* ovf_tab;   // their work records
+  int* part_idx;         // [U*P x N]
+  u64* part_key;         // exact sums; approximate sums where part_sft >= 0
+  int* part_len;         // [U*P]
+  int* part_sft;         // [U*P] -1: exact keys, s >= 0: keys are 32-bit sums of (q >> s) | 1
+  int* ovf_flag;         // per user: 1 = handed to the two-limb kernel
+  int* ovf_count;        // number of such users
+  int4* ovf_tab;         // their work records
   unsigned long long* prof;
 };
 
-constexpr int A32_BITS = 11;            // selection histogram of the 32-bit kernel: 2048 bins
+constexpr int A32_BITS = 10;            // selection histogram: 1024 bins
 constexpr int A32_BINS = 1 << A32_BITS;
-constexpr int A32_ROWS = 512;           // history rows staged per chunk (>= block size)
+constexpr int A32_ROWS = 512;           // history rows staged per chunk (= threads per CTA)
+constexpr int A32_NT = 512;
 
-// Row table of one chunk of the user's history: first block and number of blocks of every row's segment.
+// Row table of one chunk of the user's history: {first block, number of blocks} of every row's segment, and the
+// history item itself (for the history mask).
 struct RowTab {
-  int start[A32_ROWS];
-  int nb[A32_ROWS];
+  int2 seg[A32_ROWS];
+  int item[A32_ROWS];
 };
 
-// Stages rows [c0, c0 + n) of the history, one row per thread.
-__device__ __forceinline__ void stage_rows(const Pred32Params& p, int64_t xb, int c0, int n, int pass, RowTab* rt) {
-  const int tid = threadIdx.x;
-  if (tid < n) {
-    const int i = p.indices[xb + c0 + tid];
-    const int2 sb = __ldg(p.blk + (int64_t)i * p.P + pass);
-    rt->start[tid] = sb.x;
-    rt->nb[tid] = sb.y;
-  }
-  __syncthreads();
+// Histogram bin of a 32-bit sum: 32 bins per octave (bit pattern of the sum as a float, top 13 bits), so that bins
+// are ~2.2 % wide at every magnitude -- the bin of the N-th largest value holds few items whatever the scale of the
+// scores.
+__device__ __forceinline__ int a32_bin(unsigned a) {
+  const int b = (int)(__float_as_uint((float)a) >> 18) - (127 << 5);
+  return b > A32_BINS - 1 ? A32_BINS - 1 : b;
+}
+// A value that every sum of bin b and above certainly reaches: the lower edge of bin b - 1 (the float conversion
+// rounds by at most 2^-24, far less than a bin).
+__device__ __forceinline__ unsigned a32_bin_floor(int b) {
+  if (b <= 1) return 1u;
+  return (unsigned)__uint_as_float((unsigned)(b - 1 + (127 << 5)) << 18);
 }
 
-// Calls f(entry) for every entry of the staged segments (entries of neighbouring ranges and padding
-// included -- f drops them by their column).  One warp per row, a lane per entry, so that a load covers
-// 256 contiguous bytes; two rows (up to six loads per lane) are in flight before anything is added.
+// Loads of two history rows in flight: the first 96 entries of each (a row segment rarely has more).
+struct RowPair {
+  u64 e1[3], e2[3];
+};
+
+__device__ __forceinline__ void pair_load(RowPair& rp, const u64* __restrict__ ent, const RowTab* rt, int r, int n, int lane, int nwarps,
+                                          u64 idle) {
+  const int r2 = r + nwarps;
+  const int2 s1 = rt->seg[r];
+  const int2 s2 = r2 < n ? rt->seg[r2] : make_int2(0, 0);
+  const u64* b1 = ent + ((int64_t)s1.x << 2) + lane;
+  const u64* b2 = ent + ((int64_t)s2.x << 2) + lane;
+  const int n1 = (s1.y << 2) - lane, n2 = (s2.y << 2) - lane;  // entries left from this lane's first one
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    rp.e1[it] = 32 * it < n1 ? __ldg(b1 + 32 * it) : idle;
+    rp.e2[it] = 32 * it < n2 ? __ldg(b2 + 32 * it) : idle;
+  }
+}
+
 template <class F>
-__device__ __forceinline__ void sweep_rows(const Pred32Params& p, const RowTab* rt, int n, F f) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const u64* ent = reinterpret_cast<const u64*>(p.ent4);
-  for (int r = warp; r < n; r += 2 * nwarps) {
-    const int r2 = r + nwarps;
-    const u64* b1 = ent + (int64_t)rt->start[r] * 4 + lane;
-    const int n1 = rt->nb[r] * 4 - lane;  // entries left from this lane's first one
-    const u64* b2 = b1;
-    int n2 = 0;
-    if (r2 < n) {
-      b2 = ent + (int64_t)rt->start[r2] * 4 + lane;
-      n2 = rt->nb[r2] * 4 - lane;
-    }
-    u64 e1[3], e2[3];
+__device__ __forceinline__ void pair_apply(const RowPair& rp, F f) {
 #pragma unroll
-    for (int it = 0; it < 3; ++it) {
-      e1[it] = 32 * it < n1 ? __ldg(b1 + 32 * it) : ~0ull;
-      e2[it] = 32 * it < n2 ? __ldg(b2 + 32 * it) : ~0ull;
-    }
-#pragma unroll
-    for (int it = 0; it < 3; ++it) {
-      f(e1[it]);
-      f(e2[it]);
-    }
-    for (int e = 96; e < n1; e += 32) f(__ldg(b1 + e));
-    for (int e = 96; e < n2; e += 32) f(__ldg(b2 + e));
+  for (int it = 0; it < 3; ++it) {
+    f(rp.e1[it]);
+    f(rp.e2[it]);
   }
 }
 
-// Survivors of the approximate scores in one histogram round: 2048 bins over [0, kmax] (kmax = the largest
-// sum seen by sweep 1), the bin holding the K-th largest key found with two barriers, then every candidate
-// with key >= that bin's lower edge - margin is copied to the list.  Returns their number (unsorted), or -1
-// when they do not fit -- the caller then runs the general refinement.  `hist` must be all zero on entry and is
-// all zero again on return.
-__device__ int a32_select(const unsigned* acc, const int* touched, int n, int r0, unsigned kmax, u64 margin, int K,
-                          Entry* list, int cap, int direct_cap, int* hist, SelShared* sh) {
-  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
-  unsigned thr = 1u;
-  if (tid == 0) sh->count = 0;
-  if (n > direct_cap) {
-    const int bits = 32 - __clz(kmax | 1u);
-    const int shift = bits > A32_BITS ? bits - A32_BITS : 0;
-    for (int slot = tid; slot < n; slot += nt) {
-      const unsigned k = acc[touched ? touched[slot] : slot];
-      if (k) atomicAdd(&hist[min(k >> shift, (unsigned)(A32_BINS - 1))], 1);
-    }
-    __syncthreads();
-    const int per = (A32_BINS + nt - 1) / nt;
-    const int b0 = min(A32_BINS, tid * per), b1 = min(A32_BINS, b0 + per);
-    int tsum = 0;
-    for (int b = b0; b < b1; ++b) tsum += hist[b];
-    int incl = tsum;  // members of my bins and of the higher lanes' bins
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_down_sync(0xffffffffu, incl, o);
-      if (lane + o < 32) incl += t;
-    }
-    if (lane == 0) sh->warp_tot[warp] = incl;
-    if (tid == 0) sh->bstar = 0;  // fewer than K candidates: everything survives
-    __syncthreads();
-    int above = (lane > warp && lane < nwarps) ? sh->warp_tot[lane] : 0;  // totals of the higher warps
-    above = __reduce_add_sync(0xffffffffu, above) + incl - tsum;
-    if (above < K && above + tsum >= K) {
-      for (int b = b1 - 1; b >= b0; --b) {
-        above += hist[b];
-        if (above >= K) {
-          sh->bstar = b;
-          break;
-        }
-      }
-    }
-    __syncthreads();
-    for (int b = b0; b < b1; ++b) hist[b] = 0;
-    const u64 edge = (u64)sh->bstar << shift;
-    thr = edge > margin + 1ull ? (unsigned)(edge - margin) : 1u;
-  } else {
-    __syncthreads();
+// Calls f(entry) for every entry of the staged segments, padding included, and for `idle` in the places of a load
+// slot that a short segment leaves empty (idle = a padding entry: q = 0, a scratch slot of the lane's own).  One
+// warp per row, a lane per entry, so that a load covers 256 contiguous bytes.  Software pipeline: the loads of the
+// next two rows of the warp are issued before the entries of the current two are added, so that a warp always has
+// loads in flight.  Segments longer than 96 entries (rare: K / P entries on average) get their tail in a second loop.
+template <class F>
+__device__ __forceinline__ void sweep_rows(const u64* __restrict__ ent, const RowTab* rt, int n, u64 idle, F f) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int step = 2 * nwarps;
+  int r = warp;
+  if (r >= n) return;
+  RowPair A, B;
+  pair_load(A, ent, rt, r, n, lane, nwarps, idle);
+  for (;;) {
+    r += step;
+    const bool more_b = r < n;
+    if (more_b) pair_load(B, ent, rt, r, n, lane, nwarps, idle);
+    pair_apply(A, f);
+    if (!more_b) break;
+    r += step;
+    const bool more_a = r < n;
+    if (more_a) pair_load(A, ent, rt, r, n, lane, nwarps, idle);
+    pair_apply(B, f);
+    if (!more_a) break;
   }
-  for (int slot = tid; slot < n; slot += nt) {
-    const int j = touched ? touched[slot] : slot;
-    const unsigned k = acc[j];
-    if (k >= thr) {
-      const int pos = atomicAdd(&sh->count, 1);
-      if (pos < cap) {
-        Entry e;
-        e.key = (u64)k;
-        e.idx = r0 + j;
-        e.aux = 0;
-        list[pos] = e;
-      }
+  for (int q = warp; q < n; q += nwarps) {
+    const int2 sg = rt->seg[q];
+    if (sg.y > 24) {
+      const u64* b = ent + ((int64_t)sg.x << 2);
+      for (int e = 96 + lane; e < (sg.y << 2); e += 32) f(__ldg(b + e));
     }
+  }
+}
+
+// m <= 32 entries: warp w ranks entries w, w + nwarps, ... by (key desc, index asc) -- lane f holds opponent f, one
+// ballot counts the opponents that come first -- and writes them to their places in `dst`.  Barrier afterwards.
+__device__ __forceinline__ void rank_by_warps(const Entry* src, Entry* dst, int m) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  u64 kf = 0ull;
+  int jf = SENTINEL_IDX;
+  if (lane < m) {
+    kf = src[lane].key;
+    jf = src[lane].idx;
+  }
+  for (int i = warp; i < m; i += nwarps) {
+    const u64 ki = __shfl_sync(0xffffffffu, kf, i);
+    const int ji = __shfl_sync(0xffffffffu, jf, i);
+    const unsigned first = __ballot_sync(0xffffffffu, lane < m && (kf > ki || (kf == ki && jf < ji)));
+    if (lane == 0) {
+      Entry e;
+      e.key = ki;
+      e.idx = ji;
+      e.aux = 0;
+      dst[__popc(first)] = e;
+    }
+  }
+}
+
+// One warp: `sorted` holds m <= 32 entries best first.  Optionally checks that the first min(m - 1, N) neighbouring
+// keys are more than `margin` apart (the approximate sums then prove the order) and -- unless that check fails --
+// writes the first N places of the list.  Returns false when the check failed.
+__device__ __forceinline__ bool warp_check_write(const Entry* sorted, int m, int N, u64 margin, bool check, int* o_idx, u64* o_key) {
+  const int lane = threadIdx.x & 31;
+  if (check) {
+    const int pairs = (m - 1) < N ? (m - 1) : N;
+    bool bad = false;
+    for (int k = lane; k < pairs; k += 32) bad |= sorted[k].key - sorted[k + 1].key <= margin;
+    if (__any_sync(0xffffffffu, bad)) return false;
+  }
+  const int mo = m < N ? m : N;
+  for (int t = lane; t < N; t += 32) {
+    o_idx[t] = t < mo ? sorted[t].idx : -1;
+    o_key[t] = t < mo ? sorted[t].key : 0ull;
+  }
+  return true;
+}
+
+// Orders m entries best first by (key desc, index asc).  Up to SEL_RANK_MAX entries are ranked by counting
+// (nt / 64 threads per entry) from `src` into `other`; more are sorted in place.  Returns where the result is.
+__device__ __forceinline__ Entry* a32_sort(Entry* src, Entry* other, int m) {
+  ExactOrder ord;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (m <= SEL_RANK_MAX) {
+    const int tpe = nt / SEL_RANK_MAX, i = tid / tpe, part = tid % tpe;
+    int rank = 0;
+    Entry a;
+    a.key = 0;
+    a.idx = 0;
+    a.aux = 0;
+    if (i < m) {
+      a = src[i];
+      for (int f = part; f < m; f += tpe) rank += (f != i) && entry_before(ord, src[f], a);
+    }
+    for (int o = tpe >> 1; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (i < m && part == 0) other[rank] = a;
+    __syncthreads();
+    return other;
+  }
+  int n2 = 1;
+  while (n2 < m) n2 <<= 1;
+  for (int i = m + tid; i < n2; i += nt) {
+    Entry s;
+    s.key = 0;
+    s.idx = SENTINEL_IDX;
+    s.aux = 0;
+    src[i] = s;
   }
   __syncthreads();
-  const int m = sh->count;
-  return m > cap ? -1 : m;
+  bitonic_sort_entries(ord, src, n2);
+  return src;
 }
 
 #ifdef RPK_PHASE_PROF
@@ -954,44 +1101,123 @@ __device__ int a32_select(const unsigned* acc, const int* touched, int n, int r0
 #endif
 
 __host__ __device__ __forceinline__ size_t a32_fixed_bytes(int cap) {
-  return sel_smem_bytes(cap, A32_BINS) + ((sizeof(RowTab) + 15) / 16) * 16;
+  return sel_smem_bytes(cap, A32_BINS) + 2 * ((sizeof(RowTab) + 15) / 16) * 16;
 }
 
-__global__ void __launch_bounds__(512, 2) k_predict_a32(Pred32Params p) {
+// k-th work item of CTA `bid` of `G`: stripes of G items dealt forwards and backwards in turn.  The items are
+// sorted heaviest first, so every CTA gets the same mix; a static order (instead of a shared counter) lets a CTA
+// stage its next item while it still works on the current one.
+__device__ __forceinline__ int a32_work_index(int k, int bid, int G) {
+  return (k & 1) ? k * G + (G - 1 - bid) : k * G + bid;
+}
+
+__global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
   Entry* list = reinterpret_cast<Entry*>(smem);
+  Entry* list2 = list + p.cap;  // SEL_RANK_MAX entries
   int* hist = reinterpret_cast<int*>(smem + sel_list_bytes(p.cap));
   SelShared* sh = reinterpret_cast<SelShared*>(hist + A32_BINS);
-  RowTab* rt = reinterpret_cast<RowTab*>(smem + sel_smem_bytes(p.cap, A32_BINS));
+  RowTab* rtab = reinterpret_cast<RowTab*>(smem + sel_smem_bytes(p.cap, A32_BINS));
   unsigned* acc = reinterpret_cast<unsigned*>(smem + a32_fixed_bytes(p.cap));
-  int* touched = reinterpret_cast<int*>(acc + p.R);
-  __shared__ int s_work;
-  __shared__ int s_next;
-  __shared__ int s_ntouched;
-  __shared__ unsigned s_kmax;
+  __shared__ int s_flag;
+  __shared__ int4 s_rec[2];
+  __shared__ int s_w[2];
+  __shared__ u64 s_bsum[2];       // bound of the sums, in units of 2^20: rows beyond the first chunk ...
+  __shared__ unsigned s_bsum32[2];  // ... and the first chunk
 
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int total = p.U * p.P;
-  for (int s = tid; s < p.R; s += nt) acc[s] = 0u;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int total = (p.n_work ? *p.n_work : p.U) * p.P;
+  const int G = gridDim.x, bid = blockIdx.x;
+  if (a32_work_index(0, bid, G) >= total) return;
+  uint4* acc4 = reinterpret_cast<uint4*>(acc);
+  const int nvec = p.R >> 2;  // R is a multiple of 4
+  for (int v = tid; v < nvec; v += nt) acc4[v] = make_uint4(0u, 0u, 0u, 0u);
   for (int b = tid; b < A32_BINS; b += nt) hist[b] = 0;
-  if (tid == 0) s_next = atomicAdd(p.queue, 1);
+  if (tid == 0) {
+    const int w0 = a32_work_index(0, bid, G);
+    s_w[0] = w0;
+    s_rec[0] = p.work_tab[w0 / p.P];
+    s_bsum[0] = 0ull;
+    s_bsum[1] = 0ull;
+    s_bsum32[0] = 0u;
+    s_bsum32[1] = 0u;
+    s_flag = 0;
+    sh->count = 0;
+    sh->bstar = 0;
+  }
+  __syncthreads();
+  // ---- staging of a work item, in three parts so that its two dependent global loads (history item -> block
+  //      table entry) hide behind other work: part 1 issues the load of this thread's history item, part 2 the
+  //      load of that row's table entry, part 3 writes the row table and adds up the bound of the sums
+  int st_item = -1;
+  int4 st_blk = make_int4(0, 0, 0, 0);
+  auto stage1 = [&](int buf) {
+    st_item = -1;
+    if (s_w[buf] < total) {
+      const int4 rc = s_rec[buf];
+      const int64_t xb2 = ((int64_t)(unsigned)rc.z) | ((int64_t)rc.w << 32);
+      if (tid < rc.y) st_item = p.indices[xb2 + tid];
+    }
+  };
+  auto stage2 = [&](int buf) {
+    st_blk = make_int4(0, 0, 0, 0);
+    if (st_item >= 0) st_blk = __ldg(p.blk + (int64_t)st_item * p.P + (s_w[buf] % p.P));
+  };
+  auto stage3 = [&](int buf) {
+    if (s_w[buf] >= total) return;
+    const int4 rc = s_rec[buf];
+    const int d2 = rc.y, pass2 = s_w[buf] % p.P;
+    const int64_t xb2 = ((int64_t)(unsigned)rc.z) | ((int64_t)rc.w << 32);
+    RowTab* rt2 = rtab + buf;
+    unsigned b32 = 0;  // first chunk: at most 512 terms of at most 2^20 each
+    if (tid < d2) {
+      rt2->seg[tid] = make_int2(st_blk.x, st_blk.y);
+      rt2->item[tid] = st_item;
+      b32 = (unsigned)st_blk.z;
+    }
+    b32 = __reduce_add_sync(0xffffffffu, b32);
+    if (lane == 0 && b32) atomicAdd(&s_bsum32[buf], b32);
+    if (d2 > nt) {  // long histories: the rows beyond the first chunk only add to the bound
+      u64 bsum = 0;
+      for (int r = tid + nt; r < d2; r += nt) bsum += (u64)(unsigned)__ldg(p.blk + (int64_t)p.indices[xb2 + r] * p.P + pass2).z;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+      if (lane == 0 && bsum) atomicAdd(&s_bsum[buf], bsum);
+    }
+  };
+  stage1(0);
+  stage2(0);
+  stage3(0);
+  __syncthreads();
 #ifdef RPK_PHASE_PROF
   long long t_prev = clock64();
 #endif
-  for (;;) {
-    if (tid == 0) {
-      s_work = s_next;
-      const int nx = atomicAdd(p.queue, 1);
-      s_next = nx;
-      if (nx < total) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.work_tab + nx / p.P) : "memory");
-      s_ntouched = 0;
-      s_kmax = 0u;
-    }
-    __syncthreads();
-    const int w = s_work;
-    __syncthreads();
+  for (int k = 0;; ++k) {
+    const int cur = k & 1, nxt = cur ^ 1;
+    const int w = s_w[cur];
     if (w >= total) break;
-    const int4 rec = p.work_tab[w / p.P];
+    const int4 rec = s_rec[cur];
+    const RowTab* rt = rtab + cur;
+    // the next work item: its record is copied into shared memory asynchronously while this item is swept; the
+    // per-item scratch is reset here too (every thread has left the previous item, nobody reads these before the
+    // barrier after the sweep)
+    if (tid == 0) {
+      int w_n = a32_work_index(k + 1, bid, G);
+      if (w_n < total) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_rec[nxt])),
+                     "l"(p.work_tab + w_n / p.P)
+                     : "memory");
+      } else {
+        w_n = total;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      s_w[nxt] = w_n;
+      s_bsum[nxt] = 0ull;
+      s_bsum32[nxt] = 0u;
+      s_flag = 0;
+      sh->count = 0;
+      sh->bstar = 0;
+    }
     const int u = rec.x;
     const int pass = w % p.P;
     const int r0 = pass * p.R;
@@ -999,108 +1225,252 @@ __global__ void __launch_bounds__(512, 2) k_predict_a32(Pred32Params p) {
     const int64_t xb = ((int64_t)(unsigned)rec.z) | ((int64_t)rec.w << 32);
     const int d = rec.y;
     const int64_t slot_out = (int64_t)u * p.P + pass;
+    int* o_idx = p.part_idx + slot_out * p.N;
+    u64* o_key = p.part_key + slot_out * p.N;
     PROF32_MARK(0);
+    // ---- shift of the 32-bit sums from the bound staged with the item
+    // B = b20 * 2^20 >= sum over the rows of their largest q; the smallest shift with (B >> sft) + d < 2^32
+    const u64 b20 = s_bsum[cur] + (u64)s_bsum32[cur];  // < 2^45 (d < 2^24 rows of at most 2^20 each)
+    int sft = 0;
+    {
+      const u64 room = 0xffffffffull - (u64)d;
+      auto fits = [&](int sf) { return sf >= 20 ? (b20 >> (sf - 20)) <= room : b20 <= (room >> (20 - sf)); };
+      if (!fits(0)) {
+        sft = 64 - __clzll((long long)b20) - 12;  // bits(B) - 32
+        sft = sft < 1 ? 1 : sft;
+        while (!fits(sft)) ++sft;
+      }
+    }
+    const int sh_a = 24 + sft;
+    const unsigned margin = 2u * (unsigned)d;
+    const u64 idle = (u64)(unsigned)(p.R + lane);
+    // ---- sweep 1: approximate sums, one fire-and-forget atomic per entry
+    if (d > 0) {
+      RowTab* rtw = rtab + cur;
+      for (int c0 = 0; c0 < d; c0 += A32_ROWS) {
+        const int n = min(A32_ROWS, d - c0);
+        if (c0 > 0) {
+          __syncthreads();  // the previous chunk's table is still being read
+          for (int r = tid; r < n; r += nt) {
+            const int i = p.indices[xb + c0 + r];
+            const int4 b = __ldg(p.blk + (int64_t)i * p.P + pass);
+            rtw->seg[r] = make_int2(b.x, b.y);
+            rtw->item[r] = i;
+          }
+          __syncthreads();
+        }
+        // no test per entry: real entries carry their slot, padding lands in the scratch slots behind the range
+        sweep_rows(p.ent, rt, n, idle, [&](u64 e) { atomicAdd(&acc[(unsigned)e & 0xffffffu], (unsigned)(e >> sh_a) | 1u); });
+      }
+    }
+    if (tid == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");  // the next item's record has landed
+    __syncthreads();
+    PROF32_MARK(1);
+    stage1(nxt);
     if (d == 0) {  // user without history: empty prediction row (algorithms/base.py:123-127)
       for (int t = tid; t < p.N; t += nt) {
-        p.part_idx[slot_out * p.N + t] = -1;
-        p.part_sq[slot_out * p.N + t] = 0;
+        o_idx[t] = -1;
+        o_key[t] = 0;
       }
-      if (tid == 0) p.part_len[slot_out] = 0;
+      if (tid == 0) {
+        p.part_len[slot_out] = 0;
+        p.part_sft[slot_out] = -1;
+      }
+      stage2(nxt);
+      stage3(nxt);
+      __syncthreads();
       continue;
     }
-    const int sft = 9 + (d > 1 ? 32 - __clz(d - 1) : 0);
-    const int rows_per_chunk = min(nt, A32_ROWS);
-    // ---- sweep 1: approximate scores, slots recorded on their first touch (a sum is never zero again)
-    unsigned mx = 0u;  // largest sum this thread produced
-    for (int c0 = 0; c0 < d; c0 += rows_per_chunk) {
-      const int n = min(rows_per_chunk, d - c0);
-      if (c0 > 0) __syncthreads();  // the previous chunk's table is still being read
-      stage_rows(p, xb, c0, n, pass, rt);
-      sweep_rows(p, rt, n, [&](u64 e) {
-        const unsigned j = (unsigned)(e >> 40) - (unsigned)r0;
-        if (j < (unsigned)ns) {
-          const unsigned a = (unsigned)((e & Q_MASK40) >> sft) | 1u;
-          const unsigned old = atomicAdd(&acc[j], a);
-          mx = max(mx, old + a);
-          if (old == 0u) {
-            const int pos = atomicAdd(&s_ntouched, 1);
-            if (pos < p.tcap) touched[pos] = (int)j;
-          }
-        }
-      });
-    }
-    mx = __reduce_max_sync(0xffffffffu, mx);
-    if ((tid & 31) == 0 && mx) atomicMax(&s_kmax, mx);
-    __syncthreads();
-    const int n_touched = s_ntouched;
-    const bool sparse = n_touched <= p.tcap;
-    PROF32_MARK(1);
-#ifdef RPK_PHASE_PROF
-    if (tid == 0) {
-      atomicAdd(p.prof + 8, 1ull);
-      atomicAdd(p.prof + 9, (unsigned long long)sparse);
-      atomicAdd(p.prof + 10, (unsigned long long)n_touched);
-    }
-#endif
     if (p.mask) {  // pipelines/pipeline.py:174-175 -- before the truncation to N
-      for (int r = tid; r < d; r += nt) {
-        const int j = p.indices[xb + r] - r0;
-        if (j >= 0 && j < ns) acc[j] = 0u;
+      if (d <= A32_ROWS) {
+        if (tid < d) {
+          const int j = rt->item[tid] - r0;
+          if (j >= 0 && j < ns) acc[j] = 0u;
+        }
+      } else {
+        for (int r = tid; r < d; r += nt) {
+          const int j = p.indices[xb + r] - r0;
+          if (j >= 0 && j < ns) acc[j] = 0u;
+        }
       }
       __syncthreads();
     }
     PROF32_MARK(2);
-    ApproxSrc src{acc, sparse ? touched : nullptr, r0, sparse ? n_touched : ns, 0ull, 2ull * (u64)d,
-                  (u64)d * ((1ull << (40 - sft)) + 1ull)};
-    int m = a32_select(acc, src.touched, src.ns, r0, s_kmax, src.margin_, p.N, list, p.cap, p.direct_cap, hist, sh);
-    if (m < 0) {  // a crowded boundary bin: general refinement
-      __syncthreads();
-      m = block_select_topk<true, A32_BITS>(src, p.N, list, p.cap, p.direct_cap, hist, sh);
-      for (int b = tid; b < A32_BINS; b += nt) hist[b] = 0;
+    // ---- survivors.  A dense pass costs a warp its full instruction stream whenever any of its lanes has work, so
+    //      the per-item work is kept out of it: every thread takes the maximum of its own slots (no branches, no
+    //      atomics), and the N-th largest of these per-thread maxima -- found with one histogram entry per thread,
+    //      64 bins per octave -- is a lower bound of the N-th largest sum (N distinct items reach it).  Everything
+    //      within the margin below that bin survives.
+    unsigned mymax = 0u;
+    for (int v = tid; v < nvec; v += nt) {
+      const uint4 x = acc4[v];
+      mymax = max(mymax, max(max(x.x, x.y), max(x.z, x.w)));
     }
+    // N-th largest of the 512 per-thread maxima, in two rounds of a 32-bin histogram (octave, then 32 bins inside
+    // the octave).  Every warp scans the 32 bins by itself (one bin per lane), so no warp waits for another one
+    // beyond the two barriers.
+    const int mybin = mymax ? a32_bin(mymax) : -1;  // (octave << 5) | bin inside the octave
+    if (mybin >= 0) atomicAdd(&hist[mybin >> 5], 1);
+    __syncthreads();
+    PROF32_MARK(12);
+    stage2(nxt);
+    int bstar = 0;
+    {
+      const int h1 = hist[lane];
+      int incl = h1;  // maxima in my octave and the higher ones
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += t;
+      }
+      const unsigned hit = __ballot_sync(0xffffffffu, incl >= p.N);  // lanes whose octave-and-above hold N maxima
+      if (hit) {
+        const int oct = 31 - __clz(hit);  // the highest such octave holds the N-th largest
+        const int above = __shfl_sync(0xffffffffu, incl - h1, oct);
+        if (mybin >= 0 && (mybin >> 5) == oct) atomicAdd(&hist[32 + (mybin & 31)], 1);
+        __syncthreads();
+        const int h2 = hist[32 + lane];
+        int incl2 = h2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_down_sync(0xffffffffu, incl2, o);
+          if (lane + o < 32) incl2 += t;
+        }
+        const unsigned hit2 = __ballot_sync(0xffffffffu, above + incl2 >= p.N);
+        bstar = (oct << 5) | (hit2 ? 31 - __clz(hit2) : 0);
+      } else {
+        __syncthreads();  // fewer than N non-empty threads: everything survives (bstar = 0)
+      }
+    }
+    __syncthreads();  // every warp has read both histograms
+    if (mybin >= 0) {
+      hist[mybin >> 5] = 0;
+      hist[32 + (mybin & 31)] = 0;
+    }
+    const unsigned edge = a32_bin_floor(bstar);
+    const unsigned thr = edge > margin + 1u ? edge - margin : 1u;
+    PROF32_MARK(13);
+    // copy the survivors, clear the accumulators: one compare per vector, the rest only for the few that pass
+    for (int v = tid; v < nvec; v += nt) {
+      const uint4 x = acc4[v];
+      acc4[v] = make_uint4(0u, 0u, 0u, 0u);
+      if (max(max(x.x, x.y), max(x.z, x.w)) < thr) continue;
+      const unsigned xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (xs[q] >= thr) {
+          const int pos = atomicAdd(&sh->count, 1);
+          if (pos < p.cap) {
+            Entry e;
+            e.key = (u64)xs[q];
+            e.idx = r0 + 4 * v + q;
+            e.aux = 0;
+            list[pos] = e;
+          }
+        }
+    }
+    PROF32_MARK(14);
+    stage3(nxt);
+    __syncthreads();
+    const int m = sh->count;
     PROF32_MARK(3);
 #ifdef RPK_PHASE_PROF
-    if (tid == 0) atomicAdd(p.prof + 11, (unsigned long long)(m < 0 ? 0 : m));
-#endif
-    // ---- restore the all-zero invariant
-    if (sparse) {
-      for (int t = tid; t < n_touched; t += nt) acc[touched[t]] = 0u;
-    } else {
-      for (int s = tid; s < ns; s += nt) acc[s] = 0u;
+    if (tid == 0) {
+      atomicAdd(p.prof + 8, 1ull);
+      atomicAdd(p.prof + 11, (unsigned long long)(m > p.cap ? 0 : m));
     }
-    if (m < 0) {  // survivors do not fit: the exact kernel takes the whole user
+#endif
+    if (m > p.cap) {  // survivors do not fit: the exact kernel takes the whole user
       if (tid == 0 && atomicExch(&p.ovf_flag[u], 1) == 0) p.ovf_tab[atomicAdd(p.ovf_count, 1)] = rec;
       __syncthreads();
       continue;
     }
-    __syncthreads();
+    const int mo = m < p.N ? m : p.N;
+    bool need_exact = p.exact != 0;
+    Entry* surv = list;  // where the survivors are
+    if (!need_exact) {
+      // is the order of the N best (and their separation from the rest) proven by the approximate sums alone?
+      if (m <= 32) {
+        // the usual case: every warp ranks two survivors (a lane per opponent), then one warp checks the gaps and
+        // writes the list
+        rank_by_warps(list, list2, m);
+        __syncthreads();
+        if (warp == 0) {
+          const bool sure = warp_check_write(list2, m, p.N, (u64)margin, true, o_idx, o_key);
+          if (lane == 0) {
+            if (sure) {
+              p.part_len[slot_out] = mo;
+              p.part_sft[slot_out] = sft;
+            } else {
+              s_flag = 1;
+            }
+          }
+        }
+        __syncthreads();
+        need_exact = s_flag != 0;
+        if (!need_exact) {
+          PROF32_MARK(6);
+          continue;
+        }
+      } else {
+        surv = a32_sort(list, list2, m);
+        const int pairs = (m - 1) < p.N ? (m - 1) : p.N;
+        for (int kk = tid; kk < pairs; kk += nt)
+          if (surv[kk].key - surv[kk + 1].key <= (u64)margin) s_flag = 1;
+        __syncthreads();
+        need_exact = s_flag != 0;
+        if (!need_exact) {
+          for (int t = tid; t < p.N; t += nt) {
+            o_idx[t] = t < mo ? surv[t].idx : -1;
+            o_key[t] = t < mo ? surv[t].key : 0ull;
+          }
+          if (tid == 0) {
+            p.part_len[slot_out] = mo;
+            p.part_sft[slot_out] = sft;
+          }
+          __syncthreads();
+          PROF32_MARK(6);
+          continue;
+        }
+      }
+    }
+#ifdef RPK_PHASE_PROF
+    if (tid == 0) atomicAdd(p.prof + 9, 1ull);
+#endif
     // ---- sweep 2: exact scores of the survivors (slot -> survivor number + 1, key -> exact sum)
     for (int t = tid; t < m; t += nt) {
-      acc[list[t].idx - r0] = (unsigned)t + 1u;
-      list[t].key = 0ull;
+      acc[surv[t].idx - r0] = (unsigned)t + 1u;
+      surv[t].key = 0ull;
     }
     __syncthreads();
     PROF32_MARK(4);
     const bool limbs = d <= LIMB_CHUNK;  // two 32-bit adds (20-bit limbs) cannot overflow
     if (m > 0) {
-      for (int c0 = 0; c0 < d; c0 += rows_per_chunk) {
-        const int n = min(rows_per_chunk, d - c0);
-        if (d > rows_per_chunk) {  // a single chunk is still staged from sweep 1
+      RowTab* rtw = rtab + cur;
+      for (int c0 = 0; c0 < d; c0 += A32_ROWS) {
+        const int n = min(A32_ROWS, d - c0);
+        if (d > A32_ROWS) {  // a single chunk is still staged from sweep 1
           if (c0 > 0) __syncthreads();
-          stage_rows(p, xb, c0, n, pass, rt);
+          for (int r = tid; r < n; r += nt) {
+            const int i = p.indices[xb + c0 + r];
+            const int4 b = __ldg(p.blk + (int64_t)i * p.P + pass);
+            rtw->seg[r] = make_int2(b.x, b.y);
+            rtw->item[r] = i;
+          }
+          __syncthreads();
         }
-        sweep_rows(p, rt, n, [&](u64 e) {
-          const unsigned j = (unsigned)(e >> 40) - (unsigned)r0;
+        sweep_rows(p.ent, rt, n, idle, [&](u64 e) {
+          const unsigned j = (unsigned)e & 0xffffffu;
           if (j < (unsigned)ns) {
             const unsigned cn = acc[j];
             if (cn) {
-              const u64 q = e & Q_MASK40;
+              const u64 q = e >> 24;
               if (limbs) {
-                unsigned* wd = reinterpret_cast<unsigned*>(&list[cn - 1u].key);
+                unsigned* wd = reinterpret_cast<unsigned*>(&surv[cn - 1u].key);
                 atomicAdd(wd, (unsigned)q & LIMB_MASK);
                 atomicAdd(wd + 1, (unsigned)(q >> LIMB_BITS));
               } else {
-                atomicAdd(&list[cn - 1u].key, q);
+                atomicAdd(&surv[cn - 1u].key, q);
               }
             }
           }
@@ -1110,70 +1480,50 @@ __global__ void __launch_bounds__(512, 2) k_predict_a32(Pred32Params p) {
     }
     PROF32_MARK(5);
     for (int t = tid; t < m; t += nt) {
-      acc[list[t].idx - r0] = 0u;
+      acc[surv[t].idx - r0] = 0u;
       if (limbs) {
-        const u64 kv = list[t].key;
-        list[t].key = ((kv >> 32) << LIMB_BITS) + (kv & 0xffffffffull);
+        const u64 kv = surv[t].key;
+        surv[t].key = ((kv >> 32) << LIMB_BITS) + (kv & 0xffffffffull);
       }
     }
     __syncthreads();
-    ExactOrder ord;
-    const int mo = m < p.N ? m : p.N;
-    if (m <= SEL_RANK_MAX) {
-      // rank every survivor by counting the ones that precede it (nt / 64 threads per survivor) and write
-      // it straight to its place
-      const int tpe = nt / SEL_RANK_MAX, i = tid / tpe, part = tid % tpe;
-      int rank = 0;
-      Entry a;
-      a.key = 0;
-      a.idx = 0;
-      if (i < m) {
-        a = list[i];
-        for (int f = part; f < m; f += tpe) rank += (f != i) && entry_before(ord, list[f], a);
-      }
-      for (int o = tpe >> 1; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
-      if (i < m && part == 0 && rank < p.N) {
-        p.part_idx[slot_out * p.N + rank] = a.idx;
-        p.part_sq[slot_out * p.N + rank] = a.key;
-      }
-    } else {
-      int n2 = 1;
-      while (n2 < m) n2 <<= 1;
-      for (int i = m + tid; i < n2; i += nt) {
-        Entry s;
-        s.key = 0;
-        s.idx = SENTINEL_IDX;
-        s.aux = 0;
-        list[i] = s;
-      }
+    if (m <= 32) {
+      Entry* other = surv == list ? list2 : list;
+      rank_by_warps(surv, other, m);
       __syncthreads();
-      bitonic_sort_entries(ord, list, n2);
-      for (int t = tid; t < mo; t += nt) {
-        p.part_idx[slot_out * p.N + t] = list[t].idx;
-        p.part_sq[slot_out * p.N + t] = list[t].key;
+      if (warp == 0) warp_check_write(other, m, p.N, 0ull, false, o_idx, o_key);
+    } else {
+      const Entry* fin = a32_sort(surv, surv == list ? list2 : list, m);
+      for (int t = tid; t < p.N; t += nt) {
+        o_idx[t] = t < mo ? fin[t].idx : -1;
+        o_key[t] = t < mo ? fin[t].key : 0ull;
       }
     }
-    for (int t = mo + tid; t < p.N; t += nt) {
-      p.part_idx[slot_out * p.N + t] = -1;
-      p.part_sq[slot_out * p.N + t] = 0ull;
+    if (tid == 0) {
+      p.part_len[slot_out] = mo;
+      p.part_sft[slot_out] = -1;
     }
-    if (tid == 0) p.part_len[slot_out] = mo;
     __syncthreads();
     PROF32_MARK(6);
   }
 }
 
-// One warp per user: merge the P per-range lists (each best-first) into the final top-N.
-// Users flagged in `alt_flag` take their lists from the second set (the exact kernel's, alt_P ranges).
+// One warp per user: merge the P per-range lists (each best-first, exact keys) into the final top-N.
+// Users flagged in `alt_flag` take their lists from the second set (the two-limb kernel's, alt_P ranges).
+// only_a / only_b non-null: only users flagged in either are processed (second pass).
 __global__ void k_predict_finalize(const int* __restrict__ part_idx, const u64* __restrict__ part_sq,
                                    const int* __restrict__ part_len, int64_t U, int P, int N, int* __restrict__ out_idx,
                                    double* __restrict__ out_val, int* __restrict__ out_len,
                                    const int* __restrict__ alt_flag, const int* __restrict__ alt_idx,
-                                   const u64* __restrict__ alt_sq, const int* __restrict__ alt_len, int alt_P) {
+                                   const u64* __restrict__ alt_sq, const int* __restrict__ alt_len, int alt_P,
+                                   const int* __restrict__ only_a, const int* __restrict__ only_b,
+                                   const ModelScale* __restrict__ scale) {
   const int lane = threadIdx.x & 31;
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const double inv = scale->inv;
   for (int64_t u = warp; u < U; u += nwarps) {
+    if ((only_a || only_b) && !((only_a && only_a[u]) || (only_b && only_b[u]))) continue;
     const bool alt = alt_flag && alt_flag[u];
     const int Pu = alt ? alt_P : P;
     const int PN = Pu * N;
@@ -1196,13 +1546,99 @@ __global__ void k_predict_finalize(const int* __restrict__ part_idx, const u64* 
       }
       if (rank < N) {
         out_idx[u * N + rank] = je;
-        if (out_val) out_val[u * N + rank] = (double)se * (1.0 / 549755813888.0);
+        if (out_val) out_val[u * N + rank] = (double)se * inv;
       }
     }
     for (int t = m + lane; t < N; t += 32) {
       out_idx[u * N + t] = -1;
       if (out_val) out_val[u * N + t] = 0.0;
     }
+    if (lane == 0) out_len[u] = m;
+  }
+}
+
+// Lists-only mode: the P per-range lists of a user carry exact sums (part_sft < 0) or approximate ones
+// (sums of (q >> s) | 1, part_sft = s).  Every key is an interval of the exact score:
+//   exact:        [E, E]
+//   approximate:  [(a - d) * 2^s, (a + d) * 2^s]        (|a - E / 2^s| <= d, d = history length)
+// One warp per user orders the (at most MERGE_MAX) entries by their upper ends and checks that down to the
+// (N+1)-th every entry's interval lies strictly above the next one's (equal exact scores: ascending index).  Then
+// the order is the exact order and the list is written; otherwise the user is queued for a second, exact pass.
+constexpr int MERGE_MAX = 256;
+constexpr int MERGE_WARPS = 4;
+__global__ void __launch_bounds__(32 * MERGE_WARPS) k_predict_merge(const int* __restrict__ part_idx, const u64* __restrict__ part_key,
+                                                                   const int* __restrict__ part_len, const int* __restrict__ part_sft,
+                                                                   const int64_t* __restrict__ indptr, int64_t U, int P, int N,
+                                                                   int* __restrict__ out_idx, int* __restrict__ out_len,
+                                                                   const int* __restrict__ ovf_flag, int* __restrict__ redo_flag,
+                                                                   int* __restrict__ redo_count, int4* __restrict__ redo_tab) {
+  __shared__ u64 s_lo[MERGE_WARPS][MERGE_MAX], s_hi[MERGE_WARPS][MERGE_MAX];
+  __shared__ int s_ix[MERGE_WARPS][MERGE_MAX];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  u64* lo = s_lo[wib];
+  u64* hi = s_hi[wib];
+  int* ix = s_ix[wib];
+  int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int PN = P * N;
+  for (int64_t u = warp; u < U; u += nwarps) {
+    if (ovf_flag[u]) continue;  // the two-limb kernel produces this user's lists
+    const int64_t xb = indptr[u];
+    const u64 d = (u64)(indptr[u + 1] - xb);
+    int tot = 0;
+    for (int q = 0; q < P; ++q) tot += part_len[u * P + q];
+    // every lane ranks its own entries against all of them (read straight from global memory: PN is small)
+    __syncwarp();
+    for (int e = lane; e < PN; e += 32) {
+      const int q = e / N, t = e - q * N;
+      if (t >= part_len[u * P + q]) continue;
+      const int sf = part_sft[u * P + q];
+      const u64 k = part_key[u * PN + e];
+      u64 l, h;
+      if (sf < 0) {
+        l = h = k;
+      } else {
+        l = (k > d ? k - d : 0ull) << sf;
+        h = (k + d) > (~0ull >> sf) ? ~0ull : (k + d) << sf;
+      }
+      const int je = part_idx[u * PN + e];
+      int rank = 0;
+      for (int f = 0; f < PN; ++f) {
+        const int qf = f / N, tf = f - qf * N;
+        if (tf >= part_len[u * P + qf]) continue;
+        const int sff = part_sft[u * P + qf];
+        const u64 kf = part_key[u * PN + f];
+        u64 lf, hf;
+        if (sff < 0) {
+          lf = hf = kf;
+        } else {
+          lf = (kf > d ? kf - d : 0ull) << sff;
+          hf = (kf + d) > (~0ull >> sff) ? ~0ull : (kf + d) << sff;
+        }
+        const int jf = part_idx[u * PN + f];
+        rank += (hf > h) || (hf == h && (lf > l || (lf == l && jf < je)));
+      }
+      lo[rank] = l;
+      hi[rank] = h;
+      ix[rank] = je;
+    }
+    __syncwarp();
+    const int m = min(N, tot);
+    const int pairs = min(tot - 1, N);
+    bool bad = false;
+    for (int k = lane; k < pairs; k += 32) {
+      const bool exact_pair = lo[k] == hi[k] && lo[k + 1] == hi[k + 1];
+      const bool ok = lo[k] > hi[k + 1] || (exact_pair && (hi[k] > hi[k + 1] || ix[k] < ix[k + 1]));
+      bad |= !ok;
+    }
+    if (__any_sync(0xffffffffu, bad)) {
+      if (lane == 0) {
+        redo_flag[u] = 1;
+        redo_tab[atomicAdd(redo_count, 1)] = make_int4((int)u, (int)d, (int)(xb & 0xffffffffll), (int)(xb >> 32));
+      }
+      continue;
+    }
+    for (int t = lane; t < N; t += 32) out_idx[u * N + t] = t < m ? ix[t] : -1;
     if (lane == 0) out_len[u] = m;
   }
 }
@@ -1296,30 +1732,32 @@ static void ensure_segments(rpk_ctx* c, const PredGeom& g) {
   c->m_R = g.R;
 }
 
-// Padded block layout of the model (once per model) and the block table of a geometry.
+// Block layout of the model for one geometry of the 32-bit kernel (rebuilt when the model or the geometry changes).
 static void ensure_blocks(rpk_ctx* c, int P, int R) {
+  if (c->m_pad && c->m_P2 == P && c->m_R2 == R) return;
   const int64_t I = c->m_I;
   cudaStream_t st = c->stream;
   const int64_t* m_ptr = c->get<int64_t>("m_ptr");
   const u64* m_ent = c->get<u64>("m_ent");
-  if (!c->m_pad) {
-    int* len4 = c->buf<int>("m_len4", (size_t)I);
-    int64_t* ptr4 = c->buf<int64_t>("m_ptr4", (size_t)I + 1);
-    k_model_pad_len<<<ceil_div(I, 256), 256, 0, st>>>(m_ptr, I, len4);
+  const int64_t nseg = I * P;
+  int2* seg = c->buf<int2>("m_seg2", (size_t)nseg);
+  int* len4 = c->buf<int>("m_len4", (size_t)nseg);
+  int64_t* ptr4 = c->buf<int64_t>("m_ptr4", (size_t)nseg + 1);
+  int4* blk = c->buf<int4>("m_blk", (size_t)nseg);
+  // every segment is padded by at most 3 entries
+  u64* ent4 = c->buf<u64>("m_ent4", (size_t)c->m_nnz + 3 * (size_t)nseg + 4);
+  if (nseg > 0) {
+    k_model_seg_len<<<ceil_div(nseg, 256), 256, 0, st>>>(m_ptr, m_ent, I, P, R, seg, len4);
     RPK_LAUNCH_CHECK(c);
-    k_scan_i32_i64<<<1, 1024, 0, st>>>(len4, ptr4, I);
-    RPK_LAUNCH_CHECK(c);
-    // rows are padded by at most 3 entries each
-    u64* ent4 = c->buf<u64>("m_ent4", (size_t)c->m_nnz + 3 * (size_t)I + 4);
-    k_model_pad<<<(int)std::min<int64_t>(ceil_div(I * 32, 256), (int64_t)c->sm_count * 32), 256, 0, st>>>(m_ptr, m_ent, ptr4, I, ent4);
-    RPK_LAUNCH_CHECK(c);
-    c->m_pad = true;
-    c->m_P2 = 0;
   }
-  if (c->m_P2 == P && c->m_R2 == R) return;
-  int2* blk = c->buf<int2>("m_blk", (size_t)I * P);
-  k_model_blocks<<<ceil_div(I * P, 256), 256, 0, st>>>(m_ptr, m_ent, c->get<int64_t>("m_ptr4"), I, P, R, blk);
+  k_scan_i32_i64<<<1, 1024, 0, st>>>(len4, ptr4, nseg);
   RPK_LAUNCH_CHECK(c);
+  if (nseg > 0) {
+    k_model_pad<<<(int)std::min<int64_t>(ceil_div(nseg * 32, 256), (int64_t)c->sm_count * 32), 256, 0, st>>>(m_ptr, m_ent, seg, ptr4, I, P, R,
+                                                                                                          ent4, blk);
+    RPK_LAUNCH_CHECK(c);
+  }
+  c->m_pad = true;
   c->m_P2 = P;
   c->m_R2 = R;
 }
@@ -1327,7 +1765,7 @@ static void ensure_blocks(rpk_ctx* c, int P, int R) {
 // Geometry of the 32-bit kernel: two CTAs per SM when that costs at most one more item range than one CTA
 // per SM would need (or at most three ranges), else one.
 struct Pred32Geom {
-  int cap, direct_cap, P, R, nt, tcap, ctas;
+  int cap, P, R, nt, ctas;
   size_t smem;
 };
 
@@ -1335,27 +1773,23 @@ static Pred32Geom predict32_geometry(rpk_ctx* c, int N) {
   Pred32Geom g;
   const bool tiny = c->flags & DBG_TINY_LIST;
   g.cap = std::max(tiny ? 64 : 256, next_pow2(2 * std::max(N, 1)));
-  g.direct_cap = tiny ? std::max(N, 1) : std::min(g.cap, std::max(64, 2 * N));
   const size_t fixed = a32_fixed_bytes(g.cap);
   const int64_t I = c->m_I;
-  auto solve = [&](int ctas, int& P, int64_t& R, int64_t& T) -> bool {
+  auto solve = [&](int ctas, int& P, int64_t& R) -> bool {
     const size_t per_cta = std::min<size_t>((size_t)c->smem_max, (size_t)c->smem_per_sm / ctas - 1024);
     if (per_cta < fixed + 1024 + 4096) return false;
     const size_t avail = per_cta - fixed - 256;
     for (P = 1;; ++P) {
       R = ((I + P - 1) / P + 3) & ~(int64_t)3;
       if (R < 4) R = 4;
-      // touched-slot list: what is left after the accumulators, at least 2048 slots (or all of them)
-      const int64_t left = ((int64_t)avail - R * 4) / 4;
-      T = std::min<int64_t>(R, tiny ? 48 : std::min<int64_t>(left, 8192));
-      if (left >= std::min<int64_t>(R, tiny ? 48 : 2048)) return true;
+      if ((size_t)R * 4 + 128 <= avail) return true;  // + 32 scratch slots for padding entries
       if (R <= 4) return false;
     }
   };
   int P1 = 0, P2 = 0;
-  int64_t R1 = 0, T1 = 0, R2 = 0, T2 = 0;
-  const bool ok1 = solve(1, P1, R1, T1);
-  const bool ok2 = solve(2, P2, R2, T2);
+  int64_t R1 = 0, R2 = 0;
+  const bool ok1 = solve(1, P1, R1);
+  const bool ok2 = solve(2, P2, R2);
   RPK_REQUIRE(ok1, "N too large for shared memory");
   bool two = ok2 && (P2 <= 3 || P2 <= P1 + 1);
   if (const char* e = getenv("RPK_PRED_CTAS")) {  // tuning hook
@@ -1365,21 +1799,14 @@ static Pred32Geom predict32_geometry(rpk_ctx* c, int N) {
   }
   g.ctas = two ? 2 : 1;
   g.P = two ? P2 : P1;
-  int64_t R = two ? R2 : R1, T = two ? T2 : T1;
+  int64_t R = two ? R2 : R1;
   if ((c->flags & DBG_MULTI_PASS) && g.P < 2 && I >= 8) {
     g.P = 2;
     R = ((I + g.P - 1) / g.P + 3) & ~(int64_t)3;
-    T = std::min<int64_t>(R, tiny ? 48 : 4096);
   }
   g.R = (int)R;
-  g.tcap = (int)T;
-  g.smem = fixed + (size_t)R * 4 + (size_t)T * 4;
-  g.nt = two ? 512 : (g.R >= 8192 ? 1024 : (g.R >= 2048 ? 512 : 256));
-  if (g.nt > 512) g.nt = 512;  // the kernel is compiled for at most 512 threads
-  if (const char* e = getenv("RPK_PRED_NT")) {  // tuning hook
-    int v = atoi(e);
-    if (v == 64 || v == 128 || v == 256 || v == 512) g.nt = v;
-  }
+  g.smem = fixed + (size_t)R * 4 + 128;
+  g.nt = A32_NT;  // the kernel stages one history row per thread
   return g;
 }
 
@@ -1395,7 +1822,7 @@ static PredWork prepare_work(rpk_ctx* c, int64_t U, const int64_t* indptr) {
   int* order = c->buf<int>("p_order", (size_t)U);
   int* bcnt = c->buf<int>("p_bcnt", 65 * 2 + 4);
   int* boff = bcnt + 65;
-  int* queue = boff + 65;
+  int* queue = boff + 65;  // [0] two-limb kernel, [1] 32-bit kernel, [2] its second (exact) pass
   RPK_CUDA(cudaMemsetAsync(bcnt, 0, sizeof(int) * (65 * 2 + 4), st));
   k_row_lengths<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, work);
   RPK_LAUNCH_CHECK(c);
@@ -1466,6 +1893,7 @@ static void fill_common(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_t U
   pp.out_indptr = nullptr;
   pp.out_indices = nullptr;
   pp.out_values = nullptr;
+  pp.scale = c->get<ModelScale>("m_scale");
 }
 
 static void check_predict_args(rpk_ctx* c, int64_t U, int64_t nnz) {
@@ -1473,6 +1901,7 @@ static void check_predict_args(rpk_ctx* c, int64_t U, int64_t nnz) {
   RPK_REQUIRE(c->bufs.count("m_ptr") != 0, "no similarity model loaded (call rpk_model_load_* first)");
   RPK_REQUIRE(U >= 0 && nnz >= 0, "negative dimension");
   RPK_REQUIRE(U < ((int64_t)1 << 27), "too many users in one call; split the batch");
+  RPK_REQUIRE(c->bufs.count("m_scale") != 0, "no similarity model loaded (call rpk_model_load_* first)");
 }
 
 void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr_u, const int32_t* indices_u, int N,
@@ -1490,50 +1919,61 @@ void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr_
   o_len.init(c, out_len_u, (size_t)U, "p_out_len");
   if (U > 0) {
     PredGeom g = predict_geometry(c, N);
+    RPK_REQUIRE(U * (int64_t)g.P < ((int64_t)1 << 31), "too many (user, item range) work items in one call; split the batch");
     ensure_segments(c, g);
     PredParams pp;
     fill_common(c, pp, g, U, indptr, indices, N, mask_history, PRED_TOPN);
     pp.part_idx = c->buf<int>("p_part_idx", (size_t)U * g.P * N);
     pp.part_sq = c->buf<u64>("p_part_sq", (size_t)U * g.P * N);
     pp.part_len = c->buf<int>("p_part_len", (size_t)U * g.P);
+    const ModelScale* scale = c->get<ModelScale>("m_scale");
     const int fgrid = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
     // the block table of the 32-bit kernel indexes 4-entry blocks with 32 bits
-    const bool blocks_fit = (c->m_nnz + 3 * c->m_I) / 4 < (int64_t)0x7fffffff;
+    const Pred32Geom g2 = predict32_geometry(c, N);
+    const bool blocks_fit = (c->m_nnz + 3 * c->m_I * g2.P) / 4 < (int64_t)0x7fffffff;
     if ((c->flags & DBG_WIDE_ACC) || !blocks_fit) {  // debug flag / giant models: every user through the two-limb kernel
       launch_predict(c, pp, g, U, indptr);
       k_predict_finalize<<<fgrid, 256, 0, st>>>(pp.part_idx, pp.part_sq, pp.part_len, U, g.P, N, o_idx.dev, o_val.dev,
-                                                o_len.dev, nullptr, nullptr, nullptr, nullptr, 0);
+                                                o_len.dev, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, scale);
       RPK_LAUNCH_CHECK(c);
     } else {
-      const Pred32Geom g2 = predict32_geometry(c, N);
+      RPK_REQUIRE(U * (int64_t)g2.P < ((int64_t)1 << 31), "too many (user, item range) work items in one call; split the batch");
+      ensure_blocks(c, g2.P, g2.R);
+      // lists only (no scores wanted): the approximate sums settle most lists, the rest are scored again exactly
+      const bool lists_only = o_val.dev == nullptr && (int64_t)g2.P * N <= MERGE_MAX && !(c->flags & DBG_EXACT_SCORES);
       Pred32Params qp;
       qp.indices = indices;
-      ensure_blocks(c, g2.P, g2.R);
-      qp.ent4 = reinterpret_cast<const uint4*>(c->get<u64>("m_ent4"));
-      qp.blk = c->get<int2>("m_blk");
+      qp.ent = c->get<u64>("m_ent4");
+      qp.blk = c->get<int4>("m_blk");
+      qp.n_work = nullptr;
       qp.U = (int)U;
       qp.P = g2.P;
       qp.R = g2.R;
       qp.I = (int)c->m_I;
       qp.N = N;
       qp.mask = mask_history;
+      qp.exact = lists_only ? 0 : 1;
       qp.cap = g2.cap;
-      qp.direct_cap = g2.direct_cap;
-      qp.tcap = g2.tcap;
       qp.part_idx = c->buf<int>("p_part2_idx", (size_t)U * g2.P * N);
-      qp.part_sq = c->buf<u64>("p_part2_sq", (size_t)U * g2.P * N);
+      qp.part_key = c->buf<u64>("p_part2_sq", (size_t)U * g2.P * N);
       qp.part_len = c->buf<int>("p_part2_len", (size_t)U * g2.P);
-      qp.ovf_flag = c->buf<int>("p_ovf_flag", (size_t)U + 1);
-      qp.ovf_count = qp.ovf_flag + U;
+      qp.part_sft = c->buf<int>("p_part2_sft", (size_t)U * g2.P);
+      // per-user flags: [0, U) handed to the two-limb kernel, [U] their count; [U+1, 2U+1) second exact pass, [2U+1] count
+      int* flags = c->buf<int>("p_ovf_flag", 2 * (size_t)U + 2);
+      qp.ovf_flag = flags;
+      qp.ovf_count = flags + U;
       qp.ovf_tab = c->buf<int4>("p_ovf_tab", (size_t)U);
-      RPK_CUDA(cudaMemsetAsync(qp.ovf_flag, 0, sizeof(int) * ((size_t)U + 1), st));
+      int* redo_flag = flags + U + 1;
+      int* redo_count = flags + 2 * U + 1;
+      int4* redo_tab = c->buf<int4>("p_redo_tab", (size_t)U);
+      RPK_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (2 * (size_t)U + 2), st));
       const PredWork w = prepare_work(c, U, indptr);
       qp.work_tab = w.tab;
       qp.queue = w.queue + 1;
       qp.prof = nullptr;
 #ifdef RPK_PHASE_PROF
       qp.prof = c->buf<unsigned long long>("p_prof32", 16);
-      RPK_CUDA(cudaMemsetAsync(qp.prof, 0, 16 * sizeof(unsigned long long), st));
+      RPK_CUDA(cudaMemsetAsync(qp.prof, 0, 16 * sizeof(unsigned long long), st));  // 0-6 phases, 8-11 counters, 12-14 inside select
 #endif
       RPK_CUDA(cudaFuncSetAttribute(k_predict_a32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2.smem));
       int occ = 0;
@@ -1543,6 +1983,20 @@ void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr_
       c->ev_record(4);
       k_predict_a32<<<grid, g2.nt, g2.smem, st>>>(qp);
       RPK_LAUNCH_CHECK(c);
+      if (lists_only) {
+        // order the per-range lists; users whose order the approximate sums cannot prove are scored again, exactly
+        const int mgrid = (int)std::min<int64_t>(ceil_div(U, MERGE_WARPS), (int64_t)c->sm_count * 16);
+        k_predict_merge<<<mgrid, 32 * MERGE_WARPS, 0, st>>>(qp.part_idx, qp.part_key, qp.part_len, qp.part_sft, indptr, U, g2.P, N,
+                                                           o_idx.dev, o_len.dev, qp.ovf_flag, redo_flag, redo_count, redo_tab);
+        RPK_LAUNCH_CHECK(c);
+        Pred32Params rp = qp;
+        rp.work_tab = redo_tab;
+        rp.n_work = redo_count;
+        rp.exact = 1;
+        rp.queue = w.queue + 2;
+        k_predict_a32<<<grid, g2.nt, g2.smem, st>>>(rp);
+        RPK_LAUNCH_CHECK(c);
+      }
       // users whose survivors overflowed the list: exact two-limb kernel (normally none; the kernel then exits)
       pp.work_tab = qp.ovf_tab;
       pp.n_work = qp.ovf_count;
@@ -1553,22 +2007,33 @@ void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr_
 #ifdef RPK_PHASE_PROF
       {
         unsigned long long h[16];
-        int novf = 0;
+        int novf = 0, nredo = 0;
         RPK_CUDA(cudaMemcpyAsync(h, qp.prof, sizeof(h), cudaMemcpyDeviceToHost, st));
         RPK_CUDA(cudaMemcpyAsync(&novf, qp.ovf_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        RPK_CUDA(cudaMemcpyAsync(&nredo, redo_count, sizeof(int), cudaMemcpyDeviceToHost, st));
         RPK_CUDA(cudaStreamSynchronize(st));
-        static const char* nm[7] = {"fetch", "sweep1", "mask", "select", "clean+mark", "sweep2", "sort+out"};
+        static const char* nm[7] = {"fetch", "bound+sweep1", "mask", "select", "tag", "sweep2", "sort+out"};
         unsigned long long tot = 0;
+        h[3] += 0;
         for (int k = 0; k < 7; ++k) tot += h[k];
-        fprintf(stderr, "[predict32 phases] grid=%d nt=%d P=%d R=%d tcap=%d smem=%zu occ=%d items=%llu sparse=%llu touched/item=%.0f survivors/item=%.1f overflow users=%d cycles/item=%.0f\n",
-                grid, g2.nt, g2.P, g2.R, g2.tcap, g2.smem, occ, h[8], h[9], h[8] ? (double)h[10] / h[8] : 0.0,
-                h[8] ? (double)h[11] / h[8] : 0.0, novf, h[8] ? (double)tot / h[8] : 0.0);
+        tot += h[12] + h[13] + h[14];
+        fprintf(stderr, "[predict32 phases] grid=%d nt=%d P=%d R=%d smem=%zu occ=%d lists_only=%d items=%llu exact items=%llu survivors/item=%.1f overflow users=%d redo users=%d cycles/item=%.0f\n",
+                grid, g2.nt, g2.P, g2.R, g2.smem, occ, (int)lists_only, h[8], h[9], h[8] ? (double)h[11] / h[8] : 0.0, novf, nredo,
+                h[8] ? (double)tot / h[8] : 0.0);
         for (int k = 0; k < 7; ++k)
-          fprintf(stderr, "  %-10s %5.1f%%  %8.0f cycles/item\n", nm[k], 100.0 * h[k] / (tot ? tot : 1), h[8] ? (double)h[k] / h[8] : 0.0);
+          fprintf(stderr, "  %-12s %5.1f%%  %8.0f cycles/item\n", nm[k], 100.0 * h[k] / (tot ? tot : 1), h[8] ? (double)h[k] / h[8] : 0.0);
+        fprintf(stderr, "  select = thread maxima %.0f + boundary bin %.0f + copy/clear %.0f + staging of the next item %.0f cycles/item\n",
+                h[8] ? (double)h[12] / h[8] : 0.0, h[8] ? (double)h[13] / h[8] : 0.0, h[8] ? (double)h[14] / h[8] : 0.0,
+                h[8] ? (double)h[3] / h[8] : 0.0);
       }
 #endif
-      k_predict_finalize<<<fgrid, 256, 0, st>>>(qp.part_idx, qp.part_sq, qp.part_len, U, g2.P, N, o_idx.dev, o_val.dev,
-                                                o_len.dev, qp.ovf_flag, pp.part_idx, pp.part_sq, pp.part_len, g.P);
+      if (lists_only) {
+        k_predict_finalize<<<fgrid, 256, 0, st>>>(qp.part_idx, qp.part_key, qp.part_len, U, g2.P, N, o_idx.dev, o_val.dev, o_len.dev,
+                                                  qp.ovf_flag, pp.part_idx, pp.part_sq, pp.part_len, g.P, qp.ovf_flag, redo_flag, scale);
+      } else {
+        k_predict_finalize<<<fgrid, 256, 0, st>>>(qp.part_idx, qp.part_key, qp.part_len, U, g2.P, N, o_idx.dev, o_val.dev, o_len.dev,
+                                                  qp.ovf_flag, pp.part_idx, pp.part_sq, pp.part_len, g.P, nullptr, nullptr, scale);
+      }
       RPK_LAUNCH_CHECK(c);
     }
   }

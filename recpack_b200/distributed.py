@@ -82,11 +82,19 @@ class ShardExchange:
         """Exchange in the model's own format: this rank's lists (filled through local_out()) are packed into
         model rows (rpk_model_pack_rows; 8 bytes per entry, already in column order) and all-gathered together with
         the row lengths.  Returns ([world * maxrows, K] int64, [world * maxrows] int32) for
-        rpk_model_load_packed_rows + row_source().  With engine=None the caller has filled p_ent itself."""
+        rpk_model_load_packed_rows + row_source(); the common scale exponent is left in self.scale_exp.  With
+        engine=None the caller has filled p_ent (and scale_exp) itself."""
         rows = self.cuts[self.rank + 1] - self.cuts[self.rank]
         if engine is not None:
+            # one fixed-point scale for the whole model: the smallest exponent (largest similarity) of any rank
+            import torch
+
+            e = torch.tensor([engine.model_scale_exp(self.K, self.p_val[:rows], self.p_len[:rows])], dtype=torch.int32,
+                             device=self.p_len.device)
+            self.dist.all_reduce(e, op=self.dist.ReduceOp.MIN)
+            self.scale_exp = int(e.item())
             engine.model_pack_rows(self.cuts[-1], self.K, self.p_idx[:rows], self.p_val[:rows], self.p_len[:rows],
-                                   out=self.p_ent[:rows])
+                                   self.scale_exp, out=self.p_ent[:rows])
         self.dist.all_gather_into_tensor(self.g_ent.view(-1, self.K), self.p_ent)
         self.dist.all_gather_into_tensor(self.g_len.view(-1), self.p_len)
         return self.g_ent.view(-1, self.K), self.g_len.view(-1)

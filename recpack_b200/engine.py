@@ -13,9 +13,9 @@ from . import _lib
 from ._lib import RpkError
 
 SIM_CODES = {"cosine": 0, "conditional_probability": 1}
-METRIC_CODES = {"ndcg": 0, "recall": 1, "dcg": 2, "calibrated_recall": 3, "precision": 4, "reciprocal_rank": 5}
+METRIC_CODES = {"ndcg": 0, "recall": 1, "dcg": 2, "calibrated_recall": 3, "precision": 4, "reciprocal_rank": 5, "hits": 6}
 
-DBG_WIDE_ACC, DBG_TINY_LIST, DBG_MULTI_PASS, DBG_SPLIT_ROWS = 1, 2, 4, 8
+DBG_WIDE_ACC, DBG_TINY_LIST, DBG_MULTI_PASS, DBG_SPLIT_ROWS, DBG_EXACT_SCORES = 1, 2, 4, 8, 16
 
 
 def _is_torch(x):
@@ -156,19 +156,26 @@ class Engine:
         self._check(self._lib.rpk_model_load_topk_rows(self._h, int(I), int(K), int(rows_in), _addr(idx, np.int32),
                                                        _addr(val, np.float64), _addr(ln, np.int32), _addr(row_src, np.int64)))
 
-    def model_pack_rows(self, I, K, idx, val, ln, out=None):
+    def model_scale_exp(self, K, val, ln) -> int:
+        """rpk_model_scale_exp: exponent e of the fixed-point scale 2^e these lists would get as a model of their own."""
+        e = C.c_int32(0)
+        self._check(self._lib.rpk_model_scale_exp(self._h, int(K), int(val.shape[0]), _addr(val, np.float64), _addr(ln, np.int32),
+                                                  C.byref(e)))
+        return int(e.value)
+
+    def model_pack_rows(self, I, K, idx, val, ln, scale_exp, out=None):
         """rpk_model_pack_rows: rank-ordered lists -> packed model rows (uint64 bit patterns; torch tensors carry
-        them as int64).  `out`: [rows, K] buffer to fill."""
+        them as int64) at the scale 2^scale_exp.  `out`: [rows, K] buffer to fill."""
         rows = int(idx.shape[0])
         if out is None:
             out = _empty_like_kind(idx, (rows, K), np.int64 if _is_torch(idx) else np.uint64)
         self._check(self._lib.rpk_model_pack_rows(self._h, int(I), int(K), rows, _addr(idx, np.int32), _addr(val, np.float64),
-                                                  _addr(ln, np.int32), _addr(out)))
+                                                  _addr(ln, np.int32), int(scale_exp), _addr(out)))
         return out
 
-    def model_load_packed_rows(self, I, K, rows_in, ent, ln, row_src=None):
+    def model_load_packed_rows(self, I, K, rows_in, ent, ln, scale_exp, row_src=None):
         self._check(self._lib.rpk_model_load_packed_rows(self._h, int(I), int(K), int(rows_in), _addr(ent), _addr(ln, np.int32),
-                                                         _addr(row_src, np.int64, allow_none=True)))
+                                                         _addr(row_src, np.int64, allow_none=True), int(scale_exp)))
 
     def fit_token(self) -> int:
         return int(self._lib.rpk_fit_token(self._h))
@@ -240,6 +247,16 @@ class Engine:
             _addr(np.ascontiguousarray(disc)), _addr(idcg), maxK, _addr(per_user, np.float64, allow_none=True),
             _addr(sums), _addr(n_users)))
         return sums, int(n_users[0]), per_user
+
+
+    def coverage_topn(self, U, N, K, I, top_idx, top_len, true_indptr, want_flags=False):
+        """rpk_coverage_topn: (number of covered items, uint8[I] flags or None)."""
+        count = np.zeros(1, dtype=np.int64)
+        flags = np.zeros(I, dtype=np.uint8) if want_flags else None
+        self._check(self._lib.rpk_coverage_topn(self._h, int(U), int(N), int(K), int(I), _addr(top_idx, np.int32),
+                                                _addr(top_len, np.int32), _addr(true_indptr, np.int64), _addr(count),
+                                                _addr(flags, np.uint8, allow_none=True)))
+        return int(count[0]), flags
 
 
 _engines = {}

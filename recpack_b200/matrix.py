@@ -11,13 +11,17 @@ import numpy as np
 from scipy.sparse import csr_matrix
 
 
-class UnsupportedTypeError(Exception):
-    """Raised when a matrix of a type not supported by recpack is received (matrix/util.py:64-77)."""
+from . import _ref
 
-    def __init__(self, X):
-        super().__init__(
-            "Recpack only supports matrix types InteractionMatrix, csr_matrix. Received {}.".format(type(X).__name__)
-        )
+if _ref.HAVE_RECPACK:
+    UnsupportedTypeError = _ref.ref_matrix_util.UnsupportedTypeError  # the reference's own exception type
+else:
+
+    class UnsupportedTypeError(Exception):
+        """Raised when a matrix of a type not supported by recpack is received (matrix/util.py:64-77)."""
+
+        def __init__(self, X):
+            super().__init__(f"Recpack only supports matrix types InteractionMatrix, csr_matrix. Received {type(X).__name__}.")
 
 
 def to_csr_matrix(X, binary: bool = False):

@@ -11,6 +11,16 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
+# The unmodified reference, installed by baseline/install_ref.sh (travels to the GPU box with the snapshot), and the
+# stand-in for its missing `hyperopt` dependency: with them on the path recpack_b200's classes subclass the
+# reference's own (recpack_b200/_ref.py) and the reference's Pipeline can drive them.
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+HAVE_REF = os.path.isdir(os.path.join(REF_DIR, "recpack"))
+if HAVE_REF:
+    for p in (os.path.join(ROOT, "baseline", "stubs"), REF_DIR):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")

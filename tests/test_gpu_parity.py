@@ -244,7 +244,7 @@ def _load_model_from_oracle(engine, X, K, sim="cosine", pd_=None):
     return orc.topk_to_csr(want["idx"], want["val"], want["len"], I)
 
 
-@pytest.mark.parametrize("flags", [0, 1, 2, 4, 7])
+@pytest.mark.parametrize("flags", [0, 1, 2, 4, 7, 16, 20])
 @pytest.mark.parametrize("case", [CASES[0], CASES[1], CASES[2], CASES[3], CASES[5]])
 def test_predict_topn_matches_oracle(engine, case, flags):
     from recpack_b200.matrix import binary_structure
@@ -262,7 +262,45 @@ def test_predict_topn_matches_oracle(engine, case, flags):
         assert np.array_equal(got["len"], want["len"])
         assert np.array_equal(got["idx"], want["idx"])
         assert np.array_equal(got["val"], want["val"])
+        # lists only (no scores asked for): most lists are settled by the approximate sums, the rest are scored
+        # again exactly -- the lists must be the same
+        lists = engine.predict_topn(U, indptr, indices, N, mask_history=mask, want_val=False)
+        assert np.array_equal(lists["len"], want["len"])
+        assert np.array_equal(lists["idx"], want["idx"])
     engine.debug_flags(0)
+
+
+@pytest.mark.parametrize("flags", [0, 2, 4, 6])
+def test_predict_lists_only_near_ties_take_the_exact_pass(engine, flags):
+    """Scores that differ only in the lowest bits of the fixed-point sums -- inside one item range and across two
+    ranges (flag 4: two passes) -- cannot be ordered by the 32-bit approximate sums: those users must come out of
+    the second, exact pass (or the in-kernel exact sweep) with the oracle's order."""
+    from recpack_b200.matrix import binary_structure
+
+    I, K, U, N = 64, 6, 40, 5
+    rng = np.random.default_rng(3)
+    # every row: the same few target items spread over both halves of the item range, values equal up to ~1e-11
+    base = rng.random(I) * 0.5 + 0.25
+    idx = np.zeros((I, K), dtype=np.int32)
+    val = np.zeros((I, K))
+    targets = np.array([3, 9, 20, 35, 47, 60], dtype=np.int32)
+    for i in range(I):
+        idx[i] = targets
+        val[i] = base[i] * (1.0 + rng.integers(-3, 4, size=K) * 2.0**-36)
+    ln = np.full(I, K, dtype=np.int32)
+    S = orc.topk_to_csr(idx, val, ln, I)
+    engine.model_load_topk(I, K, idx, val, ln)
+    rows = [np.sort(rng.choice(np.setdiff1d(np.arange(I), targets), size=rng.integers(1, 30), replace=False)) for _ in range(U)]
+    indptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    indices = np.concatenate(rows).astype(np.int32)
+    X = csr_matrix((np.ones(len(indices), dtype=np.int32), indices, indptr), shape=(U, I))
+    engine.debug_flags(flags)
+    want = orc.canon_predict_topn(X, S, N, remove_history=True)
+    got = engine.predict_topn(U, indptr, indices, N, mask_history=True, want_val=False)
+    full = engine.predict_topn(U, indptr, indices, N, mask_history=True)
+    engine.debug_flags(0)
+    assert np.array_equal(got["idx"], want["idx"]) and np.array_equal(got["len"], want["len"])
+    assert np.array_equal(full["idx"], want["idx"]) and np.array_equal(full["val"], want["val"])
 
 
 @pytest.mark.parametrize("flags", [0, 1, 4])
@@ -325,10 +363,43 @@ def test_model_rejects_bad_values(engine):
 
     idx = np.array([[1], [0]], dtype=np.int32)
     ln = np.array([1, 1], dtype=np.int32)
-    with pytest.raises(RpkError):
-        engine.model_load_topk(2, 1, idx, np.array([[-0.5], [0.1]]), ln)
-    with pytest.raises(RpkError):
-        engine.model_load_topk(2, 1, idx, np.array([[2.5], [0.1]]), ln)
+    for bad in (-0.5, float("nan"), float("inf")):
+        with pytest.raises(RpkError):
+            engine.model_load_topk(2, 1, idx, np.array([[bad], [0.1]]), ln)
+    engine.model_load_topk(2, 1, idx, np.array([[2.5], [0.1]]), ln)  # any non-negative magnitude is representable
+
+
+@pytest.mark.parametrize("scale", [1.0, 3.7e-9, 5.0e6])
+def test_fixed_point_scale_is_relative_to_the_largest_similarity(engine, scale):
+    """the resolution of the scores must not depend on the magnitude of the similarities
+    (conditional probability with pop_discount ~ 1 on a large catalogue gives values ~1e-8..1e-10): scaling every
+    value of the model by a constant scales the scores by it and leaves the lists alone; scores agree with the
+    float64 product to 1e-11 relative."""
+    from recpack_b200.matrix import binary_structure
+    from recpack_b200.synth import synth_interactions
+
+    X = synth_interactions(300, 200, 4000, seed=5)
+    K, N = 15, 10
+    want = orc.canon_fit(X, K=K)
+    _, indptr, indices = binary_structure(X)
+    engine.model_load_topk(200, K, want["idx"], want["val"], want["len"])
+    base = engine.predict_topn(300, indptr, indices, N)
+    engine.model_load_topk(200, K, want["idx"], want["val"] * scale, want["len"])
+    got = engine.predict_topn(300, indptr, indices, N)
+    S = orc.topk_to_csr(want["idx"], want["val"] * scale, want["len"], 200)
+    oracle = orc.canon_predict_topn(X, S, N, remove_history=True)
+    assert np.array_equal(got["idx"], oracle["idx"]) and np.array_equal(got["val"], oracle["val"])
+    ref = (orc.binarize(X).astype(np.float64) @ S).toarray()  # float64 scores of the reference's X @ S
+    m = got["idx"] >= 0
+    rows = np.repeat(np.arange(300), N).reshape(300, N)
+    np.testing.assert_allclose(got["val"][m], ref[rows[m], got["idx"][m]], rtol=1e-10)
+    if scale != 1.0 and np.log2(scale) != np.floor(np.log2(scale)):
+        # the lists of the scaled model agree with the unscaled model's except where rounding moves a near tie
+        assert np.mean(got["idx"] == base["idx"]) > 0.99
+    # full CSR output carries the same scale
+    o_ptr, o_idx, o_val = engine.predict_csr(300, indptr, indices)
+    full = csr_matrix((o_val, o_idx, o_ptr), shape=(300, 200)).toarray()
+    np.testing.assert_allclose(full[ref > 0], ref[ref > 0], rtol=1e-10)
 
 
 # ------------------------------------------------------------------------------- metrics / ranking
@@ -488,8 +559,13 @@ def test_model_load_from_padded_shards(engine):
     g_ent = np.full((3 * maxrows, K), ~np.uint64(0), dtype=np.uint64)
     for r in range(3):
         b, e = cuts[r], cuts[r + 1]
-        g_ent[r * maxrows : r * maxrows + e - b] = engine.model_pack_rows(200, K, want["idx"][b:e], want["val"][b:e], want["len"][b:e])
-    engine.model_load_packed_rows(200, K, 3 * maxrows, g_ent, g_len, src)
+    exps = [engine.model_scale_exp(K, np.ascontiguousarray(want["val"][cuts[r] : cuts[r + 1]]), np.ascontiguousarray(want["len"][cuts[r] : cuts[r + 1]])) for r in range(3)]
+    e_all = min(exps)  # what the all-reduce(MIN) of the ranks gives
+    assert e_all == orc.scale_exp(want["val"][np.arange(K)[None, :] < want["len"][:, None]])
+    for r in range(3):
+        b, e = cuts[r], cuts[r + 1]
+        g_ent[r * maxrows : r * maxrows + e - b] = engine.model_pack_rows(200, K, want["idx"][b:e], want["val"][b:e], want["len"][b:e], e_all)
+    engine.model_load_packed_rows(200, K, 3 * maxrows, g_ent, g_len, e_all, src)
     c_ = engine.predict_topn(300, indptr, indices, N)
     for key in ("idx", "val", "len"):
         assert np.array_equal(a[key], b_[key]) and np.array_equal(a[key], c_[key])
@@ -499,7 +575,7 @@ def test_model_load_from_padded_shards(engine):
         bad = g_ent.copy()
         r = int(src[np.flatnonzero(want["len"] >= 2)[0]])
         bad[r, :2] = bad[r, 1::-1]
-        engine.model_load_packed_rows(200, K, 3 * maxrows, bad, g_len, src)
+        engine.model_load_packed_rows(200, K, 3 * maxrows, bad, g_len, e_all, src)
     engine.model_load_topk(200, K, want["idx"], want["val"], want["len"])  # leave a valid model behind
 
 

@@ -209,51 +209,78 @@ def test_packed_counter_carry_property():
 
 
 def test_registers_in_the_reference_registries():
-    """the drop-in classes register in recpack's own ALGORITHM_REGISTRY / METRIC_REGISTRY
-    (recpack/pipelines/registries.py:50-75) under new keys and PipelineBuilder accepts them.  Needs the reference
-    checkout (absent on the GPU box: skipped there); hyperopt is not installed, a six-name stub stands in."""
-    import sys
-    import types
+    """the drop-in classes ARE the reference's classes (subclasses) when recpack imports, register in
+    recpack's own ALGORITHM_REGISTRY / METRIC_REGISTRY (recpack/pipelines/registries.py:50-75) under new keys and
+    PipelineBuilder accepts them.  Needs the reference install (baseline/install_ref.sh -> baseline/_ref)."""
+    from conftest import HAVE_REF
 
-    ref = "/root/reference"
-    if not os.path.isdir(os.path.join(ref, "recpack")):
-        pytest.skip("reference checkout not present")
-    added_path = ref not in sys.path
-    if added_path:
-        sys.path.insert(0, ref)
-    stub = None
-    if "hyperopt" not in sys.modules:
-        stub = types.ModuleType("hyperopt")
-        for name in ("Trials", "fmin", "tpe", "space_eval", "STATUS_OK", "hp"):
-            setattr(stub, name, object())
-        sys.modules["hyperopt"] = stub
-    try:
-        from recpack.pipelines import ALGORITHM_REGISTRY, METRIC_REGISTRY, PipelineBuilder
+    if not HAVE_REF:
+        pytest.skip("baseline/_ref not installed")
+    import recpack.algorithms
+    import recpack.algorithms.base
+    import recpack.metrics
+    import recpack.metrics.base
+    from recpack.pipelines import ALGORITHM_REGISTRY, METRIC_REGISTRY, PipelineBuilder
 
-        import recpack_b200
+    import recpack_b200
+    from recpack_b200 import _ref
 
-        class ItemKNNB200(recpack_b200.ItemKNN):
-            pass
+    assert _ref.HAVE_RECPACK
+    algo = recpack_b200.ItemKNN(K=5)
+    assert isinstance(algo, recpack.algorithms.ItemKNN)
+    assert isinstance(algo, recpack.algorithms.base.TopKItemSimilarityMatrixAlgorithm)
+    assert isinstance(recpack_b200.NDCGK(10), recpack.metrics.NDCGK)
+    assert isinstance(recpack_b200.RecallK(10), recpack.metrics.base.ListwiseMetricK)
+    assert isinstance(recpack_b200.HitK(10), recpack.metrics.base.ElementwiseMetricK)
+    assert isinstance(recpack_b200.CoverageK(10), recpack.metrics.base.GlobalMetricK)
+    # the wrappers are the reference's own functions, not restatements
+    assert type(algo).fit is recpack.algorithms.base.Algorithm.fit
+    assert type(algo).predict is recpack.algorithms.base.Algorithm.predict
 
-        class NDCGKB200(recpack_b200.NDCGK):
-            pass
+    class ItemKNNB200(recpack_b200.ItemKNN):
+        pass
 
+    class NDCGKB200(recpack_b200.NDCGK):
+        pass
+
+    if "ItemKNNB200" not in ALGORITHM_REGISTRY:
         ALGORITHM_REGISTRY.register("ItemKNNB200", ItemKNNB200)
         METRIC_REGISTRY.register("NDCGKB200", NDCGKB200)
-        assert ALGORITHM_REGISTRY.get("ItemKNNB200") is ItemKNNB200 and "ItemKNNB200" in ALGORITHM_REGISTRY
-        assert METRIC_REGISTRY.get("NDCGKB200") is NDCGKB200
-        with pytest.raises(KeyError):  # built-in names cannot be taken over (registries.py:63-75)
-            ALGORITHM_REGISTRY.register("ItemKNN", ItemKNNB200)
-        builder = PipelineBuilder()
-        builder.add_algorithm("ItemKNNB200", params={"K": 200, "predict_topK": 20, "remove_history": True})
-        builder.add_metric("NDCGKB200", K=[10])
-        algo = ALGORITHM_REGISTRY.get("ItemKNNB200")(K=200, predict_topK=20, remove_history=True)
-        assert algo.identifier.startswith("ItemKNNB200(K=200,") and algo.name == "ItemKNNB200"
-        assert NDCGKB200(10).name == "NDCGKB200_10"
-    finally:
-        if stub is not None:
-            sys.modules.pop("hyperopt", None)
-        if added_path:
-            sys.path.remove(ref)
-        for m in [k for k in sys.modules if k == "recpack" or k.startswith("recpack.")]:
-            sys.modules.pop(m, None)
+    assert "ItemKNNB200" in ALGORITHM_REGISTRY and METRIC_REGISTRY.get("NDCGKB200") is not None
+    with pytest.raises(KeyError):  # built-in names cannot be taken over (registries.py:63-75)
+        ALGORITHM_REGISTRY.register("ItemKNN", ItemKNNB200)
+    builder = PipelineBuilder()
+    builder.add_algorithm("ItemKNNB200", params={"K": 200, "predict_topK": 20, "remove_history": True})
+    builder.add_metric("NDCGKB200", K=[10])
+    algo = ItemKNNB200(K=200, predict_topK=20, remove_history=True)
+    assert algo.identifier.startswith("ItemKNNB200(K=200,") and algo.name == "ItemKNNB200"
+    assert NDCGKB200(10).name == "NDCGKB200_10"
+
+
+def test_mirror_fallback_without_recpack():
+    """Without recpack (forced here with RPK_NO_RECPACK=1) the stand-alone mirror keeps the constructor contract."""
+    import subprocess
+    import sys
+
+    code = (
+        "import warnings, pytest\n"
+        "from recpack_b200 import ItemKNN, NDCGK, HitK, CoverageK, _ref\n"
+        "assert not _ref.HAVE_RECPACK\n"
+        "a = ItemKNN(K=7, similarity='conditional_probability', pop_discount=0.5)\n"
+        "assert a.identifier.startswith('ItemKNN(K=7,') and a.name == 'ItemKNN' and a.get_params()['pop_discount'] == 0.5\n"
+        "with pytest.raises(ValueError): ItemKNN(similarity='nope')\n"
+        "with pytest.raises(ValueError): ItemKNN(similarity='conditional_probability', pop_discount=1.5)\n"
+        "with pytest.warns(UserWarning): ItemKNN(pop_discount=0.3)\n"
+        "assert NDCGK(10).name == 'NDCGK_10' and HitK(3).name == 'HitK_3' and CoverageK(5).name == 'CoverageK_5'\n"
+    )
+    env = dict(os.environ, RPK_NO_RECPACK="1", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_only_the_binding_module_imports_recpack():
+    pkg = os.path.join(ROOT, "recpack_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py") and f != "_ref.py":
+            text = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(from|import)\s+recpack(\.|\s)", text, flags=re.M), f
