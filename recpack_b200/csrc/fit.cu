@@ -7,11 +7,25 @@
 //   recpack/util.py:50-96                           get_top_K_ranks / get_top_K_values
 // Row i of the Gram is  c_ij = sum_{u in users(i)} [j in hist(u)]: one CTA owns (row i, item range p),
 // walks users(i) through the CSC copy of X and bumps 32-bit shared-memory counters (native ATOMS.ADD).
+#include <stdio.h>
+
 #include <vector>
 
 #include "common.cuh"
 #include "internal.h"
 #include "prims.cuh"
+#ifdef RPK_PHASE_PROF
+__device__ unsigned long long g_sel_prof[16];
+#define SEL_MARK_BEGIN() __shared__ long long sel_tprev; if (threadIdx.x == 0) sel_tprev = clock64()
+#define SEL_MARK(k)                                                               \
+  do {                                                                            \
+    if (threadIdx.x == 0) {                                                       \
+      const long long t_now = clock64();                                          \
+      atomicAdd(&g_sel_prof[k], (unsigned long long)(t_now - sel_tprev));         \
+      sel_tprev = t_now;                                                          \
+    }                                                                             \
+  } while (0)
+#endif
 #include "select.cuh"
 
 namespace rpk {
@@ -391,7 +405,32 @@ struct RowCountSrc {
   __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return sk.margin(); }
   int cmin;  // set_floor(): counts below this cannot reach the requested key
-  __device__ __forceinline__ void set_floor(u64 thr) { cmin = sk.min_count(thr); }
+  // cosine with coded popularities, packed counters: the smallest count that can reach the requested key, per
+  // popularity code (key = c^2 * 2^(-code/12) >= thr  <=>  c >= sqrt(thr * 2^(code/12))).  One shared table of 256
+  // entries, rebuilt by set_floor; the passes then test a counter against its item's entry with one load and one
+  // compare instead of computing its key.  Null: only the global bound `cmin` is used.
+  unsigned short* cm_tab;
+  int count_bound;  // >= number of candidates of the row (0: unknown, stats() scans)
+  const unsigned char* code_s;  // the coded popularities and their table again, as shared-memory pointers the compiler
+  const float* tab_s;           // can see through (sk.code / sk.code_tab travel through the parameter struct: generic loads)
+  u64 floor_key;                // set_floor(): candidates below this key may be skipped
+  __device__ __forceinline__ void set_floor(u64 thr) {
+    floor_key = thr;
+    cmin = sk.min_count(thr);
+    if (PACK16 && cm_tab) {
+      __syncthreads();  // readers of the previous table are done
+      if (threadIdx.x < 256) {
+        int v = 1;
+        if (thr) {
+          const float need = __uint_as_float((unsigned)thr) / sk.code_tab[threadIdx.x];  // c^2 must reach this
+          const float c = sqrtf(need) - 1.0f;                                            // one count of slack for rounding
+          v = c < 1.0f ? 1 : (c > 65535.0f ? 65535 : (int)c);
+        }
+        cm_tab[threadIdx.x] = (unsigned short)v;
+      }
+      __syncthreads();
+    }
+  }
   // Visit every candidate whose count reaches the floor.  The row's own slot (the diagonal) has been zeroed by the
   // caller, so no slot needs a self test.  Packed counters are read 16 bytes (eight counters) at a time and a
   // vector is skipped as a whole when none of its counters reaches the floor -- in the copy pass after a threshold
@@ -401,7 +440,23 @@ struct RowCountSrc {
   template <class F>
   __device__ __forceinline__ void visit(F f) const {
     const int tid = threadIdx.x, nt = blockDim.x;
-    if (PACK16) {
+    if (PACK16 && cm_tab) {
+      // eight counters and the eight popularity codes of their items per iteration
+      const uint4* c4 = reinterpret_cast<const uint4*>(cnt);
+      const uint2* g8 = reinterpret_cast<const uint2*>(sk.code + r0);
+      for (int v = tid; v < nvec16; v += nt) {
+        const uint4 x = c4[v];
+        if ((x.x | x.y | x.z | x.w) == 0u) continue;
+        const uint2 g = g8[v];
+        const unsigned xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c = (int)((xs[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
+          const unsigned code = ((q < 4 ? g.x : g.y) >> ((q & 3) * 8)) & 0xffu;
+          if (c >= (int)cm_tab[code]) f(8 * v + q, sk.akey(c, r0 + 8 * v + q));
+        }
+      }
+    } else if (PACK16) {
       const uint4* c4 = reinterpret_cast<const uint4*>(cnt);
       const unsigned cm = (unsigned)(cmin > 65535 ? 65535 : (cmin < 1 ? 1 : cmin));
       const unsigned cm_hi = cm << 16;
@@ -428,6 +483,69 @@ struct RowCountSrc {
         if (c0 >= cmin && c0 > 0) f(w, sk.akey(c0, r0 + w));
       }
     }
+  }
+  // Two-step visit (see compact_above).  Pass 1 computes the key of every counter without a branch -- eight counters
+  // and their eight popularity codes per iteration, the same float operations as SimKey::akey -- and queues the
+  // slots whose key reaches the floor, one shared-memory counter update per warp and iteration.  (Counts are small
+  // numbers in most rows, so no cheap integer test separates the few survivors from the bulk: a test that lets a
+  // fifth of the counters through makes every warp run the slow path at every step.)  Pass 2 hands the queued
+  // slots to f, a candidate per thread.  Returns false (nothing visited) when the queue overflowed.
+  __device__ __forceinline__ bool has_queue() const { return PACK16 && cm_tab != nullptr && floor_key > 0ull; }
+  template <class F>
+  __device__ bool for_each_queued(F f, int* queue, int qcap, int* qcount) const {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    if (tid == 0) *qcount = 0;
+    __syncthreads();
+    const uint4* c4 = reinterpret_cast<const uint4*>(cnt);
+    const uint2* g8 = reinterpret_cast<const uint2*>(code_s + r0);
+    const unsigned fk = (unsigned)floor_key;  // cosine keys are float bit patterns
+    for (int v0 = 0; v0 < nvec16; v0 += nt) {  // warp-uniform trip count: the warp queues together
+      const int v = v0 + tid;
+      unsigned hit = 0u;  // which of my eight counters reach the floor
+      if (v < nvec16) {
+        const uint4 x = c4[v];
+        if ((x.x | x.y | x.z | x.w) != 0u) {
+          const uint2 g = g8[v];
+          const unsigned xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float a = (float)((xs[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
+            const float r = tab_s[((q < 4 ? g.x : g.y) >> ((q & 3) * 8)) & 0xffu];
+            const unsigned k = __float_as_uint(__fmul_rn(__fmul_rn(a, a), r));
+            hit |= (k >= fk ? 1u : 0u) << q;
+          }
+        }
+      }
+      const int mine = __popc(hit);
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+      if (wtot == 0) continue;
+      int base = 0;
+      if (lane == 31) base = atomicAdd(qcount, wtot);
+      base = __shfl_sync(0xffffffffu, base, 31);
+      int pos = base + incl - mine;
+      while (hit) {
+        const int q = __ffs(hit) - 1;
+        hit &= hit - 1u;
+        if (pos < qcap) queue[pos] = 8 * v + q;
+        ++pos;
+      }
+    }
+    __syncthreads();
+    const int total = *qcount;
+    if (total > qcap) return false;
+    for (int t = tid; t < total; t += nt) {
+      const int slot = queue[t];
+      const int c = count(slot);
+      f(slot, sk.akey(c, r0 + slot));
+    }
+    visit_extras(f);
+    return true;
   }
   template <class F>
   __device__ __forceinline__ void visit_extras(F f) const {
@@ -461,6 +579,20 @@ struct RowCountSrc {
   // follow from that (no popularity loads, no float math).
   __device__ void stats(SelShared* sh) const {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    if (PACK16 && cm_tab && count_bound > 0) {
+      // no pass over the counters: a count is at most the row's own popularity, which bounds the keys; the number
+      // of candidates is only needed as an upper bound (few real candidates under a large bound cost one
+      // refinement pass more, nothing else)
+      if (tid == 0) {
+        u64 lo = 0, hi = 0;
+        sk.bounds(sk.n[self], lo, hi);
+        sh->count = count_bound;
+        sh->kmin = lo;
+        sh->kmax = hi;
+      }
+      __syncthreads();
+      return;
+    }
     if (tid == 0) {
       sh->count = 0;
       sh->bstar = 0;
@@ -512,6 +644,9 @@ struct RowCountSrc {
 };
 
 struct PairListSrc {  // (idx, cnt) pairs in global memory, idx < 0 = empty slot
+  __device__ __forceinline__ bool has_queue() const { return false; }
+  template <class F>
+  __device__ __forceinline__ bool for_each_queued(F, int*, int, int*) const { return false; }
   SimKey sk;
   const int* idx;
   const int* cnt;
@@ -575,7 +710,21 @@ struct FitParams {
   int* scr_idx;    // [rows x defer_max] unsorted survivors (item, count)
   int* scr_cnt;
   int* scr_len;    // [rows] survivors in scratch, -1 = row already final in out_*
+  unsigned long long* prof;  // RPK_PHASE_PROF builds: cycles of thread 0 per phase
 };
+
+#ifdef RPK_PHASE_PROF
+#define FIT_MARK(k)                                                \
+  do {                                                             \
+    if (threadIdx.x == 0 && p.prof) {                              \
+      const long long t_now = clock64();                           \
+      atomicAdd(p.prof + (k), (unsigned long long)(t_now - t_prev)); \
+      t_prev = t_now;                                              \
+    }                                                              \
+  } while (0)
+#else
+#define FIT_MARK(k) do {} while (0)
+#endif
 
 // Adds the histories of the users of item i whose work prefix lies in [lo, hi) to the counters (one warp;
 // the window is a piece of the row's total work = sum of its users' history lengths).
@@ -722,6 +871,7 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
   unsigned* cnt = reinterpret_cast<unsigned*>(smem + sel_smem_bytes(p.cap));
   __shared__ int s_work;
   __shared__ float s_code_tab[256];
+  __shared__ unsigned short s_cm_tab[256];
   __shared__ int s_ex_idx[HEAVY_CAP], s_ex_cnt[HEAVY_CAP];
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -731,18 +881,22 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
   // coded item popularities for the selection keys: one byte per item behind the counters, loaded once
   if (p.pop_code) {
     unsigned char* code_s = reinterpret_cast<unsigned char*>(cnt) + (size_t)p.R * (PACK16 ? 2 : 4);
-    for (int j = tid; j < p.I; j += nt) code_s[j] = p.pop_code[j];
+    for (int j = tid; j < p.R * p.P; j += nt) code_s[j] = j < p.I ? p.pop_code[j] : (unsigned char)0;
     for (int t = tid; t < 256; t += nt) s_code_tab[t] = exp2f(-(float)t / 12.0f);
     p.sk.code = code_s;
     p.sk.code_tab = s_code_tab;
     __syncthreads();
   }
+#ifdef RPK_PHASE_PROF
+  long long t_prev = clock64();
+#endif
   for (;;) {
     if (tid == 0) s_work = atomicAdd(p.queue, 1);
     __syncthreads();
     const int w = s_work;
     __syncthreads();
     if (w >= total) break;
+    FIT_MARK(0);
     if (PACK16 && w < n_pieces) {
       // ---- a piece of a split row: count it, add the counters into the row's global copy
       const int4 pc = p.piece_tab[w];
@@ -827,6 +981,7 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       for (int s = tid; s < nv; s += nt) c4[s] = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
+    FIT_MARK(1);
     if (pre_slot >= 0) {  // the row's users were counted in pieces (P == 1 there): start from their sum
       const unsigned* hb = p.hbuf + (int64_t)pre_slot * p.hstride;
       for (int s = tid; s < nwords; s += nt) cnt[s] += __ldcg(hb + s);
@@ -872,6 +1027,7 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       }
     }
     __syncthreads();
+    FIT_MARK(2);
     // ---- fused epilogue: similarity ordering, diagonal removal, top-K -- all on the shared-memory row
     // columns of a heavy row that are heavy themselves: their 16-bit counters may have wrapped -- zero them and
     // use the exact pair counts instead
@@ -913,9 +1069,21 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       }
     }
     __syncthreads();
-    RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i, s_ex_idx, s_ex_cnt, nex, 1, p.R >> 3};
+    // upper bound of the row's candidates: every slot when dense counts were loaded, else one per counter update
+    int cbound = ns + nex;
+    if (!p.g16 && pre_slot < 0) cbound = (int)min((u64)cbound, p.work[i]);
+    RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i, s_ex_idx, s_ex_cnt, nex, 1, (PACK16 && p.sk.code) ? s_cm_tab : nullptr, cbound,
+                            reinterpret_cast<const unsigned char*>(cnt) + (size_t)p.R * (PACK16 ? 2 : 4), s_code_tab, 0ull, p.R >> 3};
     bool sorted = true;
+    FIT_MARK(3);
     const int m = block_select_topk(src, p.K, list, p.cap, p.direct_cap, hist, sh, p.defer_max, &sorted);
+    FIT_MARK(4);
+#ifdef RPK_PHASE_PROF
+    if (tid == 0 && p.prof) {
+      atomicAdd(p.prof + 8, 1ull);
+      atomicAdd(p.prof + 9, (unsigned long long)m);
+    }
+#endif
     if (!sorted) {
       // hand the unsorted survivors to k_fit_sort_rows: many small CTAs sort rows concurrently there,
       // instead of this 1024-thread CTA idling through the sort's barriers
@@ -927,6 +1095,7 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
       }
       if (tid == 0) p.scr_len[orow] = m;
       __syncthreads();
+      FIT_MARK(5);
       continue;
     }
     if (p.defer_max > 0 && tid == 0) p.scr_len[orow] = -1;
@@ -1290,7 +1459,8 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     const SimKey sk{n, rnf, pw, nmax, reinterpret_cast<const double*>(pwmin), nullptr, nullptr, mode};
     // coded reciprocals (1 B per item in shared memory) when the catalogue leaves room for them
     const bool use_code = mode == 0 && (size_t)I + 65536 < avail && U < ((int64_t)1 << 21);  // code 255 = 2.5M users
-    const size_t code_bytes = use_code ? (((size_t)I + 15) & ~(size_t)15) : 0;
+    // (the kernel keeps R * P >= I code bytes: R is rounded up to a multiple of 8 per range)
+    const size_t code_bytes = use_code ? (((size_t)I + 8 * 64 + 15) & ~(size_t)15) : 0;
 
     c->ev_record(2);
     const int defer_max = cap;
@@ -1403,6 +1573,13 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
         fp.hdone = hmeta + 2 + HEAVY_ROWS;
         fp.hneed = hmeta + 2 + 2 * HEAVY_ROWS;
       }
+      fp.prof = nullptr;
+#ifdef RPK_PHASE_PROF
+      if (!wide) {
+        fp.prof = c->buf<unsigned long long>("fit_prof", 16);
+        RPK_CUDA(cudaMemsetAsync(fp.prof, 0, 16 * sizeof(unsigned long long), st));
+      }
+#endif
       auto kern = wide ? k_fit_rows<false> : k_fit_rows<true>;
       RPK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       int occ = 0;
@@ -1436,6 +1613,24 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     }
     RPK_CUDA(cudaEventRecord(c->side_ev[1], c->side));
     RPK_CUDA(cudaStreamWaitEvent(st, c->side_ev[1], 0));
+#ifdef RPK_PHASE_PROF
+    {
+      unsigned long long h[16];
+      RPK_CUDA(cudaMemcpyAsync(h, c->get<unsigned long long>("fit_prof"), sizeof(h), cudaMemcpyDeviceToHost, st));
+      RPK_CUDA(cudaStreamSynchronize(st));
+      unsigned long long sp[16];
+      RPK_CUDA(cudaMemcpyFromSymbol(sp, g_sel_prof, sizeof(sp)));
+      fprintf(stderr, "[select phases, all selection calls of the fit so far] stats %.3g  sampled histogram %.3g  boundary %.3g  copy %.3g  tail %.3g  (refinements entered: mark %.3g)\n",
+              (double)sp[0], (double)sp[1], (double)sp[2], (double)sp[3], (double)sp[4], (double)sp[6]);
+      static const char* nm[6] = {"queue", "init counters", "accumulate", "heavy + diagonal", "select", "survivors out"};
+      unsigned long long tot = 0;
+      for (int k = 0; k < 6; ++k) tot += h[k];
+      fprintf(stderr, "[fit rows phases] rows=%llu survivors/row=%.0f cycles/row=%.0f\n", h[8], h[8] ? (double)h[9] / h[8] : 0.0,
+              h[8] ? (double)tot / h[8] : 0.0);
+      for (int k = 0; k < 6; ++k)
+        fprintf(stderr, "  %-18s %5.1f%%  %8.0f cycles/row\n", nm[k], 100.0 * h[k] / (tot ? tot : 1), h[8] ? (double)h[k] / h[8] : 0.0);
+    }
+#endif
     c->ev_record(3);  // the row kernels end here (rpk_last_timings); the deferred sort is timed with the rest of the fit
     c->ev_valid[1] = true;
     if (any_deferred) {

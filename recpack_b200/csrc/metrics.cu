@@ -20,6 +20,9 @@ __device__ __forceinline__ u64 ordered_bits(double v) {
 }
 
 struct CsrRowSrc {
+  __device__ __forceinline__ bool has_queue() const { return false; }
+  template <class F>
+  __device__ __forceinline__ bool for_each_queued(F, int*, int, int*) const { return false; }
   const int* idx;
   const double* val;
   int ns;

@@ -216,8 +216,9 @@ __global__ void k_model_seg(const int64_t* __restrict__ m_ptr, const u64* __rest
 
 // ---- block layout for the 32-bit scoring kernel, built per geometry (P item ranges of R items).  The entries of
 // every (row, item range) segment are copied out on their own, padded to a multiple of 4 entries (32 bytes, one
-// sector), and re-packed as (q << 24) | slot with slot = column - p*R, the accumulator the kernel adds to: one AND
-// and one shift per entry, no range test.  Padding entries have q = 0 and slot = R + (position in the segment & 31):
+// sector), and re-packed as (q << 24) | 4 * slot with slot = column - p*R, the accumulator the kernel adds to (as a
+// byte offset): one AND and one shift per entry, no range test -- which bounds R to 2^22 slots, far beyond what
+// shared memory holds.  Padding entries have q = 0 and slot = R + (position in the segment & 31):
 // they land in 32 scratch accumulators behind the range, a different bank for every lane of the warp that reads them.
 // seg[t] = {offset of the segment inside its model row, entries}, t = row * P + range
 __global__ void k_model_seg_len(const int64_t* __restrict__ m_ptr, const u64* __restrict__ m_ent, int64_t I, int P, int R,
@@ -257,11 +258,11 @@ __global__ void k_model_pad(const int64_t* __restrict__ m_ptr, const u64* __rest
     const int64_t src = m_ptr[i] + sg.x, o = ptr4[t], n4 = ptr4[t + 1] - o;
     u64 qmax = 0;
     for (int64_t k = lane; k < n4; k += 32) {
-      u64 v = (u64)(unsigned)(R + (int)(k & 31));  // padding: q = 0, a scratch slot of this lane's own
+      u64 v = (u64)(unsigned)(R + (int)(k & 31)) << 2;  // padding: q = 0, a scratch slot of this lane's own
       if (k < sg.y) {
         const u64 e = m_ent[src + k];
         const u64 q = e & Q_MASK40;
-        v = (q << 24) | (u64)((unsigned)(e >> 40) - (unsigned)p * (unsigned)R);
+        v = (q << 24) | ((u64)((unsigned)(e >> 40) - (unsigned)p * (unsigned)R) << 2);
         qmax = max(qmax, q);
       }
       ent4[o + k] = v;
@@ -534,6 +535,9 @@ void run_model_load_csr(rpk_ctx* c, int64_t I, int64_t nnz, const int64_t* indpt
 // ------------------------------------------------------------------------------------------
 // Candidate sources: the dense accumulator range, or the list of slots touched by this user.
 struct ScoreSrc {
+  __device__ __forceinline__ bool has_queue() const { return false; }
+  template <class F>
+  __device__ __forceinline__ bool for_each_queued(F, int*, int, int*) const { return false; }
   const unsigned* lo;
   const unsigned* hi;
   const u64* wide;     // non-null: 64-bit accumulators
@@ -989,8 +993,9 @@ __device__ __forceinline__ void pair_apply(const RowPair& rp, F f) {
 // loads in flight.  Segments longer than 96 entries (rare: K / P entries on average) get their tail in a second loop.
 template <class F>
 __device__ __forceinline__ void sweep_rows(const u64* __restrict__ ent, const RowTab* rt, int n, u64 idle, F f) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const int step = 2 * nwarps;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nwarps = A32_NT / 32;
+  constexpr int step = 2 * nwarps;
   int r = warp;
   if (r >= n) return;
   RowPair A, B;
@@ -1130,6 +1135,7 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
   const int G = gridDim.x, bid = blockIdx.x;
   if (a32_work_index(0, bid, G) >= total) return;
   uint4* acc4 = reinterpret_cast<uint4*>(acc);
+  const unsigned acc_s = (unsigned)__cvta_generic_to_shared(acc);
   const int nvec = p.R >> 2;  // R is a multiple of 4
   for (int v = tid; v < nvec; v += nt) acc4[v] = make_uint4(0u, 0u, 0u, 0u);
   for (int b = tid; b < A32_BINS; b += nt) hist[b] = 0;
@@ -1243,7 +1249,7 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
     }
     const int sh_a = 24 + sft;
     const unsigned margin = 2u * (unsigned)d;
-    const u64 idle = (u64)(unsigned)(p.R + lane);
+    const u64 idle = (u64)(unsigned)(p.R + lane) << 2;
     // ---- sweep 1: approximate sums, one fire-and-forget atomic per entry
     if (d > 0) {
       RowTab* rtw = rtab + cur;
@@ -1260,7 +1266,9 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
           __syncthreads();
         }
         // no test per entry: real entries carry their slot, padding lands in the scratch slots behind the range
-        sweep_rows(p.ent, rt, n, idle, [&](u64 e) { atomicAdd(&acc[(unsigned)e & 0xffffffu], (unsigned)(e >> sh_a) | 1u); });
+        sweep_rows(p.ent, rt, n, idle, [&](u64 e) {
+          asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(acc_s + ((unsigned)e & 0xffffffu)), "r"((unsigned)(e >> sh_a) | 1u) : "memory");
+        });
       }
     }
     if (tid == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");  // the next item's record has landed
@@ -1460,7 +1468,7 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
           __syncthreads();
         }
         sweep_rows(p.ent, rt, n, idle, [&](u64 e) {
-          const unsigned j = (unsigned)e & 0xffffffu;
+          const unsigned j = ((unsigned)e & 0xffffffu) >> 2;
           if (j < (unsigned)ns) {
             const unsigned cn = acc[j];
             if (cn) {

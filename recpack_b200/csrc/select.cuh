@@ -31,6 +31,13 @@ namespace rpk {
 
 typedef unsigned long long u64;
 
+// Profiling hook (RPK_PHASE_PROF builds of fit.cu define it): cycles of thread 0 between the marks of
+// block_select_topk.
+#ifndef SEL_MARK
+#define SEL_MARK(k) do {} while (0)
+#define SEL_MARK_BEGIN() do {} while (0)
+#endif
+
 struct __align__(16) Entry {
   u64 key;
   int idx;
@@ -284,12 +291,33 @@ __device__ void refine_keys(Src& src, int need, int room, u64 lo, u64 hi, int g,
 
 // Copies every candidate with key >= thr to list; returns how many there were (may exceed cap).
 // With `certain` set, *certain is also incremented for every candidate with key >= edge (edge >= thr).
+// Sources with a cheap pre-filter (has_queue()) are visited in two steps when `scratch` is given: a dense pass queues
+// the slots that pass the pre-filter, then the queue is worked off one candidate per thread -- so the expensive part
+// (exact key, the entry's global loads, the append) runs with full warps instead of once per warp for every lane
+// that happens to hold a candidate.
 template <class Src>
 __device__ int compact_above(Src& src, u64 thr, Entry* list, int cap, SelShared* sh, u64 edge = 0ull,
-                             int* certain = nullptr) {
+                             int* certain = nullptr, int* scratch = nullptr, int scratch_cap = 0) {
   if (threadIdx.x == 0) sh->count = 0;
   src.set_floor(thr);
   __syncthreads();
+  auto take = [&](int slot, u64 k) {
+    if (k >= thr) {
+      Entry e;
+      src.entry(slot, e);
+      append_one(e, list, cap, &sh->count);
+      if (certain && k >= edge) atomicAdd(certain, 1);
+    }
+  };
+  if (scratch && src.has_queue()) {
+    if (src.for_each_queued(take, scratch, scratch_cap, &sh->n_in)) {
+      __syncthreads();
+      return sh->count;
+    }
+    // the queue overflowed: nothing was taken yet, visit directly
+    if (threadIdx.x == 0) sh->count = 0;
+    __syncthreads();
+  }
   src.for_each([&](int slot, u64 k) {
     if (k >= thr) {
       Entry e;
@@ -318,8 +346,10 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
   if (direct_cap > cap) direct_cap = cap;
 
   // ---- A: count candidates and bound their keys
+  SEL_MARK_BEGIN();
   src.set_floor(0ull);
   src.stats(sh);
+  SEL_MARK(0);
   const int n_c = sh->count;
   const u64 kmin = sh->kmin, kmax = sh->kmax;
   __syncthreads();
@@ -341,6 +371,7 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
         if (k >= kmin && k <= kmax) atomicAdd(&hist[(int)((k - kmin) >> shift)], 1);
       });
       __syncthreads();
+      SEL_MARK(1);
       const int ks = (K + SEL_SAMPLE - 1) / SEL_SAMPLE;
       int sd = 1;
       while (sd * sd < ks) ++sd;
@@ -348,14 +379,17 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
       const u64 edge = kmin + ((u64)sh->bstar << shift);
       const u64 thr = edge > M ? edge - M : 0;
       __syncthreads();
+      SEL_MARK(2);
       // the guess stands when at least K candidates lie at or above the edge (they certainly beat everything
       // below edge - M) and the copy fitted
       if (tid == 0) sh->count2 = 0;
-      const int got = compact_above(src, thr, list, cap, sh, edge, &sh->count2);
+      const int got = compact_above(src, thr, list, cap, sh, edge, &sh->count2, hist, 1 << BITS);
       if (sh->count2 >= K && got <= cap) m = got;
       __syncthreads();
+      SEL_MARK(3);
     }
     if (m < 0) {
+      SEL_MARK(6);
       // ---- B: exact radix refinement on the (approximate) key until the survivors fit
       refine_keys<BITS>(src, K, room, kmin, kmax, 0, n_c, hist, sh);
       u64 lo = sh->lo, hi = sh->hi;
@@ -514,6 +548,7 @@ __device__ int block_select_topk(Src& src, int K, Entry* list, int cap, int dire
     }
   }
   // ---- D: exact sort of the survivors
+  SEL_MARK(4);
   src.set_floor(0ull);
   if (SURVIVORS_ONLY) {
     __syncthreads();
