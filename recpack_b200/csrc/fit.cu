@@ -756,46 +756,45 @@ __device__ __forceinline__ void accumulate_window(const FitParams& p, unsigned* 
       len = (int)(p.indptr[u + 1] - beg);
     }
     if (__shfl_sync(0xffffffffu, pf, 0) >= hi) break;
-    // software pipeline over the users of the batch: the first 128 indices of user l+1 are loaded
-    // while the counters of user l are updated
-    int jn[4] = {-1, -1, -1, -1};
-    int64_t bn = 0;
-    int sn = 0, en = 0;
-    auto fetch = [&](int l) {  // clip user l to [lo, hi) and issue its first loads
-      sn = 0;
-      en = 0;
+    // software pipeline over the users of the batch, three deep: while the counters of user l are updated the first
+    // 128 indices of users l+1 and l+2 are already on their way (an index load is an L2 round trip: one user in
+    // flight left every warp waiting most of the time)
+    struct Stage {
+      int j[4];
+      int64_t b;
+      int s, e;
+    };
+    auto fetch = [&](Stage& st, int l) {  // clip user l to [lo, hi) and issue its first loads
+      st.s = 0;
+      st.e = 0;
+      st.b = 0;
       if (l < 32) {
         const unsigned pfl = __shfl_sync(0xffffffffu, pf, l);
         const int n = __shfl_sync(0xffffffffu, len, l);
-        bn = __shfl_sync(0xffffffffu, beg, l);
+        st.b = __shfl_sync(0xffffffffu, beg, l);
         if (pfl < hi) {
-          sn = lo > pfl ? (int)(lo - pfl) : 0;
-          en = (int)min((unsigned)n, hi - pfl);
+          st.s = lo > pfl ? (int)(lo - pfl) : 0;
+          st.e = (int)min((unsigned)n, hi - pfl);
         }
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const int e = sn + lane + 32 * q;
-        jn[q] = e < en ? p.indices[bn + e] - r0 : -1;
+        const int e = st.s + lane + 32 * q;
+        st.j[q] = e < st.e ? p.indices[st.b + e] - r0 : -1;
       }
     };
-    fetch(0);
-    for (int l = 0; l < 32; ++l) {
-      if (__shfl_sync(0xffffffffu, pf, l) >= hi) break;
-      int jj[4] = {jn[0], jn[1], jn[2], jn[3]};
-      const int64_t bb = bn;
-      const int s0 = sn, e1 = en;
-      fetch(l + 1);
+    auto apply = [&](const Stage& st) {
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (jj[q] >= 0) {
-          if (PACK16) atomicAdd(&cnt[jj[q] >> 1], 1u << ((jj[q] & 1) * 16));
-          else atomicAdd(&cnt[jj[q]], 1u);
+        if (st.j[q] >= 0) {
+          if (PACK16) atomicAdd(&cnt[st.j[q] >> 1], 1u << ((st.j[q] & 1) * 16));
+          else atomicAdd(&cnt[st.j[q]], 1u);
         }
       // long histories: the rest, four loads in flight per lane
-      for (int e = s0 + 128 + lane; e < e1; e += 128) {
+      for (int e = st.s + 128 + lane; e < st.e; e += 128) {
+        int jj[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) jj[q] = e + 32 * q < e1 ? p.indices[bb + e + 32 * q] - r0 : -1;
+        for (int q = 0; q < 4; ++q) jj[q] = e + 32 * q < st.e ? p.indices[st.b + e + 32 * q] - r0 : -1;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           if (jj[q] >= 0) {
@@ -803,6 +802,20 @@ __device__ __forceinline__ void accumulate_window(const FitParams& p, unsigned* 
             else atomicAdd(&cnt[jj[q]], 1u);
           }
       }
+    };
+    Stage A, B, C;
+    fetch(A, 0);
+    fetch(B, 1);
+    for (int l = 0; l < 32; l += 3) {
+      if (__shfl_sync(0xffffffffu, pf, l) >= hi) break;
+      fetch(C, l + 2);
+      apply(A);
+      if (l + 1 >= 32 || __shfl_sync(0xffffffffu, pf, l + 1) >= hi) break;
+      fetch(A, l + 3);
+      apply(B);
+      if (l + 2 >= 32 || __shfl_sync(0xffffffffu, pf, l + 2) >= hi) break;
+      fetch(B, l + 4);
+      apply(C);
     }
   }
 }
