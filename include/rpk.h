@@ -155,6 +155,13 @@ RPK_EXPORT int rpk_predict_topn(rpk_ctx* ctx, int64_t U, int64_t nnz,
                      int N, int mask_history,
                      int32_t* out_idx, double* out_val, int32_t* out_len);
 
+/*
+ * Item filter of the predict calls (recpack/postprocessing/filters.py:58-101, ExcludeItems / SelectItems, applied
+ * INSIDE predict so that a truncated list is refilled from the items that remain): allowed uint8[I], 1 = the item
+ * may be recommended.  NULL removes the filter.  The mask is copied; it stays in force until changed.
+ */
+RPK_EXPORT int rpk_predict_item_filter(rpk_ctx* ctx, const uint8_t* allowed, int64_t I);
+
 /* Full score matrix in CSR, as the reference's predict() returns it.  Two steps: _count fills
  * out_row_nnz int64[U]; the caller prefix-sums it into out_indptr and allocates; _fill writes
  * the column indices (ascending per row) and float64 scores. */

@@ -43,12 +43,39 @@ class GpuSimilarityMixin:
 
     With both unset ``predict`` returns every non-zero score like the reference.  Scores are exact sums
     of the similarities in fixed point relative to the largest similarity of the model
-    (``q = rint(v / vmax * (2^39 - 1))``): they agree with the reference's float64 sums to
-    ``d_u * vmax * 2^-40`` and do not depend on summation order.  Similarity values must be finite and
-    non-negative (a signed model, e.g. EASE, uses ``recpack_b200.EASE``'s dense scorer)."""
+    (``q = rint(v * 2^e)`` with ``2^e * vmax`` in ``[2^39, 2^40)``): they agree with the
+    reference's float64 sums to ``d_u * vmax * 2^-40`` and do not depend on summation order.  Similarity values
+    must be finite and non-negative (a signed, dense model such as EASE's has its own scorer: ``recpack_b200.EASE``)."""
 
     predict_topK = None
     remove_history = False
+    _postfilters = ()
+
+    def set_postfilters(self, filters):
+        """Post-filters (``recpack_b200.postprocessing.ExcludeItems`` / ``SelectItems``) applied inside predict,
+        before the truncation to ``predict_topK``: the filtered items are never recommended and the lists are
+        refilled from the items that remain (postprocessing/filters.py:58-101 on an untruncated matrix)."""
+        self._postfilters = tuple(filters or ())
+        return self
+
+    def truncated(self, K: int):
+        """The same model cut to the K (<= self.K) best neighbours per item, without fitting again: the fitted lists
+        are in rank order, so the first K places ARE the fit at K -- a sweep over K fits once at the largest value
+        (recpack/algorithms/nearest_neighbour.py:360-397 refits for every K)."""
+        from sklearn.base import clone
+
+        dev = self.__dict__.get("_fit_dev")
+        if dev is None:
+            raise ValueError("truncated() needs the rank-ordered lists of a GPU fit (fit on this object first)")
+        K = int(K)
+        if not 1 <= K <= dev["idx"].shape[1]:
+            raise ValueError(f"K must be in [1, {dev['idx'].shape[1]}]")
+        other = clone(self)
+        other.set_params(K=K)
+        out = {"idx": dev["idx"][:, :K].contiguous(), "val": dev["val"][:, :K].contiguous(), "len": dev["len"].clamp(max=K)}
+        other._set_device_fit(out, dev["I"], dev["device"])
+        other._postfilters = self._postfilters
+        return other
 
     # -- similarity_matrix_: host CSR, materialised on first use when the fit result lives on the device ----
     @property
@@ -139,8 +166,11 @@ class GpuSimilarityMixin:
         if X.shape[1] != I:
             raise ValueError("matmul: dimension mismatch with signature (n?,k),(k,m?)->(n?,m?)")
         U = X.shape[0]
+        from .postprocessing import combined_mask
+
         with engine.model_lock:  # load + score as one step: the engine holds one model at a time
             self._ensure_device_model(engine)
+            engine.predict_item_filter(combined_mask(self._postfilters, I))
             if self.predict_topK is None:
                 X, indptr, indices = binary_structure(X)
                 o_ptr, o_idx, o_val = engine.predict_csr(U, indptr, indices, mask_history=bool(self.remove_history))

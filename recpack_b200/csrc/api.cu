@@ -166,6 +166,12 @@ int rpk_predict_topn(rpk_ctx* ctx, int64_t U, int64_t nnz, const int64_t* indptr
   RPK_API_END(ctx)
 }
 
+int rpk_predict_item_filter(rpk_ctx* ctx, const uint8_t* allowed, int64_t I) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_predict_item_filter(ctx, allowed, I);
+  RPK_API_END(ctx)
+}
+
 int rpk_predict_csr_count(rpk_ctx* ctx, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices,
                           int mask_history, int64_t* out_row_nnz) {
   RPK_API_BEGIN(ctx)

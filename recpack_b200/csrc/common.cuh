@@ -90,6 +90,7 @@ struct rpk_ctx {
   bool m_pad = false;  // padded block layout of the model is current
   int m_max_len = 0;  // longest model row
   int m_exp = 39;     // scale of the loaded model: q = rint(v * 2^m_exp)
+  int64_t filter_I = -1;  // item filter of the predict calls (buffer p_item_ok), -1 = none
 
   // ---- per-pass candidate counts of the last rpk_predict_csr_count
   int64_t pc_U = 0;

@@ -24,6 +24,7 @@ void run_model_load_csr(rpk_ctx* c, int64_t I, int64_t nnz, const int64_t* indpt
                         const double* values);
 void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices, int N,
                       int mask_history, int32_t* out_idx, double* out_val, int32_t* out_len);
+void run_predict_item_filter(rpk_ctx* c, const uint8_t* allowed, int64_t I);
 void run_predict_csr_count(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices,
                            int mask_history, int64_t* out_row_nnz);
 void run_predict_csr_fill(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices,

@@ -611,6 +611,7 @@ struct PredParams {
   int* out_indices;
   double* out_values;
   const ModelScale* scale;   // scores are reported as sum * scale->inv
+  const unsigned char* item_ok;  // non-null: item filter, 1 = may be recommended
   unsigned long long* prof;  // RPK_PHASE_PROF builds: cycles of thread 0 per phase
 };
 
@@ -821,6 +822,17 @@ __global__ void __launch_bounds__(1024, 1) k_predict(PredParams p) {
       }
       __syncthreads();
     }
+    if (p.item_ok) {  // postprocessing/filters.py:58-101: filtered items are never recommended
+      for (int s = tid; s < ns; s += nt)
+        if (!p.item_ok[r0 + s]) {
+          if (wide) acc64[s] = 0ull;
+          else {
+            acc_lo[s] = 0u;
+            acc_hi[s] = 0u;
+          }
+        }
+      __syncthreads();
+    }
     ScoreSrc src{acc_lo, acc_hi, wide ? acc64 : nullptr, sparse ? touched : nullptr, r0, sparse ? n_touched : ns, 0ull};
     PROF_MARK(3);
     if (p.mode == PRED_TOPN) {
@@ -925,6 +937,7 @@ struct Pred32Params {
   u64* part_key;         // exact sums; approximate sums where part_sft >= 0
   int* part_len;         // [U*P]
   int* part_sft;         // [U*P] -1: exact keys, s >= 0: keys are 32-bit sums of (q >> s) | 1
+  const unsigned char* item_ok;  // non-null: item filter (1 = may be recommended), padded to a multiple of 4 items
   int* ovf_flag;         // per user: 1 = handed to the two-limb kernel
   int* ovf_count;        // number of such users
   int4* ovf_tab;         // their work records
@@ -1124,7 +1137,7 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
   SelShared* sh = reinterpret_cast<SelShared*>(hist + A32_BINS);
   RowTab* rtab = reinterpret_cast<RowTab*>(smem + sel_smem_bytes(p.cap, A32_BINS));
   unsigned* acc = reinterpret_cast<unsigned*>(smem + a32_fixed_bytes(p.cap));
-  __shared__ int s_flag;
+  __shared__ int s_flag3[3];  // "exact scores needed" of item k lives in s_flag3[k % 3]; reset two items ahead
   __shared__ int4 s_rec[2];
   __shared__ int s_w[2];
   __shared__ u64 s_bsum[2];       // bound of the sums, in units of 2^20: rows beyond the first chunk ...
@@ -1147,7 +1160,7 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
     s_bsum[1] = 0ull;
     s_bsum32[0] = 0u;
     s_bsum32[1] = 0u;
-    s_flag = 0;
+    s_flag3[0] = s_flag3[1] = s_flag3[2] = 0;
     sh->count = 0;
     sh->bstar = 0;
   }
@@ -1200,6 +1213,7 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
 #endif
   for (int k = 0;; ++k) {
     const int cur = k & 1, nxt = cur ^ 1;
+    int& s_flag = s_flag3[k % 3];
     const int w = s_w[cur];
     if (w >= total) break;
     const int4 rec = s_rec[cur];
@@ -1220,7 +1234,7 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
       s_w[nxt] = w_n;
       s_bsum[nxt] = 0ull;
       s_bsum32[nxt] = 0u;
-      s_flag = 0;
+      s_flag3[(k + 1) % 3] = 0;  // the next item's flag; the previous item's may still be read by slow threads
       sh->count = 0;
       sh->bstar = 0;
     }
@@ -1299,6 +1313,21 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
         for (int r = tid; r < d; r += nt) {
           const int j = p.indices[xb + r] - r0;
           if (j >= 0 && j < ns) acc[j] = 0u;
+        }
+      }
+      __syncthreads();
+    }
+    if (p.item_ok) {  // postprocessing/filters.py:58-101: filtered items are never recommended (4 items per word)
+      const unsigned* ok4 = reinterpret_cast<const unsigned*>(p.item_ok + r0);
+      for (int v = tid; v < nvec; v += nt) {
+        const unsigned okw = 4 * v < ns ? __ldg(ok4 + v) : 0x01010101u;
+        if (okw != 0x01010101u) {
+          uint4 x = acc4[v];
+          if (!(okw & 0xffu)) x.x = 0u;
+          if (!(okw & 0xff00u)) x.y = 0u;
+          if (!(okw & 0xff0000u)) x.z = 0u;
+          if (!(okw & 0xff000000u)) x.w = 0u;
+          acc4[v] = x;
         }
       }
       __syncthreads();
@@ -1874,6 +1903,8 @@ static void launch_predict(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_
   c->ev_valid[2] = true;
 }
 
+static const unsigned char* item_filter_ptr(rpk_ctx* c);
+
 static void fill_common(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_t U, const int64_t* indptr,
                         const int32_t* indices, int N, int mask, int mode) {
   pp.indptr = indptr;
@@ -1902,6 +1933,35 @@ static void fill_common(rpk_ctx* c, PredParams& pp, const PredGeom& g, int64_t U
   pp.out_indices = nullptr;
   pp.out_values = nullptr;
   pp.scale = c->get<ModelScale>("m_scale");
+  pp.item_ok = item_filter_ptr(c);
+}
+
+// Item filter of the predict calls: a copy of the caller's mask, normalised to 0 / 1 bytes and padded (with 1 = allowed)
+// so that the kernels can read it four items at a time up to the end of the last item range.
+__global__ void k_filter_copy(const unsigned char* __restrict__ in, int64_t I, int64_t padded, unsigned char* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < padded) out[j] = j < I ? (in[j] ? 1 : 0) : 1;
+}
+
+void run_predict_item_filter(rpk_ctx* c, const uint8_t* allowed_u, int64_t I) {
+  if (!allowed_u) {
+    c->filter_I = -1;
+    return;
+  }
+  RPK_REQUIRE(I >= 0, "negative item count");
+  const unsigned char* in = stage_in(c, allowed_u, (size_t)I, "p_item_ok_in");
+  const int64_t padded = I + 4096;
+  unsigned char* ok = c->buf<unsigned char>("p_item_ok", (size_t)padded);
+  k_filter_copy<<<ceil_div(padded, 256), 256, 0, c->stream>>>(in, I, padded, ok);
+  RPK_LAUNCH_CHECK(c);
+  c->filter_I = I;
+  if (!is_device_ptr(allowed_u)) RPK_CUDA(cudaStreamSynchronize(c->stream));  // the caller may reuse its buffer
+}
+
+static const unsigned char* item_filter_ptr(rpk_ctx* c) {
+  if (c->filter_I < 0) return nullptr;
+  RPK_REQUIRE(c->filter_I == c->m_I, "the item filter was set for a different number of items than the model has");
+  return c->get<unsigned char>("p_item_ok");
 }
 
 static void check_predict_args(rpk_ctx* c, int64_t U, int64_t nnz) {
@@ -1961,6 +2021,7 @@ void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr_
       qp.N = N;
       qp.mask = mask_history;
       qp.exact = lists_only ? 0 : 1;
+      qp.item_ok = item_filter_ptr(c);
       qp.cap = g2.cap;
       qp.part_idx = c->buf<int>("p_part2_idx", (size_t)U * g2.P * N);
       qp.part_key = c->buf<u64>("p_part2_sq", (size_t)U * g2.P * N);

@@ -201,6 +201,13 @@ class Engine:
             _addr(out["len"], np.int32)))
         return out
 
+    def predict_item_filter(self, allowed):
+        """rpk_predict_item_filter: uint8[I] mask of the items that may be recommended (None removes the filter)."""
+        if allowed is None:
+            self._check(self._lib.rpk_predict_item_filter(self._h, None, 0))
+        else:
+            self._check(self._lib.rpk_predict_item_filter(self._h, _addr(allowed, np.uint8), int(allowed.shape[0])))
+
     def predict_csr(self, U, indptr, indices, mask_history=False):
         """Full score matrix as (indptr int64, indices int32, data float64) numpy arrays."""
         nnz = int(indices.shape[0])

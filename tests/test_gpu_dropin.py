@@ -214,3 +214,65 @@ def test_reference_pipeline_runs_the_dropin(similarity, K):
     val = orc.canon_metrics_from_lists(top["idx"], top["len"], test_out, [("ndcg", 10), ("recall", 10)])
     assert topn_row["NDCGKB200_10"] == pytest.approx(val[("ndcg", 10)][0], rel=1e-12)
     assert topn_row["RecallKB200_10"] == pytest.approx(val[("recall", 10)][0], rel=1e-12)
+
+
+def test_postfilters_inside_predict_refill_the_lists():
+    """postprocessing/filters.py:58-101 applied inside predict: equal to filtering the UNTRUNCATED prediction matrix and
+    ranking afterwards -- the places of the removed items are taken by the next best ones."""
+    from recpack_b200 import ExcludeItems, ItemKNN, SelectItems
+    from recpack_b200.util import top_k_lists
+
+    train, _ = _data(U=300, I=120, nnz=5000, seed=31)
+    N = 10
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        algo = ItemKNN(K=30).fit(train)
+        full = algo.predict(train)  # every score, no filter
+        popular = np.argsort(-np.bincount(train.indices, minlength=120))[:15]
+        keep = np.arange(0, 120, 2)
+        for filters in ([ExcludeItems(popular)], [SelectItems(keep)], [ExcludeItems(popular), SelectItems(keep)]):
+            want = full
+            for f in filters:
+                want = csr_matrix(f.apply(want))
+            want.eliminate_zeros()
+            want = csr_matrix(want - want.multiply(train.astype(bool)))  # history removal (pipeline.py:174-175)
+            want.eliminate_zeros()
+            w_idx, w_len = top_k_lists(want, N)
+            algo.set_params(predict_topK=N, remove_history=True)
+            got = algo.set_postfilters(filters).predict(train)
+            g_idx, g_len = got._rpk_topn
+            assert np.array_equal(g_len, w_len) and np.array_equal(g_idx, w_idx)
+            allowed = np.ones(120, dtype=bool)
+            for f in filters:
+                allowed &= f.item_mask(120).astype(bool)
+            assert allowed[g_idx[g_idx >= 0]].all()
+            # the full-matrix mode honours the filters too
+            algo.set_params(predict_topK=None, remove_history=False)
+            dense = algo.predict(train).toarray()
+            assert not dense[:, ~allowed].any()
+            ref_dense = full.toarray()
+            np.testing.assert_array_equal(dense[:, allowed], ref_dense[:, allowed])
+        algo.set_postfilters(None)
+        algo.set_params(predict_topK=None, remove_history=False)
+        assert (algo.predict(train) != full).nnz == 0  # the filter is gone again
+
+
+def test_truncated_model_equals_a_fit_at_the_smaller_K():
+    """A sweep over K fits once: the first K places of the rank-ordered lists are the fit at K, bit for bit."""
+    from recpack_b200 import ItemKNN
+
+    train, _ = _data(U=500, I=200, nnz=9000, seed=41)
+    for sim in ("cosine", "conditional_probability"):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            big = ItemKNN(K=60, similarity=sim, predict_topK=10, remove_history=True).fit(train)
+            for K in (1, 7, 60):
+                small = ItemKNN(K=K, similarity=sim, predict_topK=10, remove_history=True).fit(train)
+                cut = big.truncated(K)
+                assert cut.K == K and cut.get_params()["similarity"] == sim
+                a, b = cut.similarity_matrix_.copy(), small.similarity_matrix_.copy()
+                a.sort_indices()
+                b.sort_indices()
+                assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) and np.array_equal(a.data, b.data)
+                pa, pb = cut.predict(train), small.predict(train)
+                assert np.array_equal(pa._rpk_topn[0], pb._rpk_topn[0]) and np.array_equal(pa.data, pb.data)
