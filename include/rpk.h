@@ -17,6 +17,8 @@
  *   rpk_topk_csr        get_top_K_ranks on an arbitrary prediction matrix (util.py:50-77)
  *   rpk_metrics_topn    NDCGK / DCGK / RecallK / CalibratedRecallK._calculate
  *                       (metrics/dcg.py:21-128, metrics/recall.py:21-85)
+ *   rpk_gram_dense_f64 / rpk_ease_from_inverse / rpk_predict_dense_*
+ *                       EASE._fit and its dense X @ B predict (recpack/algorithms/ease.py:63-95)
  *
  * Conventions
  *   - plain C types only; every call returns 0 on success, non-zero on failure, with a
@@ -209,6 +211,29 @@ RPK_EXPORT int rpk_coverage_topn(rpk_ctx* ctx, int64_t U, int N, int K, int64_t 
  * rpk_fit_config enables it; this entry point exposes it for verification.
  */
 RPK_EXPORT int rpk_gram_dense_u16(rpk_ctx* ctx, int64_t I, int64_t Kd, const uint8_t* A, uint16_t* out_G);
+
+/*
+ * EASE (recpack/algorithms/ease.py:63-95).
+ *   rpk_gram_dense_f64      XTX = (X.T @ X).toarray(): exact co-occurrence counts of ALL users as float64 [I x I]
+ *                           (tensor-core Gram over 32,768-user chunks, summed).  out_G may be host or device memory.
+ *   rpk_ease_from_inverse   B_ij = -P_ij / P_jj * w_j (i != j), B_ii = 0 from P = inv(XTX + l2 I): the closed form of
+ *                           I - P @ diag(1 / diag(P)) followed by B @ diag(w), w_j = 1 / n_j^alpha (NULL: no scaling).
+ *                           P and out_B are DEVICE matrices [I x I] float64 and may be the same buffer.  The inverse
+ *                           itself is a library call on the caller's side (cuSOLVER potrf + potri).
+ *   rpk_predict_dense_topn  scores = X @ B for a dense float64 model B (device, [I x I] row-major): every score is
+ *   rpk_predict_dense_full  the sum over the user's history in ascending item order, one float64 addition per term
+ *                           (scipy's csr @ dense order).  _topn keeps the N best non-zero scores per user (score
+ *                           desc, item index asc; history optionally removed first), _full writes all scores
+ *                           float64 [U x I].
+ */
+RPK_EXPORT int rpk_gram_dense_f64(rpk_ctx* ctx, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr,
+                       const int32_t* indices, double* out_G);
+RPK_EXPORT int rpk_ease_from_inverse(rpk_ctx* ctx, int64_t I, const double* P, const double* w, double* out_B);
+RPK_EXPORT int rpk_predict_dense_topn(rpk_ctx* ctx, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                           int64_t I, const double* B, int N, int mask_history,
+                           int32_t* out_idx, double* out_val, int32_t* out_len);
+RPK_EXPORT int rpk_predict_dense_full(rpk_ctx* ctx, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                           int64_t I, const double* B, int mask_history, double* out_scores);
 
 /* Device time (CUDA events on the context's stream) of the dominant kernels of the last calls:
  * out_ms[0] = tensor-core Gram of the last fit, out_ms[1] = sparse fit kernels of the last fit,

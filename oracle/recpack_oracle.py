@@ -167,6 +167,20 @@ def ref_fit_row_blocked(X, K=200, block=2048, rows=None) -> csr_matrix:
     return sp.vstack(out).tocsr() if out else csr_matrix((0, n_items))
 
 
+def ref_ease(X, l2=1e3, alpha=0) -> csr_matrix:
+    """EASE._fit, recpack/algorithms/ease.py:63-95 (without the optional pruning)."""
+    X = csr_matrix(X)
+    X = X.astype(bool).astype(X.dtype)
+    XTX = (X.T @ X).toarray()
+    P = np.linalg.inv(XTX + l2 * np.identity((X.shape[1]), dtype=np.float32))
+    B = np.identity(X.shape[1]) - P @ np.diag(1.0 / np.diag(P))
+    B[np.diag_indices(B.shape[0])] = 0.0
+    if alpha != 0:
+        w = 1 / np.diag(XTX) ** alpha
+        B = B @ np.diag(w)
+    return csr_matrix(B)
+
+
 def ref_predict(X, S) -> csr_matrix:
     """ItemSimilarityMatrixAlgorithm._predict, algorithms/base.py:237-255."""
     X = csr_matrix(X)

@@ -7,6 +7,7 @@ a B200 every compute call raises."""
 from .base import Algorithm, ItemSimilarityMatrixAlgorithm, TopKItemSimilarityMatrixAlgorithm  # noqa: F401
 from .matrix import UnsupportedTypeError, to_csr_matrix  # noqa: F401
 from .metrics import NDCGK, DCGK, RecallK, CalibratedRecallK, PrecisionK, ReciprocalRankK, HitK, CoverageK  # noqa: F401
+from .ease import EASE  # noqa: F401
 from .nearest_neighbour import ItemKNN  # noqa: F401
 from .postprocessing import ExcludeItems, SelectItems  # noqa: F401
 from .util import get_top_K_ranks, get_top_K_values  # noqa: F401

@@ -210,6 +210,33 @@ int rpk_coverage_topn(rpk_ctx* ctx, int64_t U, int N, int K, int64_t I, const in
   RPK_API_END(ctx)
 }
 
+int rpk_gram_dense_f64(rpk_ctx* ctx, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices, double* out_G) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_gram_dense_f64(ctx, U, I, nnz, indptr, indices, out_G);
+  RPK_API_END(ctx)
+}
+
+int rpk_ease_from_inverse(rpk_ctx* ctx, int64_t I, const double* P, const double* w, double* out_B) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_ease_from_inverse(ctx, I, P, w, out_B);
+  RPK_API_END(ctx)
+}
+
+int rpk_predict_dense_topn(rpk_ctx* ctx, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices, int64_t I,
+                           const double* B, int N, int mask_history, int32_t* out_idx, double* out_val, int32_t* out_len) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_predict_dense(ctx, U, nnz, indptr, indices, I, B, N, mask_history, out_idx, out_val, out_len, nullptr);
+  RPK_API_END(ctx)
+}
+
+int rpk_predict_dense_full(rpk_ctx* ctx, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices, int64_t I,
+                           const double* B, int mask_history, double* out_scores) {
+  RPK_API_BEGIN(ctx)
+  if (!out_scores) throw rpk::Error("out_scores must not be null");
+  rpk::run_predict_dense(ctx, U, nnz, indptr, indices, I, B, 1, mask_history, nullptr, nullptr, nullptr, out_scores);
+  RPK_API_END(ctx)
+}
+
 int rpk_gram_dense_u16(rpk_ctx* ctx, int64_t I, int64_t Kd, const uint8_t* A, uint16_t* out_G) {
   RPK_API_BEGIN(ctx)
   rpk::run_gram_dense_u16(ctx, I, Kd, A, out_G);

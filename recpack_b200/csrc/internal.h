@@ -40,6 +40,10 @@ void run_metrics_topn(rpk_ctx* c, int64_t U, int N, const int32_t* top_idx, cons
 void run_coverage_topn(rpk_ctx* c, int64_t U, int N, int K, int64_t I, const int32_t* top_idx, const int32_t* top_len,
                        const int64_t* true_indptr, int64_t* out_count, uint8_t* out_flags);
 
+void run_gram_dense_f64(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices, double* out_G);
+void run_ease_from_inverse(rpk_ctx* c, int64_t I, const double* P, const double* w, double* B);
+void run_predict_dense(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices, int64_t I, const double* B,
+                       int N, int mask_history, int32_t* out_idx, double* out_val, int32_t* out_len, double* out_full);
 void run_gram_dense_u16(rpk_ctx* c, int64_t I, int64_t Kd, const unsigned char* A, unsigned short* G);
 void run_gram_dense_tc(rpk_ctx* c, const unsigned char* A, int64_t rows_pad, int64_t kd_pad, int64_t row_begin,
                        int64_t row_end, unsigned short* G, int64_t ldg);

@@ -1609,51 +1609,49 @@ __global__ void __launch_bounds__(32 * MERGE_WARPS) k_predict_merge(const int* _
                                                                    int* __restrict__ out_idx, int* __restrict__ out_len,
                                                                    const int* __restrict__ ovf_flag, int* __restrict__ redo_flag,
                                                                    int* __restrict__ redo_count, int4* __restrict__ redo_tab) {
+  // per warp: the user's entries as they come (a*) and in order (s*)
+  __shared__ u64 a_lo[MERGE_WARPS][MERGE_MAX], a_hi[MERGE_WARPS][MERGE_MAX];
   __shared__ u64 s_lo[MERGE_WARPS][MERGE_MAX], s_hi[MERGE_WARPS][MERGE_MAX];
-  __shared__ int s_ix[MERGE_WARPS][MERGE_MAX];
+  __shared__ int a_ix[MERGE_WARPS][MERGE_MAX], s_ix[MERGE_WARPS][MERGE_MAX];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  u64* lo = s_lo[wib];
-  u64* hi = s_hi[wib];
-  int* ix = s_ix[wib];
+  u64 *alo = a_lo[wib], *ahi = a_hi[wib], *lo = s_lo[wib], *hi = s_hi[wib];
+  int *aix = a_ix[wib], *ix = s_ix[wib];
   int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int PN = P * N;
   for (int64_t u = warp; u < U; u += nwarps) {
     if (ovf_flag[u]) continue;  // the two-limb kernel produces this user's lists
     const int64_t xb = indptr[u];
     const u64 d = (u64)(indptr[u + 1] - xb);
+    // gather the valid entries of the P lists, densely: range q contributes its first part_len places
     int tot = 0;
-    for (int q = 0; q < P; ++q) tot += part_len[u * P + q];
-    // every lane ranks its own entries against all of them (read straight from global memory: PN is small)
     __syncwarp();
-    for (int e = lane; e < PN; e += 32) {
-      const int q = e / N, t = e - q * N;
-      if (t >= part_len[u * P + q]) continue;
+    for (int q = 0; q < P; ++q) {
+      const int n = part_len[u * P + q];
       const int sf = part_sft[u * P + q];
-      const u64 k = part_key[u * PN + e];
-      u64 l, h;
-      if (sf < 0) {
-        l = h = k;
-      } else {
-        l = (k > d ? k - d : 0ull) << sf;
-        h = (k + d) > (~0ull >> sf) ? ~0ull : (k + d) << sf;
-      }
-      const int je = part_idx[u * PN + e];
-      int rank = 0;
-      for (int f = 0; f < PN; ++f) {
-        const int qf = f / N, tf = f - qf * N;
-        if (tf >= part_len[u * P + qf]) continue;
-        const int sff = part_sft[u * P + qf];
-        const u64 kf = part_key[u * PN + f];
-        u64 lf, hf;
-        if (sff < 0) {
-          lf = hf = kf;
+      for (int t = lane; t < n; t += 32) {
+        const u64 k = part_key[(u * P + q) * N + t];
+        u64 l, h;
+        if (sf < 0) {
+          l = h = k;
         } else {
-          lf = (kf > d ? kf - d : 0ull) << sff;
-          hf = (kf + d) > (~0ull >> sff) ? ~0ull : (kf + d) << sff;
+          l = (k > d ? k - d : 0ull) << sf;
+          h = (k + d) > (~0ull >> sf) ? ~0ull : (k + d) << sf;
         }
-        const int jf = part_idx[u * PN + f];
-        rank += (hf > h) || (hf == h && (lf > l || (lf == l && jf < je)));
+        alo[tot + t] = l;
+        ahi[tot + t] = h;
+        aix[tot + t] = part_idx[(u * P + q) * N + t];
+      }
+      tot += n;
+    }
+    __syncwarp();
+    // rank every entry against all of them: by upper end, then lower end, then index
+    for (int e = lane; e < tot; e += 32) {
+      const u64 l = alo[e], h = ahi[e];
+      const int je = aix[e];
+      int rank = 0;
+      for (int f = 0; f < tot; ++f) {
+        const u64 hf = ahi[f], lf = alo[f];
+        rank += (hf > h) || (hf == h && (lf > l || (lf == l && aix[f] < je)));
       }
       lo[rank] = l;
       hi[rank] = h;

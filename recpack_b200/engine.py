@@ -147,6 +147,42 @@ class Engine:
         self._check(self._lib.rpk_gram_dense_u16(self._h, int(I), int(Kd), _addr(A, np.uint8), _addr(out, np.uint16)))
         return out
 
+    # -- EASE: dense Gram, closed-form model, dense scoring ----------------------------------
+    def gram_dense_f64(self, U, I, indptr, indices):
+        """rpk_gram_dense_f64: exact X^T X of all users as float64 [I, I] (torch CUDA tensor when the inputs are)."""
+        out = _empty_like_kind(indices, (I, I), np.float64)
+        self._check(self._lib.rpk_gram_dense_f64(self._h, int(U), int(I), int(indices.shape[0]), _addr(indptr, np.int64),
+                                                 _addr(indices, np.int32), _addr(out, np.float64)))
+        return out
+
+    def ease_from_inverse(self, P, w=None, out=None):
+        """rpk_ease_from_inverse on device matrices: B = -P / diag(P) (columns), zero diagonal, optional column scale w."""
+        I = int(P.shape[0])
+        out = P if out is None else out
+        self._check(self._lib.rpk_ease_from_inverse(self._h, I, _addr(P, np.float64), _addr(w, np.float64, allow_none=True),
+                                                    _addr(out, np.float64)))
+        return out
+
+    def predict_dense_topn(self, U, indptr, indices, B, N, mask_history=True, want_val=True):
+        out = {
+            "idx": _empty_like_kind(indices, (U, N), np.int32),
+            "val": _empty_like_kind(indices, (U, N), np.float64) if want_val else None,
+            "len": _empty_like_kind(indices, (U,), np.int32),
+        }
+        self._check(self._lib.rpk_predict_dense_topn(
+            self._h, int(U), int(indices.shape[0]), _addr(indptr, np.int64), _addr(indices, np.int32), int(B.shape[0]),
+            _addr(B, np.float64), int(N), int(bool(mask_history)), _addr(out["idx"], np.int32),
+            _addr(out["val"], np.float64, allow_none=True), _addr(out["len"], np.int32)))
+        return out
+
+    def predict_dense_full(self, U, indptr, indices, B, mask_history=False):
+        """All scores X @ B as a float64 [U, I] array next to the inputs (torch CUDA tensor or numpy)."""
+        out = _empty_like_kind(indices, (U, int(B.shape[0])), np.float64)
+        self._check(self._lib.rpk_predict_dense_full(
+            self._h, int(U), int(indices.shape[0]), _addr(indptr, np.int64), _addr(indices, np.int32), int(B.shape[0]),
+            _addr(B, np.float64), int(bool(mask_history)), _addr(out, np.float64)))
+        return out
+
     # -- model ----------------------------------------------------------------------------
     def model_load_topk(self, I, K, idx, val, ln):
         self._check(self._lib.rpk_model_load_topk(self._h, int(I), int(K), _addr(idx, np.int32), _addr(val, np.float64),
