@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--similarity", default="cosine", choices=["cosine", "conditional_probability"])
     ap.add_argument("--K", type=int, default=200, help="neighbours kept per item")
     ap.add_argument("--generator", default="auto", choices=["auto", "numpy", "cuda"], help="synthetic data generator (synth.make_dataset)")
+    ap.add_argument("--trace", action="store_true", help="print rank 0's device-time trace of one extra step (rpk_trace) to stderr")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-fraction", type=float, default=0.02, help="fraction of a full pass one step of the reference arm / CPU baseline does")
@@ -310,7 +311,7 @@ def run_gpu(args):
         ev[1].record()
         if world > 1:
             g_ent, g_len = exchange.gather_packed(eng)  # rows travel in the model's packed format
-            eng.model_load_packed_rows(I, K_NEIGH, g_ent.shape[0], g_ent, g_len, exchange.scale_exp, exchange.row_source())
+            eng.model_load_packed_rows_v(I, K_NEIGH, g_ent.shape[0], g_ent, g_len, exchange.vmax, exchange.row_source())
         else:
             eng.model_load_topk(I, K_NEIGH, fit_out["idx"], fit_out["val"], fit_out["len"])
         ev[2].record()
@@ -355,6 +356,13 @@ def run_gpu(args):
         step_ms.append(ms)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
+    if args.trace:  # one more step with the library's marks on (after the timed region)
+        eng.trace(True)
+        one_step(False)
+        rep = eng.trace_report()
+        eng.trace(False)
+        if rank == 0:
+            sys.stderr.write("[trace of one step, rank 0: device ms since the previous mark]\n" + rep)
     launches = eng.launch_count() - launches0
     t = torch.tensor([float(np.sum(step_ms)), float(np.mean(phase_ms["fit"])), float(np.mean(phase_ms["score"])),
                       float(np.mean(phase_ms["exchange"]))], dtype=torch.float64, device=dev)
@@ -388,7 +396,7 @@ def run_gpu(args):
             t0 = time.perf_counter()
             eng.fit_topk(U, I, hx_ptr.numpy(), hx_idx.numpy(), K_NEIGH, similarity=SIM, item_begin=ib, item_end=ie, out=fit_out)
             g_ent, g_len = exchange.gather_packed(eng)
-            eng.model_load_packed_rows(I, K_NEIGH, g_ent.shape[0], g_ent, g_len, exchange.scale_exp, exchange.row_source())
+            eng.model_load_packed_rows_v(I, K_NEIGH, g_ent.shape[0], g_ent, g_len, exchange.vmax, exchange.row_source())
             eng.predict_topn(nU, hu_ptr.numpy(), hu_idx.numpy(), N_LIST, mask_history=True, out=top_out)
             sums, n_users, _ = eng.metrics_topn(nU, N_LIST, top_out["idx"], top_out["len"], hy_ptr.numpy(), hy_idx.numpy(), metrics,
                                                 want_per_user=False)

@@ -135,6 +135,15 @@ RPK_EXPORT int rpk_model_pack_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows,
                         const int32_t* idx, const double* val, const int32_t* len, int scale_exp, uint64_t* out_ent);
 RPK_EXPORT int rpk_model_load_packed_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in,
                                const uint64_t* ent, const int32_t* len, const int64_t* row_src, int scale_exp);
+/* The same exchange without a host round trip: rpk_model_vmax leaves the largest value of the lists as a double in
+ * device memory, the ranks all-reduce it (MAX) on the stream, and the _v forms take that device scalar instead of an
+ * exponent.  With device pointers only, nothing here synchronises; what the packing finds wrong with this rank's
+ * values is reported by the next rpk_model_load_* call. */
+RPK_EXPORT int rpk_model_vmax(rpk_ctx* ctx, int K, int64_t rows, const double* val, const int32_t* len, double* out_vmax);
+RPK_EXPORT int rpk_model_pack_rows_v(rpk_ctx* ctx, int64_t I, int K, int64_t rows,
+                          const int32_t* idx, const double* val, const int32_t* len, const double* vmax, uint64_t* out_ent);
+RPK_EXPORT int rpk_model_load_packed_rows_v(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in,
+                                 const uint64_t* ent, const int32_t* len, const int64_t* row_src, const double* vmax);
 /* Every rpk_fit_topk increments the context's fit token.  When the last fit covered all item rows and
  * produced values, its lists stay resident on the device and rpk_model_load_last_fit(token) builds the
  * model from them without any host round trip; it fails when `token` is not the current one. */
@@ -241,6 +250,12 @@ RPK_EXPORT int rpk_predict_dense_full(rpk_ctx* ctx, int64_t U, int64_t nnz, cons
  * out_ms[3] = users the last fit routed to the tensor cores, out_ms[4] = that number padded to the MMA
  * k-block.  out_ms must hold 5 doubles.  Synchronises. */
 RPK_EXPORT int rpk_last_timings(rpk_ctx* ctx, double* out_ms);
+
+/* Tracing: with `on` != 0 every later call records named marks (CUDA events) on the context's stream at its phase
+ * boundaries.  rpk_trace_report synchronises, formats "name: ms since the previous mark" lines for all marks recorded
+ * since the last report into an internal buffer (valid until the next call on the context), clears them and returns it. */
+RPK_EXPORT int rpk_trace(rpk_ctx* ctx, int on);
+RPK_EXPORT const char* rpk_trace_report(rpk_ctx* ctx);
 
 /* Fit configuration.  dense_users: how many of the users with the longest histories go through the
  * tensor-core Gram (0 = none, -1 = automatic, at most 4096); the remaining users go through the

@@ -29,6 +29,9 @@ _SIGNATURES = {
     "rpk_model_scale_exp": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _f64p, _i32p, C.POINTER(C.c_int32)]),
     "rpk_model_pack_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _i32p, _f64p, _i32p, C.c_int, _vp]),
     "rpk_model_load_packed_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _vp, _i32p, _i64p, C.c_int]),
+    "rpk_model_vmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, _f64p, _i32p, _f64p]),
+    "rpk_model_pack_rows_v": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _i32p, _f64p, _i32p, _f64p, _vp]),
+    "rpk_model_load_packed_rows_v": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _vp, _i32p, _i64p, _f64p]),
     "rpk_fit_token": (C.c_int64, [C.c_void_p]),
     "rpk_model_load_last_fit": (C.c_int, [C.c_void_p, C.c_int64]),
     "rpk_model_load_csr": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, _f64p]),
@@ -44,6 +47,8 @@ _SIGNATURES = {
                                          _i32p, _f64p, _i32p]),
     "rpk_predict_dense_full": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, C.c_int64, _f64p, C.c_int, _f64p]),
     "rpk_gram_dense_u16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _vp, _vp]),
+    "rpk_trace": (C.c_int, [C.c_void_p, C.c_int]),
+    "rpk_trace_report": (C.c_char_p, [C.c_void_p]),
     "rpk_fit_config": (C.c_int, [C.c_void_p, C.c_int]),
     "rpk_last_timings": (C.c_int, [C.c_void_p, _vp]),
     "rpk_metrics_topn": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, _i32p, _i32p, _i64p, _i32p, C.c_int64, C.c_int,

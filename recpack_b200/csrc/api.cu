@@ -1,5 +1,6 @@
 // extern "C" surface of librpk.so (include/rpk.h).  Every entry point catches all C++ exceptions
 // and turns them into a status code + message.
+#include <stdio.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -68,6 +69,8 @@ void rpk_destroy(rpk_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   for (auto& e : ctx->side_ev)
     if (e) cudaEventDestroy(e);
+  for (auto& m : ctx->marks) cudaEventDestroy(m.second);
+  for (auto& e : ctx->mark_pool) cudaEventDestroy(e);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   delete ctx;
 }
@@ -133,14 +136,36 @@ int rpk_model_scale_exp(rpk_ctx* ctx, int K, int64_t rows, const double* val, co
 int rpk_model_pack_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows, const int32_t* idx, const double* val,
                         const int32_t* len, int scale_exp, uint64_t* out_ent) {
   RPK_API_BEGIN(ctx)
-  rpk::run_model_pack_rows(ctx, I, K, rows, idx, val, len, scale_exp, out_ent);
+  rpk::run_model_pack_rows(ctx, I, K, rows, idx, val, len, scale_exp, nullptr, out_ent);
   RPK_API_END(ctx)
 }
 
 int rpk_model_load_packed_rows(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in, const uint64_t* ent, const int32_t* len,
                                const int64_t* row_src, int scale_exp) {
   RPK_API_BEGIN(ctx)
-  rpk::run_model_load_packed_rows(ctx, I, K, rows_in, ent, len, row_src, scale_exp);
+  rpk::run_model_load_packed_rows(ctx, I, K, rows_in, ent, len, row_src, scale_exp, nullptr);
+  RPK_API_END(ctx)
+}
+
+int rpk_model_vmax(rpk_ctx* ctx, int K, int64_t rows, const double* val, const int32_t* len, double* out_vmax) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_model_vmax(ctx, K, rows, val, len, out_vmax);
+  RPK_API_END(ctx)
+}
+
+int rpk_model_pack_rows_v(rpk_ctx* ctx, int64_t I, int K, int64_t rows, const int32_t* idx, const double* val,
+                          const int32_t* len, const double* vmax, uint64_t* out_ent) {
+  RPK_API_BEGIN(ctx)
+  if (!vmax) throw rpk::Error("vmax must not be null");
+  rpk::run_model_pack_rows(ctx, I, K, rows, idx, val, len, 0, vmax, out_ent);
+  RPK_API_END(ctx)
+}
+
+int rpk_model_load_packed_rows_v(rpk_ctx* ctx, int64_t I, int K, int64_t rows_in, const uint64_t* ent, const int32_t* len,
+                                 const int64_t* row_src, const double* vmax) {
+  RPK_API_BEGIN(ctx)
+  if (!vmax) throw rpk::Error("vmax must not be null");
+  rpk::run_model_load_packed_rows(ctx, I, K, rows_in, ent, len, row_src, 0, vmax);
   RPK_API_END(ctx)
 }
 
@@ -258,6 +283,33 @@ int rpk_last_timings(rpk_ctx* ctx, double* out_ms) {
   out_ms[3] = ctx->last_dense_users;
   out_ms[4] = ctx->last_dense_kd;
   RPK_API_END(ctx)
+}
+
+int rpk_trace(rpk_ctx* ctx, int on) {
+  RPK_API_BEGIN(ctx)
+  ctx->tracing = on != 0;
+  RPK_API_END(ctx)
+}
+
+const char* rpk_trace_report(rpk_ctx* ctx) {
+  if (!ctx) return "";
+  ctx->trace_text.clear();
+  try {
+    cudaSetDevice(ctx->device);
+    RPK_CUDA(cudaStreamSynchronize(ctx->stream));
+    char line[256];
+    for (size_t k = 0; k < ctx->marks.size(); ++k) {
+      float ms = 0.f;
+      if (k > 0) RPK_CUDA(cudaEventElapsedTime(&ms, ctx->marks[k - 1].second, ctx->marks[k].second));
+      snprintf(line, sizeof(line), "%-28s %9.3f ms\n", ctx->marks[k].first.c_str(), ms);
+      ctx->trace_text += line;
+    }
+    for (auto& m : ctx->marks) ctx->mark_pool.push_back(m.second);
+    ctx->marks.clear();
+  } catch (const std::exception& e) {
+    ctx->err = e.what();
+  }
+  return ctx->trace_text.c_str();
 }
 
 int rpk_fit_config(rpk_ctx* ctx, int dense_users) {

@@ -6,6 +6,8 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/rpk.h"
 
@@ -69,6 +71,23 @@ struct rpk_ctx {
     if (!ev[k]) RPK_CUDA(cudaEventCreate(&ev[k]));
     RPK_CUDA(cudaEventRecord(ev[k], stream));
   }
+  // ---- tracing (rpk_trace): named marks on the context's stream, reported as the device time between neighbours
+  bool tracing = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  std::vector<cudaEvent_t> mark_pool;
+  std::string trace_text;
+  void mark(const char* name) {
+    if (!tracing) return;
+    cudaEvent_t e = nullptr;
+    if (!mark_pool.empty()) {
+      e = mark_pool.back();
+      mark_pool.pop_back();
+    } else {
+      RPK_CUDA(cudaEventCreate(&e));
+    }
+    RPK_CUDA(cudaEventRecord(e, stream));
+    marks.emplace_back(name, e);
+  }
 
   // ---- state of the last fit (device pointers into bufs)
   int64_t fit_I = 0;
@@ -91,6 +110,7 @@ struct rpk_ctx {
   int m_max_len = 0;  // longest model row
   int m_exp = 39;     // scale of the loaded model: q = rint(v * 2^m_exp)
   int64_t filter_I = -1;  // item filter of the predict calls (buffer p_item_ok), -1 = none
+  bool pack_flag_pending = false;  // a stream-ordered rpk_model_pack_rows_v left its validation flag unchecked
 
   // ---- per-pass candidate counts of the last rpk_predict_csr_count
   int64_t pc_U = 0;

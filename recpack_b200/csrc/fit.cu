@@ -82,7 +82,7 @@ __global__ void k_len_hist(const int64_t* __restrict__ indptr, int64_t U, int64_
   }
 }
 __global__ void k_assign_dense_slots(const int64_t* __restrict__ indptr, int64_t U, int* __restrict__ thr_cnt, int hmax,
-                                     int* __restrict__ slot) {
+                                     int* __restrict__ slot, int* __restrict__ dense_user) {
   int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (u >= U) return;
   const int64_t d = indptr[u + 1] - indptr[u];
@@ -90,8 +90,23 @@ __global__ void k_assign_dense_slots(const int64_t* __restrict__ indptr, int64_t
   if (d >= thr_cnt[0]) {
     s = atomicAdd(&thr_cnt[1], 1);
     if (s >= hmax) s = -1;  // cannot happen: the threshold admits at most hmax users
+    else dense_user[s] = (int)u;
   }
   slot[u] = s;
+}
+// One block per dense user (their histories are the longest of all): A[item][slot] = 1 for its interactions, and the
+// user is taken off the sparse path's item counts.
+__global__ void k_fill_dense_users(const int64_t* __restrict__ indptr, const int* __restrict__ indices,
+                                   const int* __restrict__ dense_user, const int* __restrict__ thr_cnt, int64_t kd_pad,
+                                   unsigned char* __restrict__ A, int* __restrict__ n_light) {
+  const int s = blockIdx.x;
+  if (s >= thr_cnt[1]) return;
+  const int u = dense_user[s];
+  for (int64_t k = indptr[u] + threadIdx.x; k < indptr[u + 1]; k += blockDim.x) {
+    const int j = indices[k];
+    A[(int64_t)j * kd_pad + s] = 1;
+    atomicSub(&n_light[j], 1);
+  }
 }
 // A[item][slot] = 1 for every interaction of a dense user (one warp per user).
 __global__ void k_fill_dense(const int64_t* __restrict__ indptr, const int* __restrict__ indices, int64_t U,
@@ -1287,6 +1302,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
   const double* pw = item_pow_u ? stage_in(c, item_pow_u, (size_t)I, "fit_pw") : nullptr;
 
   // ---- preparation
+  c->mark("fit: begin");
   int* n = c->buf<int>("fit_n", (size_t)I);
   int* cursor = c->buf<int>("fit_cursor", (size_t)I);
   u64* work = c->buf<u64>("fit_work", (size_t)I);
@@ -1355,6 +1371,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     hmax = best_h;
     dense_tau = best_tau;
   }
+  c->mark("fit: item counts + split");
   const int* dense_slot = nullptr;
   const unsigned short* g16 = nullptr;
   const int* n_sparse = n;  // per-item user counts on the sparse path
@@ -1375,23 +1392,22 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     RPK_CUDA(cudaMemcpyAsync(thr_cnt, thr_init, sizeof(thr_init), cudaMemcpyHostToDevice, st));
     RPK_CUDA(cudaMemcpyAsync(n_light, n, sizeof(int) * (size_t)I, cudaMemcpyDeviceToDevice, st));
     RPK_CUDA(cudaMemsetAsync(A, 0, (size_t)rows_pad * kd_pad, st));
-    k_assign_dense_slots<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, thr_cnt, hmax, slot);
+    int* dense_user = c->buf<int>("fit_dense_user", (size_t)hmax);
+    k_assign_dense_slots<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, thr_cnt, hmax, slot, dense_user);
     RPK_LAUNCH_CHECK(c);
-    const int wblocks = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
-    k_fill_dense<<<wblocks, 256, 0, st>>>(indptr, indices, U, slot, kd_pad, A);
+    k_fill_dense_users<<<hmax, 256, 0, st>>>(indptr, indices, dense_user, thr_cnt, kd_pad, A, n_light);
     RPK_LAUNCH_CHECK(c);
-    k_item_counts_light<<<wblocks, 256, 0, st>>>(indptr, indices, U, slot, n_light);
-    RPK_LAUNCH_CHECK(c);
+    c->mark("fit: dense operand");
     c->ev_record(0);
     run_gram_dense_tc(c, A, rows_pad, kd_pad, g_row0, item_end, G, rows_pad);
     c->ev_record(1);
+    c->mark("fit: tensor-core Gram");
     c->ev_valid[0] = true;
     dense_slot = slot;
     g16 = G - g_row0 * rows_pad;  // indexed by absolute item row in the fit kernel
     n_sparse = n_light;
   }
-  k_scan_i32_i64<<<1, 1024, 0, st>>>(n_sparse, cscptr, I);
-  RPK_LAUNCH_CHECK(c);
+  scan_i32_i64(c, n_sparse, cscptr, I);
   if (nnz > 0 && U > 0) {
     int blocks = (int)std::min<int64_t>((U * 32 + 255) / 256, (int64_t)c->sm_count * 16);
     k_fill_csc<<<blocks, 256, 0, st>>>(indptr, indices, U, dense_slot, cscptr, cursor, csc_users, work, (int)item_begin,
@@ -1475,6 +1491,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     // (the kernel keeps R * P >= I code bytes: R is rounded up to a multiple of 8 per range)
     const size_t code_bytes = use_code ? (((size_t)I + 8 * 64 + 15) & ~(size_t)15) : 0;
 
+    c->mark("fit: CSC + order + heavy");
     c->ev_record(2);
     const int defer_max = cap;
     int* scr_idx = c->buf<int>("fit_scr_idx", (size_t)nrows * defer_max);
@@ -1644,6 +1661,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
         fprintf(stderr, "  %-18s %5.1f%%  %8.0f cycles/row\n", nm[k], 100.0 * h[k] / (tot ? tot : 1), h[8] ? (double)h[k] / h[8] : 0.0);
     }
 #endif
+    c->mark("fit: row kernels");
     c->ev_record(3);  // the row kernels end here (rpk_last_timings); the deferred sort is timed with the rest of the fit
     c->ev_valid[1] = true;
     if (any_deferred) {
@@ -1673,6 +1691,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
       RPK_LAUNCH_CHECK(c);
     }
   }
+  c->mark("fit: sort + values");
   // remember where the lists live on the device: predict can load its model from them without a round trip
   c->lf_token++;
   c->lf_idx = nullptr;

@@ -14,10 +14,11 @@ void run_fit_item_counts(rpk_ctx* c, int32_t* out_counts, int64_t I);
 void run_model_load_topk(rpk_ctx* c, int64_t I, int K, const int32_t* idx, const double* val, const int32_t* len);
 void run_model_load_last_fit(rpk_ctx* c, int64_t token);
 void run_model_scale_exp(rpk_ctx* c, int K, int64_t rows, const double* val, const int32_t* len, int32_t* out_exp);
+void run_model_vmax(rpk_ctx* c, int K, int64_t rows, const double* val, const int32_t* len, double* out_vmax);
 void run_model_pack_rows(rpk_ctx* c, int64_t I, int K, int64_t rows, const int32_t* idx, const double* val,
-                         const int32_t* len, int scale_exp, uint64_t* out_ent);
+                         const int32_t* len, int scale_exp, const double* vmax, uint64_t* out_ent);
 void run_model_load_packed_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, const uint64_t* ent, const int32_t* len,
-                                const int64_t* row_src, int scale_exp);
+                                const int64_t* row_src, int scale_exp, const double* vmax);
 void run_model_load_topk_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, const int32_t* idx, const double* val,
                               const int32_t* len, const int64_t* row_src);
 void run_model_load_csr(rpk_ctx* c, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices,

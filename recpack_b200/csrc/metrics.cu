@@ -225,6 +225,7 @@ void run_metrics_topn(rpk_ctx* c, int64_t U, int N, const int32_t* top_idx_u, co
   }
   k_metric_sums<<<n_metrics, 1024, 0, st>>>(pu_dev, U, o_sums.dev, reinterpret_cast<long long*>(o_n.dev));
   RPK_LAUNCH_CHECK(c);
+  c->mark("metrics");
   o_pu.finish(c);
   o_sums.finish(c);
   o_n.finish(c);

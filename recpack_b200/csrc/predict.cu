@@ -84,6 +84,7 @@ __global__ void k_model_vmax_flat(const double* __restrict__ val, int64_t n, u64
 }
 
 // e = 39 - floor(log2(vmax)): vmax * 2^e lies in [2^39, 2^40).  An empty (or all-zero) model gets e = 39.
+// (vmax_bits: bit pattern of a non-negative double, which is also how a device-resident double is passed in.)
 __global__ void k_model_scale(const u64* __restrict__ vmax_bits, ModelScale* __restrict__ sc, int forced_e, int use_forced) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int e = 39;
@@ -278,6 +279,7 @@ __global__ void k_gather_len(const int* __restrict__ len, const int64_t* __restr
 }
 
 static void model_common_begin(rpk_ctx* c, int64_t I) {
+  c->mark("model: begin");
   RPK_REQUIRE(I >= 0 && I < ((int64_t)1 << 24), "item count must be below 2^24");
   c->m_I = I;
   c->m_P = 0;  // segment tables must be rebuilt
@@ -298,12 +300,18 @@ static const ModelScale* model_set_scale(rpk_ctx* c, bool use_forced, int forced
 }
 
 static void model_check_flag(rpk_ctx* c) {
-  int h = 0;
+  int h = 0, hp = 0;
   ModelScale hs;
+  if (c->pack_flag_pending) RPK_CUDA(cudaMemcpyAsync(&hp, c->get<int>("pk_flag"), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   RPK_CUDA(cudaMemcpyAsync(&h, c->get<int>("m_flag"), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   RPK_CUDA(cudaMemcpyAsync(&hs, c->get<ModelScale>("m_scale"), sizeof(ModelScale), cudaMemcpyDeviceToHost, c->stream));
   RPK_CUDA(cudaStreamSynchronize(c->stream));
   c->m_exp = hs.e;
+  c->mark("model: loaded (sync)");
+  if (c->pack_flag_pending) {
+    c->pack_flag_pending = false;
+    h |= hp;  // what the (stream-ordered) packing of this rank's rows found
+  }
   if (h & 1) {
     c->m_I = 0;
     throw Error("similarity model: values must be finite and non-negative, columns in [0, I)");
@@ -336,8 +344,7 @@ void run_model_load_topk_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, con
       RPK_CUDA(cudaMemcpyAsync(m_len, len, sizeof(int) * (size_t)I, cudaMemcpyDeviceToDevice, st));
     }
   }
-  k_scan_i32_i64<<<1, 1024, 0, st>>>(m_len, m_ptr, I);
-  RPK_LAUNCH_CHECK(c);
+  scan_i32_i64(c, m_len, m_ptr, I);
   u64* m_ent = c->buf<u64>("m_ent", (size_t)I * K);
   unsigned* m_rowmax = c->buf<unsigned>("m_rowmax", (size_t)I);
   if (I > 0) {
@@ -417,9 +424,32 @@ void run_model_scale_exp(rpk_ctx* c, int K, int64_t rows, const double* val_u, c
   *out_exp = hs.e;
 }
 
+// Largest value of the lists as a double in device (or host) memory -- the stream-ordered form of
+// rpk_model_scale_exp: no synchronisation when out_vmax is device memory.
+void run_model_vmax(rpk_ctx* c, int K, int64_t rows, const double* val_u, const int32_t* len_u, double* out_vmax_u) {
+  RPK_REQUIRE(K >= 1 && K <= 4096, "K must be in [1, 4096]");
+  RPK_REQUIRE(rows >= 0 && out_vmax_u, "bad arguments");
+  cudaStream_t st = c->stream;
+  const double* val = stage_in(c, val_u, (size_t)rows * K, "pk_in_val");
+  const int32_t* len = stage_in(c, len_u, (size_t)rows, "pk_in_len");
+  Out<double> o;
+  o.init(c, out_vmax_u, 1, "pk_vmax_out");
+  int* flag = c->buf<int>("pk_flag", 1);
+  RPK_CUDA(cudaMemsetAsync(o.dev, 0, sizeof(double), st));
+  RPK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  if (rows > 0) {
+    k_model_vmax_lists<<<(int)std::min<int64_t>(ceil_div(rows * K, 256), (int64_t)c->sm_count * 16), 256, 0, st>>>(
+        val, len, nullptr, K, rows, reinterpret_cast<u64*>(o.dev), flag);
+    RPK_LAUNCH_CHECK(c);
+  }
+  o.finish(c);
+  finish_call(c);
+}
+
 void run_model_pack_rows(rpk_ctx* c, int64_t I, int K, int64_t rows, const int32_t* idx_u, const double* val_u,
-                         const int32_t* len_u, int scale_exp, uint64_t* out_u) {
-  RPK_REQUIRE(scale_exp > -1000 && scale_exp < 1100, "scale exponent out of range");
+                         const int32_t* len_u, int scale_exp, const double* vmax_u, uint64_t* out_u) {
+  c->mark("pack: begin");
+  RPK_REQUIRE(vmax_u || (scale_exp > -1000 && scale_exp < 1100), "scale exponent out of range");
   RPK_REQUIRE(K >= 1 && K <= 4096, "K must be in [1, 4096]");
   RPK_REQUIRE(I >= 0 && I < ((int64_t)1 << 24), "item count must be below 2^24");
   RPK_REQUIRE(rows >= 0, "negative row count");
@@ -433,7 +463,13 @@ void run_model_pack_rows(rpk_ctx* c, int64_t I, int K, int64_t rows, const int32
   int* flag = c->buf<int>("pk_flag", 1);
   RPK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
   ModelScale* sc = c->buf<ModelScale>("pk_scale", 1);
-  k_model_scale<<<1, 32, 0, st>>>(nullptr, sc, scale_exp, 1);
+  const bool deferred = vmax_u != nullptr && is_device_ptr(vmax_u) && !o.host;  // everything stays on the stream
+  if (vmax_u) {
+    const double* vm = stage_in(c, vmax_u, 1, "pk_vmax_in");
+    k_model_scale<<<1, 32, 0, st>>>(reinterpret_cast<const u64*>(vm), sc, 0, 0);
+  } else {
+    k_model_scale<<<1, 32, 0, st>>>(nullptr, sc, scale_exp, 1);
+  }
   RPK_LAUNCH_CHECK(c);
   if (rows > 0) {
     int n2 = 2;
@@ -442,22 +478,34 @@ void run_model_pack_rows(rpk_ctx* c, int64_t I, int K, int64_t rows, const int32
     k_model_from_topk<<<grid, 128, (size_t)n2 * sizeof(u64), st>>>(idx, val, len, nullptr, K, (int)I, (int)rows, nullptr, o.dev, nullptr, flag, sc);
     RPK_LAUNCH_CHECK(c);
   }
+  if (deferred) {
+    c->pack_flag_pending = true;  // checked together with the flags of the next model load (no synchronisation here)
+    c->mark("pack: rows packed");
+    return;
+  }
   int h = 0;
   RPK_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   RPK_CUDA(cudaStreamSynchronize(st));
   RPK_REQUIRE(!(h & 1), "similarity lists: values must be finite, non-negative and below 2^(40 - scale_exp); columns in [0, I)");
   RPK_REQUIRE(!(h & 2), "similarity lists: column indices must be unique within a row");
+  c->mark("pack: rows packed (sync)");
   o.finish(c);
   finish_call(c);
 }
 
 void run_model_load_packed_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, const uint64_t* ent_u, const int32_t* len_u,
-                                const int64_t* row_src_u, int scale_exp) {
+                                const int64_t* row_src_u, int scale_exp, const double* vmax_u) {
   RPK_REQUIRE(K >= 1 && K <= 4096, "K must be in [1, 4096]");
   RPK_REQUIRE(rows_in >= I || row_src_u, "fewer input rows than items");
-  RPK_REQUIRE(scale_exp > -1000 && scale_exp < 1100, "scale exponent out of range");
+  RPK_REQUIRE(vmax_u || (scale_exp > -1000 && scale_exp < 1100), "scale exponent out of range");
   model_common_begin(c, I);
-  model_set_scale(c, true, scale_exp);
+  if (vmax_u) {
+    const double* vm = stage_in(c, vmax_u, 1, "pk_vmax_in");
+    k_model_scale<<<1, 32, 0, c->stream>>>(reinterpret_cast<const u64*>(vm), c->get<ModelScale>("m_scale"), 0, 0);
+    RPK_LAUNCH_CHECK(c);
+  } else {
+    model_set_scale(c, true, scale_exp);
+  }
   cudaStream_t st = c->stream;
   const u64* ent = stage_in(c, reinterpret_cast<const u64*>(ent_u), (size_t)rows_in * K, "m_in_ent");
   const int32_t* len = stage_in(c, len_u, (size_t)rows_in, "m_in_len");
@@ -472,8 +520,7 @@ void run_model_load_packed_rows(rpk_ctx* c, int64_t I, int K, int64_t rows_in, c
       RPK_CUDA(cudaMemcpyAsync(m_len, len, sizeof(int) * (size_t)I, cudaMemcpyDeviceToDevice, st));
     }
   }
-  k_scan_i32_i64<<<1, 1024, 0, st>>>(m_len, m_ptr, I);
-  RPK_LAUNCH_CHECK(c);
+  scan_i32_i64(c, m_len, m_ptr, I);
   u64* m_ent = c->buf<u64>("m_ent", (size_t)I * K);
   unsigned* m_rowmax = c->buf<unsigned>("m_rowmax", (size_t)I);
   if (I > 0) {
@@ -1785,8 +1832,7 @@ static void ensure_blocks(rpk_ctx* c, int P, int R) {
     k_model_seg_len<<<ceil_div(nseg, 256), 256, 0, st>>>(m_ptr, m_ent, I, P, R, seg, len4);
     RPK_LAUNCH_CHECK(c);
   }
-  k_scan_i32_i64<<<1, 1024, 0, st>>>(len4, ptr4, nseg);
-  RPK_LAUNCH_CHECK(c);
+  scan_i32_i64(c, len4, ptr4, nseg);
   if (nseg > 0) {
     k_model_pad<<<(int)std::min<int64_t>(ceil_div(nseg * 32, 256), (int64_t)c->sm_count * 32), 256, 0, st>>>(m_ptr, m_ent, seg, ptr4, I, P, R,
                                                                                                           ent4, blk);
@@ -1984,6 +2030,7 @@ void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr_
   o_val.init(c, out_val_u, (size_t)U * N, "p_out_val");
   o_len.init(c, out_len_u, (size_t)U, "p_out_len");
   if (U > 0) {
+    c->mark("predict: begin");
     PredGeom g = predict_geometry(c, N);
     RPK_REQUIRE(U * (int64_t)g.P < ((int64_t)1 << 31), "too many (user, item range) work items in one call; split the batch");
     ensure_segments(c, g);
@@ -2047,9 +2094,11 @@ void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr_
       RPK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_predict_a32, g2.nt, g2.smem));
       RPK_REQUIRE(occ >= 1, "predict kernel does not fit on an SM");
       const int grid = (int)std::min<int64_t>(U * g2.P, (int64_t)c->sm_count * occ);
+      c->mark("predict: layout + work table");
       c->ev_record(4);
       k_predict_a32<<<grid, g2.nt, g2.smem, st>>>(qp);
       RPK_LAUNCH_CHECK(c);
+      c->mark("predict: scoring kernel");
       if (lists_only) {
         // order the per-range lists; users whose order the approximate sums cannot prove are scored again, exactly
         const int mgrid = (int)std::min<int64_t>(ceil_div(U, MERGE_WARPS), (int64_t)c->sm_count * 16);
@@ -2071,6 +2120,7 @@ void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr_
       launch_predict_kernel(c, pp, g, U);
       c->ev_record(5);
       c->ev_valid[2] = true;
+      c->mark("predict: merge + exact passes");
 #ifdef RPK_PHASE_PROF
       {
         unsigned long long h[16];
@@ -2104,6 +2154,7 @@ void run_predict_topn(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr_
       RPK_LAUNCH_CHECK(c);
     }
   }
+  c->mark("predict: final lists");
   o_idx.finish(c);
   o_val.finish(c);
   o_len.finish(c);

@@ -49,6 +49,7 @@ class ShardExchange:
         self.g_len = mk((self.world, self.maxrows), torch.int32, 0)
         self.p_ent = mk((self.maxrows, K), torch.int64, -1)  # packed model rows (uint64 bit patterns), all-ones = unused
         self.g_ent = mk((self.world, self.maxrows, K), torch.int64, -1)
+        self.vmax = mk((1,), torch.float64, 0)  # largest similarity of the model (device scalar)
         self.all_idx = mk((I, K), torch.int32, -1)
         self.all_val = mk((I, K), torch.float64, 0)
         self.all_len = mk((I,), torch.int32, 0)
@@ -82,19 +83,16 @@ class ShardExchange:
         """Exchange in the model's own format: this rank's lists (filled through local_out()) are packed into
         model rows (rpk_model_pack_rows; 8 bytes per entry, already in column order) and all-gathered together with
         the row lengths.  Returns ([world * maxrows, K] int64, [world * maxrows] int32) for
-        rpk_model_load_packed_rows + row_source(); the common scale exponent is left in self.scale_exp.  With
-        engine=None the caller has filled p_ent (and scale_exp) itself."""
+        rpk_model_load_packed_rows_v + row_source(); the model's largest value is left in self.vmax (device).  With
+        engine=None the caller has filled p_ent (and vmax) itself."""
         rows = self.cuts[self.rank + 1] - self.cuts[self.rank]
         if engine is not None:
-            # one fixed-point scale for the whole model: the smallest exponent (largest similarity) of any rank
-            import torch
-
-            e = torch.tensor([engine.model_scale_exp(self.K, self.p_val[:rows], self.p_len[:rows])], dtype=torch.int32,
-                             device=self.p_len.device)
-            self.dist.all_reduce(e, op=self.dist.ReduceOp.MIN)
-            self.scale_exp = int(e.item())
-            engine.model_pack_rows(self.cuts[-1], self.K, self.p_idx[:rows], self.p_val[:rows], self.p_len[:rows],
-                                   self.scale_exp, out=self.p_ent[:rows])
+            # one fixed-point scale for the whole model: the largest similarity of any rank, all-reduced on the stream
+            # (a device scalar: no host round trip anywhere in the exchange)
+            engine.model_vmax(self.K, self.p_val[:rows], self.p_len[:rows], self.vmax)
+            self.dist.all_reduce(self.vmax, op=self.dist.ReduceOp.MAX)
+            engine.model_pack_rows_v(self.cuts[-1], self.K, self.p_idx[:rows], self.p_val[:rows], self.p_len[:rows], self.vmax,
+                                     self.p_ent[:rows])
         self.dist.all_gather_into_tensor(self.g_ent.view(-1, self.K), self.p_ent)
         self.dist.all_gather_into_tensor(self.g_len.view(-1), self.p_len)
         return self.g_ent.view(-1, self.K), self.g_len.view(-1)

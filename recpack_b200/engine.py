@@ -94,6 +94,14 @@ class Engine:
     def sync(self):
         self._check(self._lib.rpk_sync(self._h))
 
+    def trace(self, on: bool = True):
+        """rpk_trace: record named marks at the phase boundaries of every later call."""
+        self._check(self._lib.rpk_trace(self._h, int(bool(on))))
+
+    def trace_report(self) -> str:
+        """rpk_trace_report: 'name  ms since the previous mark' lines of the marks since the last report."""
+        return self._lib.rpk_trace_report(self._h).decode()
+
     def launch_count(self) -> int:
         return int(self._lib.rpk_launch_count(self._h))
 
@@ -212,6 +220,21 @@ class Engine:
     def model_load_packed_rows(self, I, K, rows_in, ent, ln, scale_exp, row_src=None):
         self._check(self._lib.rpk_model_load_packed_rows(self._h, int(I), int(K), int(rows_in), _addr(ent), _addr(ln, np.int32),
                                                          _addr(row_src, np.int64, allow_none=True), int(scale_exp)))
+
+    def model_vmax(self, K, val, ln, out):
+        """rpk_model_vmax: the largest value of the lists into `out` (one float64, device tensor: stream-ordered)."""
+        self._check(self._lib.rpk_model_vmax(self._h, int(K), int(val.shape[0]), _addr(val, np.float64), _addr(ln, np.int32),
+                                             _addr(out, np.float64)))
+        return out
+
+    def model_pack_rows_v(self, I, K, idx, val, ln, vmax, out):
+        self._check(self._lib.rpk_model_pack_rows_v(self._h, int(I), int(K), int(idx.shape[0]), _addr(idx, np.int32),
+                                                    _addr(val, np.float64), _addr(ln, np.int32), _addr(vmax, np.float64), _addr(out)))
+        return out
+
+    def model_load_packed_rows_v(self, I, K, rows_in, ent, ln, vmax, row_src=None):
+        self._check(self._lib.rpk_model_load_packed_rows_v(self._h, int(I), int(K), int(rows_in), _addr(ent), _addr(ln, np.int32),
+                                                           _addr(row_src, np.int64, allow_none=True), _addr(vmax, np.float64)))
 
     def fit_token(self) -> int:
         return int(self._lib.rpk_fit_token(self._h))

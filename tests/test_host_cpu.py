@@ -31,7 +31,8 @@ def test_library_loads_and_exports_every_symbol():
 
         __graft_entry__.build()
     lib = _lib.load()
-    assert lib.rpk_abi_version() == 1
+    header = open(os.path.join(ROOT, "include", "rpk.h")).read()
+    assert lib.rpk_abi_version() == int(re.search(r"#define RPK_ABI_VERSION (\d+)", header).group(1))
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for name in _header_symbols():
         assert hasattr(raw, name), name
