@@ -102,6 +102,27 @@ RPK_EXPORT int rpk_fit_topk(rpk_ctx* ctx, int64_t U, int64_t I, int64_t nnz,
                  int64_t item_begin, int64_t item_end,
                  int32_t* out_idx, int32_t* out_cnt, double* out_val, int32_t* out_len);
 
+/*
+ * Fit on a REAL-VALUED interaction matrix (values float64[nnz], one per stored entry, no explicit zeros):
+ * ItemKNN(normalize_X=True) (nearest_neighbour.py:207-210: values = 1/d_u), compute_pearson_similarity
+ * (nearest_neighbour.py:87-111: values = centred ratings) and the decayed matrices of the TARSItemKNN family
+ * (time_aware_item_knn/base.py:166-201) reach the similarity functions with such a matrix.
+ *
+ *   similarity = RPK_SIM_COSINE:   s_ij = sum over users u (ascending) of fl(xh_ui * xh_uj), xh = x / ||x_.i||_2 with
+ *                                  the norm as sklearn computes it (sequential sum of squares, sqrt, divide)
+ *   similarity = RPK_SIM_CONDPROB: g_ij = sum over users of item i (ascending) of x_uj; s_ij = fl(fl(1/n_i) * g_ij)
+ *                                  [* item_pow[j]], n_i = stored entries of column i (to_binary(X), :48-51)
+ * Sums are float64 in the reference's operation order (scipy csr_matmat), so the values are bit-identical to the
+ * reference's; sums that are exactly zero are not stored.  Per row the K best stored entries are kept by
+ * (value descending, item ascending); the diagonal's explicit zero (setdiag, :64,81) competes and is then dropped,
+ * as in get_top_K_values (util.py:80-96).  Outputs as rpk_fit_topk (no counts).  Deterministic.
+ */
+RPK_EXPORT int rpk_fit_topk_real(rpk_ctx* ctx, int64_t U, int64_t I, int64_t nnz,
+                      const int64_t* indptr, const int32_t* indices, const double* values,
+                      int similarity, const double* item_pow, int K,
+                      int64_t item_begin, int64_t item_end,
+                      int32_t* out_idx, double* out_val, int32_t* out_len);
+
 /* Item popularities n_j of the matrix passed to the last rpk_fit_topk (int32[I]). */
 RPK_EXPORT int rpk_fit_item_counts(rpk_ctx* ctx, int32_t* out_counts, int64_t I);
 

@@ -509,6 +509,68 @@ def canon_top_k_ranks(Y: csr_matrix, K) -> csr_matrix:
 
 
 # --------------------------------------------------------------------------
+# Real-valued interaction matrices: ItemKNN(normalize_X=True), Pearson
+# --------------------------------------------------------------------------
+def ref_normalize_X(X) -> csr_matrix:
+    """nearest_neighbour.py:205-210 after the binarising wrapper (base.py:129-139): l1-normalised binary rows."""
+    from sklearn.preprocessing import Normalizer
+
+    X = csr_matrix(X)
+    X = X.astype(bool).astype(X.dtype)
+    return Normalizer(norm="l1", copy=False).transform(X)
+
+
+def ref_pearson(X: csr_matrix) -> csr_matrix:
+    """nearest_neighbour.py:87-111 -- cosine of the matrix centred per item over its positive entries."""
+    if (X == 1).sum() == X.nnz:
+        raise ValueError("Pearson similarity can not be computed on a binary matrix.")
+    count = (X > 0).sum(axis=0).A
+    avg = X.sum(axis=0).A.astype(float)
+    avg[count > 0] = avg[count > 0] / count[count > 0]
+    X = X - (X > 0).multiply(avg)
+    return ref_cosine(csr_matrix(X))
+
+
+def ref_real_full(X, similarity="cosine", pop_discount=None) -> csr_matrix:
+    """The full item x item matrix of a real-valued X, as compute_cosine_similarity / compute_conditional_probability
+    return it (explicit zeros on the diagonal)."""
+    X = csr_matrix(X)
+    if similarity == "cosine":
+        return csr_matrix(ref_cosine(X))
+    if similarity == "conditional_probability":
+        return csr_matrix(ref_conditional_probability(X, pop_discount))
+    if similarity == "pearson":
+        return csr_matrix(ref_pearson(X))
+    raise ValueError(f"similarity {similarity} not supported")
+
+
+def canon_topk_of_full(full: csr_matrix, K: int):
+    """Canonical get_top_K_values (util.py:50-96) of a full similarity matrix: per row the min(K, stored) best STORED
+    entries by (value descending, item ascending) -- explicit zeros such as the diagonal compete (util.py:63-68) --
+    and entries equal to zero then drop out of the product (util.py:96).  Returns dict(idx, val, len), rank order."""
+    full = csr_matrix(full)
+    rows = full.shape[0]
+    idx = np.full((rows, K), -1, dtype=np.int32)
+    val = np.zeros((rows, K), dtype=np.float64)
+    ln = np.zeros(rows, dtype=np.int32)
+    for r in range(rows):
+        lo, hi = full.indptr[r], full.indptr[r + 1]
+        cols = full.indices[lo:hi]
+        vals = full.data[lo:hi].astype(np.float64)
+        order = np.lexsort((cols, -vals))[: min(K, hi - lo)]
+        keep = order[vals[order] != 0.0]
+        ln[r] = keep.size
+        idx[r, : keep.size] = cols[keep]
+        val[r, : keep.size] = vals[keep]
+    return {"idx": idx, "val": val, "len": ln}
+
+
+def canon_fit_real(X, K, similarity="cosine", pop_discount=None):
+    """Canonical top-K of the reference's own float64 similarity values for a real-valued X."""
+    return canon_topk_of_full(ref_real_full(X, similarity, pop_discount), K)
+
+
+# --------------------------------------------------------------------------
 # Tie-aware comparison against the unmodified reference (SURVEY.md 8c (3))
 # --------------------------------------------------------------------------
 def compare_topk_tie_aware(ref_S: csr_matrix, got, Xb: csr_matrix, similarity="cosine", rel=1e-5):

@@ -23,6 +23,8 @@ _SIGNATURES = {
     "rpk_debug_flags": (C.c_int, [C.c_void_p, C.c_int]),
     "rpk_fit_topk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, _i64p, _i32p, C.c_int, _f64p, C.c_int,
                                C.c_int64, C.c_int64, _i32p, _i32p, _f64p, _i32p]),
+    "rpk_fit_topk_real": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, _i64p, _i32p, _f64p, C.c_int, _f64p, C.c_int,
+                                    C.c_int64, C.c_int64, _i32p, _f64p, _i32p]),
     "rpk_fit_item_counts": (C.c_int, [C.c_void_p, _i32p, C.c_int64]),
     "rpk_model_load_topk": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, _i32p, _f64p, _i32p]),
     "rpk_model_load_topk_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int64, _i32p, _f64p, _i32p, _i64p]),

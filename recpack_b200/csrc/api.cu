@@ -108,6 +108,15 @@ int rpk_fit_topk(rpk_ctx* ctx, int64_t U, int64_t I, int64_t nnz, const int64_t*
   RPK_API_END(ctx)
 }
 
+int rpk_fit_topk_real(rpk_ctx* ctx, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                      const double* values, int similarity, const double* item_pow, int K, int64_t item_begin,
+                      int64_t item_end, int32_t* out_idx, double* out_val, int32_t* out_len) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_fit_real(ctx, U, I, nnz, indptr, indices, values, similarity, item_pow, K, item_begin, item_end, out_idx, out_val,
+                    out_len);
+  RPK_API_END(ctx)
+}
+
 int rpk_fit_item_counts(rpk_ctx* ctx, int32_t* out_counts, int64_t I) {
   RPK_API_BEGIN(ctx)
   rpk::run_fit_item_counts(ctx, out_counts, I);

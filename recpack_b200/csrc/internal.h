@@ -9,6 +9,9 @@ namespace rpk {
 void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices, int similarity,
              const double* item_pow, int K, int64_t item_begin, int64_t item_end, int32_t* out_idx, int32_t* out_cnt,
              double* out_val, int32_t* out_len);
+void run_fit_real(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices,
+                  const double* values, int similarity, const double* item_pow, int K, int64_t item_begin, int64_t item_end,
+                  int32_t* out_idx, double* out_val, int32_t* out_len);
 void run_fit_item_counts(rpk_ctx* c, int32_t* out_counts, int64_t I);
 
 void run_model_load_topk(rpk_ctx* c, int64_t I, int K, const int32_t* idx, const double* val, const int32_t* len);

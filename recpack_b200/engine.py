@@ -110,12 +110,8 @@ class Engine:
 
     # -- fit ------------------------------------------------------------------------------
     def fit_topk(self, U, I, indptr, indices, K, similarity="cosine", item_pow=None, item_begin=0, item_end=None,
-                 want_cnt=True, want_val=True, out=None, normalize_X=False):
-        """rpk_fit_topk.  Returns dict(idx, cnt, val, len); rows in rank order."""
-        if normalize_X:
-            # l1-normalised rows make X real-valued; the GPU Gram is defined on exact integer counts
-            # (SURVEY.md 8f-2).  No silent CPU path: say so.
-            raise NotImplementedError("normalize_X=True is not implemented on the B200 path yet")
+                 want_cnt=True, want_val=True, out=None):
+        """rpk_fit_topk (binary X).  Returns dict(idx, cnt, val, len); rows in rank order."""
         item_end = I if item_end is None else item_end
         rows = item_end - item_begin
         nnz = int(indices.shape[0])
@@ -131,6 +127,24 @@ class Engine:
             _addr(item_pow, np.float64, allow_none=True), int(K), int(item_begin), int(item_end),
             _addr(out["idx"], np.int32), _addr(out.get("cnt"), np.int32, allow_none=True),
             _addr(out.get("val"), np.float64, allow_none=True), _addr(out["len"], np.int32)))
+        return out
+
+    def fit_topk_real(self, U, I, indptr, indices, values, K, similarity="cosine", item_pow=None, item_begin=0,
+                      item_end=None, out=None):
+        """rpk_fit_topk_real (real-valued X: one float64 per stored entry).  Returns dict(idx, val, len)."""
+        item_end = I if item_end is None else item_end
+        rows = item_end - item_begin
+        nnz = int(indices.shape[0])
+        if out is None:
+            out = {
+                "idx": _empty_like_kind(indices, (rows, K), np.int32),
+                "val": _empty_like_kind(indices, (rows, K), np.float64),
+                "len": _empty_like_kind(indices, (rows,), np.int32),
+            }
+        self._check(self._lib.rpk_fit_topk_real(
+            self._h, U, I, nnz, _addr(indptr, np.int64), _addr(indices, np.int32), _addr(values, np.float64),
+            SIM_CODES[similarity], _addr(item_pow, np.float64, allow_none=True), int(K), int(item_begin), int(item_end),
+            _addr(out["idx"], np.int32), _addr(out["val"], np.float64), _addr(out["len"], np.int32)))
         return out
 
     def fit_item_counts(self, I, like=None):

@@ -60,8 +60,18 @@ class ItemKNN(GpuSimilarityMixin, _ItemKNNBase):
         K = int(self.K)
         # the rank-ordered lists stay on the device (torch tensors owned by this estimator); similarity_matrix_
         # is built from them on first use
-        out = engine.fit_topk(U, I, ptr_d, idx_d, K, similarity=self.similarity, item_pow=item_pow, want_cnt=False,
-                              normalize_X=bool(self.normalize_X))
+        if self.normalize_X:
+            # Normalizer(norm="l1") on the binary rows (nearest_neighbour.py:207-210): every entry of user u becomes
+            # fl(1 / d_u); the real-valued Gram kernel sums in the reference's order (rpk_fit_topk_real)
+            import torch
+
+            d = ptr_d[1:] - ptr_d[:-1]
+            values = torch.repeat_interleave(1.0 / d.to(torch.float64), d)
+            torch.cuda.current_stream(values.device).synchronize()  # the library runs on its own stream
+            out = engine.fit_topk_real(U, I, ptr_d, idx_d, values, K, similarity=self.similarity, item_pow=item_pow)
+            out["cnt"] = None
+        else:
+            out = engine.fit_topk(U, I, ptr_d, idx_d, K, similarity=self.similarity, item_pow=item_pow, want_cnt=False)
         if self.normalize_sim:
             # Normalizer(norm="l1") over the kept entries of each row (nearest_neighbour.py:220-222), on the host
             idx, val, ln = to_host(out["idx"], out["val"], out["len"])
@@ -71,3 +81,31 @@ class ItemKNN(GpuSimilarityMixin, _ItemKNNBase):
             self.similarity_matrix_ = lists_to_csr(idx, np.ascontiguousarray(val / row_sum[:, None]), ln, I)
         else:
             self._set_device_fit(out, I, engine.device)
+
+
+def pearson_top_k(X: csr_matrix, K: int) -> csr_matrix:
+    """``get_top_K_values(compute_pearson_similarity(X), K)`` (nearest_neighbour.py:87-111, util.py:80-96) without the
+    item x item matrix: ratings are centred per item over the positive entries, the cosine Gram of the centred matrix and
+    the per-row selection run on the GPU (rpk_fit_topk_real).  Similarities can be negative, so the result is a similarity
+    matrix for inspection / the TARSItemKNN family, not a model for the fixed-point scorer of ``ItemKNN.predict``."""
+    if not isinstance(X, csr_matrix):
+        raise TypeError("pearson_top_k expects a scipy csr_matrix")
+    X = X.astype(np.float64).tocsr()
+    X.sum_duplicates()
+    X.eliminate_zeros()
+    if (X.data == 1).sum() == X.nnz:
+        raise ValueError("Pearson similarity can not be computed on a binary matrix.")
+    U, I = X.shape
+    pos = X.data > 0
+    count = np.bincount(X.indices[pos], minlength=I)
+    avg = np.bincount(X.indices, weights=X.data, minlength=I).astype(np.float64)
+    nz = count > 0
+    avg[nz] = avg[nz] / count[nz]
+    data = X.data.copy()
+    data[pos] = data[pos] - avg[X.indices[pos]]
+    C = csr_matrix((data, X.indices.copy(), X.indptr.copy()), shape=X.shape)
+    C.eliminate_zeros()  # the sparse subtraction of the reference stores no zero results
+    engine = get_engine()
+    out = engine.fit_topk_real(U, I, np.ascontiguousarray(C.indptr, dtype=np.int64), np.ascontiguousarray(C.indices, dtype=np.int32),
+                               np.ascontiguousarray(C.data, dtype=np.float64), int(K), similarity="cosine")
+    return lists_to_csr(out["idx"], out["val"], out["len"], I)

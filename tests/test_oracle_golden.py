@@ -217,3 +217,60 @@ def test_precision_and_reciprocal_rank_vs_reference():
     # test_reciprocal_rank.py:14-19)
     np.testing.assert_almost_equal(float(g["true_precision2_value"]), 0.75)
     np.testing.assert_almost_equal(float(g["true_reciprocal_rank2_value"]), 0.75)
+
+
+# ---- real-valued interaction matrices (ItemKNN(normalize_X=True), Pearson): fixtures of tests/golden/make_golden_real.py
+REAL_NORMX = ["real_unit_normx_cosine", "real_unit_normx_condprob", "real_small_normx_cosine", "real_small_normx_condprob",
+              "real_small_normx_condprob_pd", "real_mid_normx_cosine"]
+REAL_PEARSON = ["real_unit_pearson", "real_small_pearson"]
+
+
+def _kept_sets_tie_aware(canon, ref_S, full, K):
+    """Row by row: same number of kept entries, same multiset of values, and every item picked by only one side carries
+    the boundary value (the reference's introselect breaks ties arbitrarily)."""
+    ref_S, full = csr_matrix(ref_S), csr_matrix(full)
+    for r in range(full.shape[0]):
+        n = int(canon["len"][r])
+        mine = dict(zip(canon["idx"][r, :n].tolist(), canon["val"][r, :n].tolist()))
+        lo, hi = ref_S.indptr[r], ref_S.indptr[r + 1]
+        theirs = dict(zip(ref_S.indices[lo:hi].tolist(), ref_S.data[lo:hi].tolist()))
+        assert len(mine) == len(theirs), r
+        assert sorted(mine.values()) == sorted(theirs.values()), r
+        only = set(mine) ^ set(theirs)
+        if only:
+            boundary = min(mine.values())
+            for j in only:
+                assert (mine.get(j, theirs.get(j))) == boundary, (r, j)
+        for j in set(mine) & set(theirs):
+            assert mine[j] == theirs[j]
+
+
+@pytest.mark.parametrize("name", REAL_NORMX)
+def test_real_valued_oracle_reproduces_reference_normalize_X(name):
+    g = load_golden(name)
+    K, sim, pd_ = _params(g)
+    full = orc.ref_real_full(orc.ref_normalize_X(unpack(g, "X")), sim, pd_)
+    assert _same_csr(full, unpack(g, "full"))
+    S = orc.ref_fit(unpack(g, "X"), K=K, similarity=sim, pop_discount=pd_, normalize_X=True)
+    assert _same_csr(S, unpack(g, "S"))
+    _kept_sets_tie_aware(orc.canon_topk_of_full(unpack(g, "full"), K), unpack(g, "S"), unpack(g, "full"), K)
+
+
+@pytest.mark.parametrize("name", REAL_PEARSON)
+def test_real_valued_oracle_reproduces_reference_pearson(name):
+    g = load_golden(name)
+    K = int(g["K"])
+    full = orc.ref_real_full(unpack(g, "X"), "pearson")
+    assert _same_csr(full, unpack(g, "full"))
+    _kept_sets_tie_aware(orc.canon_topk_of_full(unpack(g, "full"), K), unpack(g, "S"), unpack(g, "full"), K)
+
+
+def test_normalize_X_closed_form():
+    """recpack/tests/test_algorithms/test_nearest_neighbour.py:73-107."""
+    g = load_golden("real_unit_normx_cosine")
+    got = orc.canon_topk_of_full(unpack(g, "full"), 2)
+    S = orc.topk_to_csr(got["idx"], got["val"], got["len"], 3).toarray()
+    a, b = 1 / 9, 1 / 9 + 1 / 4
+    d = math.sqrt(1 / 4 + 1 / 9)
+    f = math.sqrt(2 / 4 + 1 / 9)
+    np.testing.assert_almost_equal(S, [[0, a / (d * d), b / (d * f)], [a / (d * d), 0, b / (d * f)], [b / (d * f), b / (d * f), 0]])
