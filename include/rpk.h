@@ -282,6 +282,11 @@ RPK_EXPORT const char* rpk_trace_report(rpk_ctx* ctx);
  * tensor-core Gram (0 = none, -1 = automatic, at most 4096); the remaining users go through the
  * sparse kernel.  The result of rpk_fit_topk does not depend on this setting. */
 RPK_EXPORT int rpk_fit_config(rpk_ctx* ctx, int dense_users);
+/* rpk_fit_topk runs its item rows in strips so that only one strip of the dense leg's count matrix (uint16,
+ * rows x I) exists at a time -- the item x item matrix is never materialised as a whole.  rows: rows per strip
+ * (rounded down to a multiple of 128, at least 128); 0 = automatic (a strip of at most 8 GB).  The result does not
+ * depend on this setting. */
+RPK_EXPORT int rpk_fit_strip_rows(rpk_ctx* ctx, int64_t rows);
 
 #ifdef __cplusplus
 }

@@ -281,13 +281,24 @@ int rpk_last_timings(rpk_ctx* ctx, double* out_ms) {
   RPK_API_BEGIN(ctx)
   if (!out_ms) throw rpk::Error("out_ms must not be null");
   RPK_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 0; k < 2; ++k) {  // fit: sums over the strips
     out_ms[k] = -1.0;
-    if (ctx->ev_valid[k]) {
+    double sum = 0.0;
+    bool any = false;
+    for (auto& pr : ctx->spans[k]) {
+      if (!pr.second) continue;
       float ms = 0.f;
-      RPK_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2 * k], ctx->ev[2 * k + 1]));
-      out_ms[k] = ms;
+      RPK_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+      sum += ms;
+      any = true;
     }
+    if (any) out_ms[k] = sum;
+  }
+  out_ms[2] = -1.0;
+  if (ctx->ev_valid[2]) {
+    float ms = 0.f;
+    RPK_CUDA(cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]));
+    out_ms[2] = ms;
   }
   out_ms[3] = ctx->last_dense_users;
   out_ms[4] = ctx->last_dense_kd;
@@ -325,6 +336,13 @@ int rpk_fit_config(rpk_ctx* ctx, int dense_users) {
   RPK_API_BEGIN(ctx)
   if (dense_users < -1 || dense_users > 4096) throw rpk::Error("dense_users must be in [-1, 4096]");
   ctx->dense_users = dense_users;
+  RPK_API_END(ctx)
+}
+
+int rpk_fit_strip_rows(rpk_ctx* ctx, int64_t rows) {
+  RPK_API_BEGIN(ctx)
+  if (rows < 0) throw rpk::Error("rows must be >= 0");
+  ctx->strip_rows = rows;
   RPK_API_END(ctx)
 }
 

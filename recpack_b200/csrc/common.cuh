@@ -71,6 +71,36 @@ struct rpk_ctx {
     if (!ev[k]) RPK_CUDA(cudaEventCreate(&ev[k]));
     RPK_CUDA(cudaEventRecord(ev[k], stream));
   }
+  // A fit runs its row range in strips: the tensor-core Gram (k = 0) and the row kernels (k = 1) are timed as the
+  // sum of one (begin, end) event pair per strip.
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> spans[2];
+  std::vector<cudaEvent_t> span_pool;
+  cudaEvent_t span_event() {
+    cudaEvent_t e = nullptr;
+    if (!span_pool.empty()) {
+      e = span_pool.back();
+      span_pool.pop_back();
+    } else {
+      RPK_CUDA(cudaEventCreate(&e));
+    }
+    RPK_CUDA(cudaEventRecord(e, stream));
+    return e;
+  }
+  void span_reset() {
+    for (auto& v : spans) {
+      for (auto& pr : v) {
+        span_pool.push_back(pr.first);
+        if (pr.second) span_pool.push_back(pr.second);
+      }
+      v.clear();
+    }
+  }
+  void span_begin(int k) { spans[k].emplace_back(span_event(), nullptr); }
+  void span_end(int k) { spans[k].back().second = span_event(); }
+  // strip state of the running fit (see run_fit): the dense / sparse split chosen by strip 0
+  int strip_hmax = 0;
+  int strip_tau = 32;
+  int64_t strip_rows = 0;  // rows per strip, 0 = automatic (rpk_fit_strip_rows)
   // ---- tracing (rpk_trace): named marks on the context's stream, reported as the device time between neighbours
   bool tracing = false;
   std::vector<std::pair<std::string, cudaEvent_t>> marks;

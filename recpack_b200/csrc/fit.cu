@@ -1283,9 +1283,14 @@ static int next_pow2(int v) {
   return p;
 }
 
-void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr_u, const int32_t* indices_u,
-             int similarity, const double* item_pow_u, int K, int64_t item_begin, int64_t item_end, int32_t* out_idx_u,
-             int32_t* out_cnt_u, double* out_val_u, int32_t* out_len_u) {
+// One contiguous block of item rows [item_begin, item_end).  `strip` > 0: a later strip of the same fit
+// (run_fit cuts a large row range into strips so that only one strip of the dense-leg counts exists at a time):
+// item counts, the dense/sparse split, the dense slots and the dense operand of strip 0 are reused.
+// `rows_total` is the row count of the whole fit (the split is chosen for all of it).
+static void fit_range(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr_u, const int32_t* indices_u,
+                      int similarity, const double* item_pow_u, int K, int64_t item_begin, int64_t item_end,
+                      int32_t* out_idx_u, int32_t* out_cnt_u, double* out_val_u, int32_t* out_len_u, int strip,
+                      int64_t rows_total) {
   RPK_REQUIRE(U >= 0 && I >= 0 && nnz >= 0, "negative dimension");
   RPK_REQUIRE(I < (int64_t)1 << 24, "more than 2^24 items are not supported");
   RPK_REQUIRE(U < (int64_t)1 << 31, "more than 2^31 users are not supported");
@@ -1314,11 +1319,11 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
   int* boff = bcnt + 65;
   (void)boff;
   c->fit_I = I;
-  RPK_CUDA(cudaMemsetAsync(n, 0, sizeof(int) * (size_t)I, st));
+  if (strip == 0) RPK_CUDA(cudaMemsetAsync(n, 0, sizeof(int) * (size_t)I, st));
   RPK_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)I, st));
   RPK_CUDA(cudaMemsetAsync(work, 0, sizeof(u64) * (size_t)I, st));
   RPK_CUDA(cudaMemsetAsync(bcnt, 0, sizeof(int) * (65 * 2 + 2), st));
-  if (nnz > 0) {
+  if (nnz > 0 && strip == 0) {
     int blocks = (int)std::min<int64_t>((nnz + 255) / 256, (int64_t)c->sm_count * 16);
     k_item_counts<<<blocks, 256, 0, st>>>(indices, nnz, n);
     RPK_LAUNCH_CHECK(c);
@@ -1328,15 +1333,15 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
   int hmax = c->dense_users;
   const int64_t rows_pad = (I + 255) / 256 * 256;
   const bool dense_auto = hmax < 0;
-  if (dense_auto) {
-    const double g16_bytes = (double)nrows * (double)rows_pad * 2.0;
-    hmax = (I >= 4096 && U >= 8192 && g16_bytes <= 16e9) ? 4096 : 0;
-  }
+  if (dense_auto) hmax = (I >= 4096 && U >= 8192) ? 4096 : 0;
   if (hmax > U) hmax = (int)U;
   if (nnz == 0 || I < 2 || nrows == 0) hmax = 0;
   int dense_tau = 32;  // histories shorter than this are never worth a dense column
   int* lhist = nullptr;
-  if (hmax > 0) {
+  if (strip > 0) {
+    hmax = c->strip_hmax;
+    dense_tau = c->strip_tau;
+  } else if (hmax > 0) {
     lhist = c->buf<int>("fit_len_hist", (size_t)I + 2);
     RPK_CUDA(cudaMemsetAsync(lhist, 0, sizeof(int) * ((size_t)I + 2), st));
     k_len_hist<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, I, lhist);
@@ -1347,9 +1352,9 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     std::vector<int> h((size_t)I + 1);
     RPK_CUDA(cudaMemcpyAsync(h.data(), lhist, sizeof(int) * ((size_t)I + 1), cudaMemcpyDeviceToHost, st));
     RPK_CUDA(cudaStreamSynchronize(st));
-    const double share = (double)nrows / (double)I;
+    const double share = (double)rows_total / (double)I;
     const double dense_rate = 1.6e15, sparse_rate = 7e11, hbm = 5e12;  // measured on B200 (profiles/r1_summary.md)
-    const double fixed = (double)nrows * (double)rows_pad * 4.0 / hbm;
+    const double fixed = (double)rows_total * (double)rows_pad * 4.0 / hbm;
     double best_gain = 0.0, saved = 0.0;
     int best_h = 0, best_tau = 0;
     int64_t taken = 0;
@@ -1360,7 +1365,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
       taken += cnt_d;
       saved += (double)cnt_d * (double)d * (double)d * share / sparse_rate;
       const double kd = (double)((taken + 127) / 128 * 128);
-      const double cost = 2.0 * kd * (double)nrows * (double)rows_pad / dense_rate + fixed;
+      const double cost = 2.0 * kd * (double)rows_total * (double)rows_pad / dense_rate + fixed;
       const double gain = saved - cost;
       if (!dense_auto || gain > best_gain) {  // a fixed request takes as many users as allowed
         best_gain = gain;
@@ -1371,12 +1376,12 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     hmax = best_h;
     dense_tau = best_tau;
   }
+  c->strip_hmax = hmax;
+  c->strip_tau = dense_tau;
   c->mark("fit: item counts + split");
   const int* dense_slot = nullptr;
   const unsigned short* g16 = nullptr;
   const int* n_sparse = n;  // per-item user counts on the sparse path
-  c->ev_valid[0] = false;
-  c->ev_valid[1] = false;
   c->last_dense_users = hmax;
   c->last_dense_kd = hmax > 0 ? (int)(((int64_t)hmax + 127) / 128 * 128) : 0;
   if (hmax > 0) {
@@ -1388,21 +1393,22 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     // only this shard's item rows of the dense Gram are needed (row block aligned down to the 128-row tile)
     const int64_t g_row0 = item_begin / 128 * 128;
     unsigned short* G = c->buf<unsigned short>("fit_dense_G", (size_t)(item_end - g_row0 + 1) * rows_pad);
-    const int thr_init[2] = {dense_tau, 0};
-    RPK_CUDA(cudaMemcpyAsync(thr_cnt, thr_init, sizeof(thr_init), cudaMemcpyHostToDevice, st));
-    RPK_CUDA(cudaMemcpyAsync(n_light, n, sizeof(int) * (size_t)I, cudaMemcpyDeviceToDevice, st));
-    RPK_CUDA(cudaMemsetAsync(A, 0, (size_t)rows_pad * kd_pad, st));
-    int* dense_user = c->buf<int>("fit_dense_user", (size_t)hmax);
-    k_assign_dense_slots<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, thr_cnt, hmax, slot, dense_user);
-    RPK_LAUNCH_CHECK(c);
-    k_fill_dense_users<<<hmax, 256, 0, st>>>(indptr, indices, dense_user, thr_cnt, kd_pad, A, n_light);
-    RPK_LAUNCH_CHECK(c);
-    c->mark("fit: dense operand");
-    c->ev_record(0);
+    if (strip == 0) {
+      const int thr_init[2] = {dense_tau, 0};
+      RPK_CUDA(cudaMemcpyAsync(thr_cnt, thr_init, sizeof(thr_init), cudaMemcpyHostToDevice, st));
+      RPK_CUDA(cudaMemcpyAsync(n_light, n, sizeof(int) * (size_t)I, cudaMemcpyDeviceToDevice, st));
+      RPK_CUDA(cudaMemsetAsync(A, 0, (size_t)rows_pad * kd_pad, st));
+      int* dense_user = c->buf<int>("fit_dense_user", (size_t)hmax);
+      k_assign_dense_slots<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, thr_cnt, hmax, slot, dense_user);
+      RPK_LAUNCH_CHECK(c);
+      k_fill_dense_users<<<hmax, 256, 0, st>>>(indptr, indices, dense_user, thr_cnt, kd_pad, A, n_light);
+      RPK_LAUNCH_CHECK(c);
+      c->mark("fit: dense operand");
+    }
+    c->span_begin(0);
     run_gram_dense_tc(c, A, rows_pad, kd_pad, g_row0, item_end, G, rows_pad);
-    c->ev_record(1);
+    c->span_end(0);
     c->mark("fit: tensor-core Gram");
-    c->ev_valid[0] = true;
     dense_slot = slot;
     g16 = G - g_row0 * rows_pad;  // indexed by absolute item row in the fit kernel
     n_sparse = n_light;
@@ -1492,7 +1498,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     const size_t code_bytes = use_code ? (((size_t)I + 8 * 64 + 15) & ~(size_t)15) : 0;
 
     c->mark("fit: CSC + order + heavy");
-    c->ev_record(2);
+    c->span_begin(1);
     const int defer_max = cap;
     int* scr_idx = c->buf<int>("fit_scr_idx", (size_t)nrows * defer_max);
     int* scr_cnt = c->buf<int>("fit_scr_cnt", (size_t)nrows * defer_max);
@@ -1662,8 +1668,7 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     }
 #endif
     c->mark("fit: row kernels");
-    c->ev_record(3);  // the row kernels end here (rpk_last_timings); the deferred sort is timed with the rest of the fit
-    c->ev_valid[1] = true;
+    c->span_end(1);  // the row kernels end here (rpk_last_timings); the deferred sort is timed with the rest of the fit
     if (any_deferred) {
       SortParams sp;
       sp.sk = sk;
@@ -1692,6 +1697,42 @@ void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indpt
     }
   }
   c->mark("fit: sort + values");
+}
+
+// The public fit: stages the inputs and outputs once and runs the row range in strips of at most `strip_rows` rows, so
+// that only one strip of the dense-leg count matrix (uint16, rows x I) exists at a time: the item x item matrix is
+// never materialised as a whole (an 80 GB object at I = 200,000) and the tensor-core leg stays on for large catalogues.
+void run_fit(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr_u, const int32_t* indices_u,
+             int similarity, const double* item_pow_u, int K, int64_t item_begin, int64_t item_end, int32_t* out_idx_u,
+             int32_t* out_cnt_u, double* out_val_u, int32_t* out_len_u) {
+  RPK_REQUIRE(U >= 0 && I >= 0 && nnz >= 0, "negative dimension");
+  RPK_REQUIRE(K >= 1 && K <= 4096, "K must be in [1, 4096]");
+  RPK_REQUIRE(0 <= item_begin && item_begin <= item_end && item_end <= I, "bad item range");
+  RPK_REQUIRE(out_idx_u && out_len_u, "out_idx / out_len must not be null");
+  const int64_t nrows = item_end - item_begin;
+  const int64_t* indptr = stage_in(c, indptr_u, (size_t)U + 1, "fit_indptr");
+  const int32_t* indices = stage_in(c, indices_u, (size_t)nnz, "fit_indices");
+  const double* pw = item_pow_u ? stage_in(c, item_pow_u, (size_t)I, "fit_pw") : nullptr;
+  Out<int32_t> o_idx, o_cnt, o_len;
+  Out<double> o_val;
+  o_idx.init(c, out_idx_u, (size_t)nrows * K, "fit_out_idx");
+  o_len.init(c, out_len_u, (size_t)nrows, "fit_out_len");
+  if (out_cnt_u) o_cnt.init(c, out_cnt_u, (size_t)nrows * K, "fit_out_cnt");
+  o_val.init(c, out_val_u, (size_t)nrows * K, "fit_out_val");
+  c->span_reset();
+  const int64_t rows_pad = (I + 255) / 256 * 256;
+  int64_t strip_rows = c->strip_rows > 0 ? c->strip_rows : (int64_t)(8e9 / ((double)rows_pad * 2.0));
+  strip_rows = std::max<int64_t>(128, strip_rows / 128 * 128);
+  if (c->dense_users == 0 || nrows <= strip_rows) strip_rows = std::max<int64_t>(nrows, 1);  // no dense leg: nothing to bound
+  int strip = 0;
+  for (int64_t b = item_begin; b < item_end || strip == 0; b += strip_rows, ++strip) {
+    const int64_t e = std::min(item_end, b + strip_rows);
+    const int64_t off = b - item_begin;
+    fit_range(c, U, I, nnz, indptr, indices, similarity, pw, K, b, e, o_idx.dev + off * K,
+              o_cnt.dev ? o_cnt.dev + off * K : nullptr, o_val.dev ? o_val.dev + off * K : nullptr, o_len.dev + off, strip,
+              nrows);
+    if (e >= item_end) break;
+  }
   // remember where the lists live on the device: predict can load its model from them without a round trip
   c->lf_token++;
   c->lf_idx = nullptr;

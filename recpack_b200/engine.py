@@ -162,6 +162,10 @@ class Engine:
     def fit_config(self, dense_users: int = -1):
         self._check(self._lib.rpk_fit_config(self._h, int(dense_users)))
 
+    def fit_strip_rows(self, rows: int = 0):
+        """rpk_fit_strip_rows: item rows per strip of the fit (0 = automatic)."""
+        self._check(self._lib.rpk_fit_strip_rows(self._h, int(rows)))
+
     def gram_dense_u16(self, A):
         """G = A A^T on the tensor cores for a 0/1 uint8 matrix A [I, Kd] (verification entry)."""
         I, Kd = A.shape

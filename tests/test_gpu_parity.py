@@ -176,6 +176,33 @@ def test_fit_hybrid_dense_users_gives_identical_results(engine, case, dense_user
     _assert_fit_equal(got, orc.canon_fit(X, K=K, similarity=sim, pop_discount=pd_))
 
 
+@pytest.mark.parametrize("flags", [0, 1, 4])
+@pytest.mark.parametrize("strip_rows,dense_users", [(128, 64), (256, 4096), (128, 0)])
+@pytest.mark.parametrize("case", [CASES[2], CASES[3], CASES[5]])
+def test_fit_in_row_strips_gives_identical_results(engine, case, strip_rows, dense_users, flags):
+    """The fit cuts its row range into strips so that only one strip of the dense leg's count matrix exists at a time
+    (rpk_fit_strip_rows): later strips reuse the item counts, the dense / sparse split and the dense operand of the first.
+    Whole range and an unaligned item shard."""
+    from recpack_b200.synth import synth_interactions
+
+    U, I, nnz, K, sim, pd_ = case
+    X = synth_interactions(U, I, nnz, seed=U + I)
+    want = orc.canon_fit(X, K=K, similarity=sim, pop_discount=pd_)
+    engine.debug_flags(flags)
+    engine.fit_config(dense_users)
+    engine.fit_strip_rows(strip_rows)
+    try:
+        got = _fit_lists(engine, X, K, sim, pd_)
+        b, e = I // 7 + 3, I - I // 5
+        part = _fit_lists(engine, X, K, sim, pd_, item_begin=b, item_end=e)
+    finally:
+        engine.fit_strip_rows(0)
+        engine.fit_config(-1)
+        engine.debug_flags(0)
+    _assert_fit_equal(got, want)
+    _assert_fit_equal(part, {k: v[b:e] for k, v in want.items()})
+
+
 @pytest.mark.parametrize("flags", [0, 2, 6])
 def test_fit_total_ties(engine, flags):
     """Every pair ties: 3 users who all saw all items.  The canonical pick is the lowest indices."""
