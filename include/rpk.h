@@ -235,6 +235,17 @@ RPK_EXPORT int rpk_coverage_topn(rpk_ctx* ctx, int64_t U, int N, int K, int64_t 
                       int64_t* out_count, uint8_t* out_flags);
 
 /*
+ * Data side: FractionInteractionSplitter.split (recpack/scenarios/splitters.py:233-263).  The interactions are given
+ * grouped by user: user g has id uids[g] and the grouped positions seg[g] .. seg[g+1]-1, rows[] maps a grouped
+ * position to the interaction's row in the caller's table (the reference's per-user order = table order).  For every
+ * user the positions are shuffled exactly as np.random.RandomState(seed + uid).shuffle does (MT19937, Fisher-Yates
+ * with masked rejection sampling) and the first ceil(n * in_frac) go to data_in: out_in_mask[row] = 1, else 0
+ * (uint8[n_rows]).  seed + uid must fit 32 bits (numpy raises otherwise; the caller checks).
+ */
+RPK_EXPORT int rpk_split_fraction(rpk_ctx* ctx, int64_t n_users, const int64_t* uids, const int64_t* seg,
+                       const int64_t* rows, int64_t n_rows, double in_frac, uint64_t seed, uint8_t* out_in_mask);
+
+/*
  * Dense leg of the fit on the tensor cores (tcgen05 int8 MMA, int32 accumulation in TMEM):
  * G[i][j] = sum_k A[i][k] * A[j][k] for a 0/1 matrix A (uint8 [I x Kd] row-major, Kd <= 32768),
  * written as uint16 [I x I].  rpk_fit_topk uses this kernel for the densest user columns when

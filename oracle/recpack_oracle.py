@@ -571,6 +571,27 @@ def canon_fit_real(X, K, similarity="cosine", pop_discount=None):
 
 
 # --------------------------------------------------------------------------
+# Data side: FractionInteractionSplitter
+# --------------------------------------------------------------------------
+def ref_fraction_split_mask(user_ix: np.ndarray, in_frac: float, seed: int) -> np.ndarray:
+    """scenarios/splitters.py:233-263 -- per user (ascending id, rows in table order, as pandas groupby yields them)
+    shuffle the row positions with np.random.RandomState(seed + u) and send the first ceil(n * in_frac) to data_in.
+    Returns the boolean mask of the table rows that end up in data_in.  The generator is numpy's (MT19937 + legacy
+    shuffle; not vendored in the reference)."""
+    user_ix = np.asarray(user_ix, dtype=np.int64)
+    order = np.argsort(user_ix, kind="stable")
+    su = user_ix[order]
+    bounds = np.flatnonzero(np.r_[True, su[1:] != su[:-1], True])
+    mask = np.zeros(user_ix.shape[0], dtype=bool)
+    for b, e in zip(bounds[:-1], bounds[1:]):
+        hist = order[b:e].copy()
+        np.random.RandomState(int(seed) + int(su[b])).shuffle(hist)
+        cut = int(np.ceil((e - b) * in_frac))
+        mask[hist[:cut]] = True
+    return mask
+
+
+# --------------------------------------------------------------------------
 # Tie-aware comparison against the unmodified reference (SURVEY.md 8c (3))
 # --------------------------------------------------------------------------
 def compare_topk_tie_aware(ref_S: csr_matrix, got, Xb: csr_matrix, similarity="cosine", rel=1e-5):

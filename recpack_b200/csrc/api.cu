@@ -339,6 +339,13 @@ int rpk_fit_config(rpk_ctx* ctx, int dense_users) {
   RPK_API_END(ctx)
 }
 
+int rpk_split_fraction(rpk_ctx* ctx, int64_t n_users, const int64_t* uids, const int64_t* seg, const int64_t* rows,
+                       int64_t n_rows, double in_frac, uint64_t seed, uint8_t* out_in_mask) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_split_fraction(ctx, n_users, uids, seg, rows, n_rows, in_frac, seed, out_in_mask);
+  RPK_API_END(ctx)
+}
+
 int rpk_fit_strip_rows(rpk_ctx* ctx, int64_t rows) {
   RPK_API_BEGIN(ctx)
   if (rows < 0) throw rpk::Error("rows must be >= 0");

@@ -1353,7 +1353,10 @@ static void fit_range(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64
     RPK_CUDA(cudaMemcpyAsync(h.data(), lhist, sizeof(int) * ((size_t)I + 1), cudaMemcpyDeviceToHost, st));
     RPK_CUDA(cudaStreamSynchronize(st));
     const double share = (double)rows_total / (double)I;
-    const double dense_rate = 1.6e15, sparse_rate = 7e11, hbm = 5e12;  // measured on B200 (profiles/r1_summary.md)
+    // rates measured on B200 (profiles/r2_summary.md): the sparse kernel does 6-7e11 counter updates/s when the packed
+    // counters of a row fit one pass, 1.8e11/s when the catalogue needs several item-range passes (I = 200,000: 3)
+    const bool one_pass = (size_t)I * 2 + 49152 <= (size_t)c->smem_max;
+    const double dense_rate = 1.6e15, sparse_rate = one_pass ? 7e11 : 1.8e11, hbm = 5e12;
     const double fixed = (double)rows_total * (double)rows_pad * 4.0 / hbm;
     double best_gain = 0.0, saved = 0.0;
     int best_h = 0, best_tau = 0;

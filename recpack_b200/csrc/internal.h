@@ -44,6 +44,8 @@ void run_metrics_topn(rpk_ctx* c, int64_t U, int N, const int32_t* top_idx, cons
 void run_coverage_topn(rpk_ctx* c, int64_t U, int N, int K, int64_t I, const int32_t* top_idx, const int32_t* top_len,
                        const int64_t* true_indptr, int64_t* out_count, uint8_t* out_flags);
 
+void run_split_fraction(rpk_ctx* c, int64_t n_users, const int64_t* uids, const int64_t* seg, const int64_t* rows,
+                        int64_t n_rows, double in_frac, uint64_t seed, uint8_t* out_in_mask);
 void run_gram_dense_f64(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices, double* out_G);
 void run_ease_from_inverse(rpk_ctx* c, int64_t I, const double* P, const double* w, double* B);
 void run_predict_dense(rpk_ctx* c, int64_t U, int64_t nnz, const int64_t* indptr, const int32_t* indices, int64_t I, const double* B,

@@ -162,6 +162,14 @@ class Engine:
     def fit_config(self, dense_users: int = -1):
         self._check(self._lib.rpk_fit_config(self._h, int(dense_users)))
 
+    def split_fraction(self, uids, seg, rows, in_frac, seed):
+        """rpk_split_fraction: uint8 mask over the table rows, 1 = data_in (see include/rpk.h)."""
+        n_rows = int(rows.shape[0])
+        out = _empty_like_kind(rows, (n_rows,), np.uint8)
+        self._check(self._lib.rpk_split_fraction(self._h, int(uids.shape[0]), _addr(uids, np.int64), _addr(seg, np.int64),
+                                                 _addr(rows, np.int64), n_rows, float(in_frac), int(seed), _addr(out, np.uint8)))
+        return out
+
     def fit_strip_rows(self, rows: int = 0):
         """rpk_fit_strip_rows: item rows per strip of the fit (0 = automatic)."""
         self._check(self._lib.rpk_fit_strip_rows(self._h, int(rows)))

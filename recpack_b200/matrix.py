@@ -30,6 +30,10 @@ def to_csr_matrix(X, binary: bool = False):
     if isinstance(X, csr_matrix):
         res = X
     elif type(X).__name__ == "InteractionMatrix" and hasattr(X, "values"):
+        if binary:
+            fast = interaction_matrix_structure(X)
+            if fast is not None:
+                return fast
         res = X.values
     else:
         raise UnsupportedTypeError(X)
@@ -64,6 +68,43 @@ def binary_structure(X: csr_matrix):
             pass
         return X, indptr, indices
     return X, memo[1], memo[2]
+
+
+def interaction_matrix_structure(im, device: int = 0):
+    """Binary CSR of a recpack InteractionMatrix without the host COO -> CSR conversion of ``InteractionMatrix.values``
+    (matrix/interaction_matrix.py:212-217): the (user, item) pairs are sorted and de-duplicated on the device (torch:
+    plumbing), the index arrays stay there for fit / predict (the ``device_structure`` memo) and one copy comes back
+    for the scipy object.  Returns None when no GPU is visible or the object has no ``_df`` (the caller then takes the
+    reference's route)."""
+    df = getattr(im, "_df", None)
+    if df is None or "uid" not in df or "iid" not in df:
+        return None
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            return None
+    except ImportError:
+        return None
+    U, I = (int(v) for v in im.shape)
+    dev = torch.device("cuda", device)
+    u = torch.from_numpy(np.ascontiguousarray(df["uid"].to_numpy(), dtype=np.int64)).to(dev)
+    i = torch.from_numpy(np.ascontiguousarray(df["iid"].to_numpy(), dtype=np.int64)).to(dev)
+    keys = torch.unique(u * I + i)  # sorted, duplicates collapse to one entry (the binary matrix)
+    rows = torch.div(keys, I, rounding_mode="floor")
+    idx_d = (keys - rows * I).to(torch.int32)
+    ptr_d = torch.zeros(U + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(torch.bincount(rows, minlength=U), 0, out=ptr_d[1:])
+    indptr, indices = to_host(ptr_d, idx_d)
+    X = csr_matrix((np.ones(indices.shape[0], dtype=np.int32), indices, indptr), shape=(U, I))
+    X.has_canonical_format = True
+    sig = (X.indptr.ctypes.data, X.indices.ctypes.data, X.data.ctypes.data, X.nnz, X.shape)
+    try:
+        X._rpk_canon = (sig, np.ascontiguousarray(X.indptr, dtype=np.int64), np.ascontiguousarray(X.indices, dtype=np.int32))
+        X._rpk_dev = (sig, device, ptr_d, idx_d)
+    except AttributeError:
+        pass
+    return X
 
 
 def device_structure(X: csr_matrix, device: int):

@@ -274,3 +274,12 @@ def test_normalize_X_closed_form():
     d = math.sqrt(1 / 4 + 1 / 9)
     f = math.sqrt(2 / 4 + 1 / 9)
     np.testing.assert_almost_equal(S, [[0, a / (d * d), b / (d * f)], [a / (d * d), 0, b / (d * f)], [b / (d * f), b / (d * f), 0]])
+
+
+@pytest.mark.parametrize("name", ["split_small", "split_heavy"])
+def test_fraction_split_oracle_reproduces_reference(name):
+    """Fixtures of tests/golden/make_golden_split.py (the reference's FractionInteractionSplitter.split)."""
+    g = load_golden(name)
+    mask = orc.ref_fraction_split_mask(g["uid"], float(g["in_frac"]), int(g["seed"]))
+    assert np.array_equal(np.sort(g["interactionid"][mask]), g["in_ids"])
+    assert np.array_equal(np.sort(g["interactionid"][~mask]), g["out_ids"])
