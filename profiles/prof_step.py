@@ -1,8 +1,10 @@
+"""Two fit -> predict -> metrics passes at ML-25M shape through the drop-in classes; run with
+RPK_LIB=profiles/librpk_prof.so (a -DRPK_PHASE_PROF build) to get the per-phase cycle tables on stderr."""
 import sys, warnings
 sys.path.insert(0, ".")
-from bench import make_data
 from recpack_b200 import ItemKNN, NDCGK, RecallK
-train, test_out = make_data("ml25m")
+from recpack_b200.synth import make_dataset
+train, test_out, _ = make_dataset("ml25m", seed=0, split_seed=42, generator="cuda")
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
     for _ in range(2):
