@@ -71,6 +71,10 @@ void rpk_destroy(rpk_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   for (auto& m : ctx->marks) cudaEventDestroy(m.second);
   for (auto& e : ctx->mark_pool) cudaEventDestroy(e);
+  ctx->span_reset();
+  for (auto& e : ctx->span_pool) cudaEventDestroy(e);
+  if (ctx->hist_ev) cudaEventDestroy(ctx->hist_ev);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   delete ctx;
 }

@@ -97,6 +97,20 @@ struct rpk_ctx {
   }
   void span_begin(int k) { spans[k].emplace_back(span_event(), nullptr); }
   void span_end(int k) { spans[k].back().second = span_event(); }
+  // pinned host scratch for small device -> host reads that the host waits for on an event, not on the stream
+  int* pinned = nullptr;
+  size_t pinned_cap = 0;
+  cudaEvent_t hist_ev = nullptr;
+  int* pinned_ints(size_t count) {
+    if (pinned_cap < count) {
+      if (pinned) RPK_CUDA(cudaFreeHost(pinned));
+      pinned = nullptr;
+      pinned_cap = 0;
+      RPK_CUDA(cudaMallocHost(&pinned, sizeof(int) * (count + count / 8 + 64)));
+      pinned_cap = count + count / 8 + 64;
+    }
+    return pinned;
+  }
   // strip state of the running fit (see run_fit): the dense / sparse split chosen by strip 0
   int strip_hmax = 0;
   int strip_tau = 32;

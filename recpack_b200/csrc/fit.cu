@@ -1319,15 +1319,6 @@ static void fit_range(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64
   int* boff = bcnt + 65;
   (void)boff;
   c->fit_I = I;
-  if (strip == 0) RPK_CUDA(cudaMemsetAsync(n, 0, sizeof(int) * (size_t)I, st));
-  RPK_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)I, st));
-  RPK_CUDA(cudaMemsetAsync(work, 0, sizeof(u64) * (size_t)I, st));
-  RPK_CUDA(cudaMemsetAsync(bcnt, 0, sizeof(int) * (65 * 2 + 2), st));
-  if (nnz > 0 && strip == 0) {
-    int blocks = (int)std::min<int64_t>((nnz + 255) / 256, (int64_t)c->sm_count * 16);
-    k_item_counts<<<blocks, 256, 0, st>>>(indices, nnz, n);
-    RPK_LAUNCH_CHECK(c);
-  }
   // ---- hybrid split: the users with the longest histories carry most of the
   //      sum of d_u^2; their Gram goes to the tensor cores, everybody else to the sparse kernel
   int hmax = c->dense_users;
@@ -1338,20 +1329,36 @@ static void fit_range(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64
   if (nnz == 0 || I < 2 || nrows == 0) hmax = 0;
   int dense_tau = 32;  // histories shorter than this are never worth a dense column
   int* lhist = nullptr;
-  if (strip > 0) {
-    hmax = c->strip_hmax;
-    dense_tau = c->strip_tau;
-  } else if (hmax > 0) {
+  const bool decide = strip == 0 && hmax > 0;
+  if (decide) {
+    // the history-length histogram goes to the host first (pinned buffer, asynchronous copy); the item counts below
+    // run while the host waits for it
     lhist = c->buf<int>("fit_len_hist", (size_t)I + 2);
     RPK_CUDA(cudaMemsetAsync(lhist, 0, sizeof(int) * ((size_t)I + 2), st));
     k_len_hist<<<ceil_div(U, 256), 256, 0, st>>>(indptr, U, I, lhist);
     RPK_LAUNCH_CHECK(c);
+    RPK_CUDA(cudaMemcpyAsync(c->pinned_ints((size_t)I + 1), lhist, sizeof(int) * ((size_t)I + 1), cudaMemcpyDeviceToHost, st));
+    if (!c->hist_ev) RPK_CUDA(cudaEventCreateWithFlags(&c->hist_ev, cudaEventDisableTiming));
+    RPK_CUDA(cudaEventRecord(c->hist_ev, st));
+  }
+  if (strip == 0) RPK_CUDA(cudaMemsetAsync(n, 0, sizeof(int) * (size_t)I, st));
+  RPK_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int) * (size_t)I, st));
+  RPK_CUDA(cudaMemsetAsync(work, 0, sizeof(u64) * (size_t)I, st));
+  RPK_CUDA(cudaMemsetAsync(bcnt, 0, sizeof(int) * (65 * 2 + 2), st));
+  if (nnz > 0 && strip == 0) {
+    int blocks = (int)std::min<int64_t>((nnz + 255) / 256, (int64_t)c->sm_count * 16);
+    k_item_counts<<<blocks, 256, 0, st>>>(indices, nnz, n);
+    RPK_LAUNCH_CHECK(c);
+  }
+  if (strip > 0) {
+    hmax = c->strip_hmax;
+    dense_tau = c->strip_tau;
+  } else if (decide) {
     // The split is chosen per density on the host from the history-length histogram (one small copy):
     // moving the H longest histories to the tensor cores costs 2*H*rows*I int8 ops (+ the count matrix
     // traffic) and saves sum(d_u^2) * rows/I counter updates of the sparse kernel.
-    std::vector<int> h((size_t)I + 1);
-    RPK_CUDA(cudaMemcpyAsync(h.data(), lhist, sizeof(int) * ((size_t)I + 1), cudaMemcpyDeviceToHost, st));
-    RPK_CUDA(cudaStreamSynchronize(st));
+    RPK_CUDA(cudaEventSynchronize(c->hist_ev));
+    const int* h = c->pinned_ints((size_t)I + 1);
     const double share = (double)rows_total / (double)I;
     // rates measured on B200 (profiles/r2_summary.md): the sparse kernel does 6-7e11 counter updates/s when the packed
     // counters of a row fit one pass, 1.8e11/s when the catalogue needs several item-range passes (I = 200,000: 3)

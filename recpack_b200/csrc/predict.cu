@@ -1169,12 +1169,14 @@ __host__ __device__ __forceinline__ size_t a32_fixed_bytes(int cap) {
   return sel_smem_bytes(cap, A32_BINS) + 2 * ((sizeof(RowTab) + 15) / 16) * 16;
 }
 
-// k-th work item of CTA `bid` of `G`: stripes of G items dealt forwards and backwards in turn.  The items are
-// sorted heaviest first, so every CTA gets the same mix; a static order (instead of a shared counter) lets a CTA
-// stage its next item while it still works on the current one.
-__device__ __forceinline__ int a32_work_index(int k, int bid, int G) {
-  return (k & 1) ? k * G + (G - 1 - bid) : k * G + bid;
-}
+// Work distribution: the items are sorted heaviest first; CTA b starts with item b and takes every further item from a
+// shared counter (longest-processing-time scheduling: the few users with five-digit histories then cost their CTAs
+// other items instead of coming on top of an equal share of everything -- that tail bounded the kernel once a rank's
+// shard became small).  The counter is read TWO items ahead by thread 0 and kept in a register, so the atomic's
+// latency hides behind a whole item and the next item can still be staged while the current one is swept.
+// Users with histories of at least A32_EXACT_D rows get their exact sums in the same work item: the margin 2 d of
+// their approximate sums never proves a list, and a second launch for them would run on a handful of CTAs.
+constexpr int A32_EXACT_D = 2048;
 
 __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -1193,14 +1195,16 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int total = (p.n_work ? *p.n_work : p.U) * p.P;
   const int G = gridDim.x, bid = blockIdx.x;
-  if (a32_work_index(0, bid, G) >= total) return;
+  if (bid >= total) return;
   uint4* acc4 = reinterpret_cast<uint4*>(acc);
   const unsigned acc_s = (unsigned)__cvta_generic_to_shared(acc);
   const int nvec = p.R >> 2;  // R is a multiple of 4
   for (int v = tid; v < nvec; v += nt) acc4[v] = make_uint4(0u, 0u, 0u, 0u);
   for (int b = tid; b < A32_BINS; b += nt) hist[b] = 0;
+  int pend = total;  // thread 0: the item after the next one (fetched one item ahead of its use)
   if (tid == 0) {
-    const int w0 = a32_work_index(0, bid, G);
+    const int w0 = bid;
+    pend = G + atomicAdd(p.queue, 1);
     s_w[0] = w0;
     s_rec[0] = p.work_tab[w0 / p.P];
     s_bsum[0] = 0ull;
@@ -1269,7 +1273,8 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
     // per-item scratch is reset here too (every thread has left the previous item, nobody reads these before the
     // barrier after the sweep)
     if (tid == 0) {
-      int w_n = a32_work_index(k + 1, bid, G);
+      int w_n = pend;                    // asked for while the previous item was processed
+      pend = G + atomicAdd(p.queue, 1);  // used at the top of the next item
       if (w_n < total) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_rec[nxt])),
                      "l"(p.work_tab + w_n / p.P)
@@ -1470,7 +1475,7 @@ __global__ void __launch_bounds__(A32_NT, 2) k_predict_a32(Pred32Params p) {
       continue;
     }
     const int mo = m < p.N ? m : p.N;
-    bool need_exact = p.exact != 0;
+    bool need_exact = p.exact != 0 || d >= A32_EXACT_D;
     Entry* surv = list;  // where the survivors are
     if (!need_exact) {
       // is the order of the N best (and their separation from the rest) proven by the approximate sums alone?
