@@ -12,7 +12,7 @@ from __future__ import annotations
 import os
 
 HAVE_RECPACK = False
-ref_base = ref_nn = ref_metrics = ref_metrics_base = ref_matrix_util = None
+ref_base = ref_nn = ref_metrics = ref_metrics_base = ref_matrix_util = ref_splitters = None
 
 if os.environ.get("RPK_NO_RECPACK", "0") != "1":
     try:
@@ -22,7 +22,12 @@ if os.environ.get("RPK_NO_RECPACK", "0") != "1":
         import recpack.metrics as ref_metrics
         import recpack.metrics.base as ref_metrics_base
 
+        try:  # needs pandas / tqdm like the reference itself; optional for the algorithm and metric classes
+            import recpack.scenarios.splitters as ref_splitters
+        except Exception:
+            ref_splitters = None
+
         HAVE_RECPACK = True
     except Exception:  # not installed, or an incompatible environment: use the mirror
         HAVE_RECPACK = False
-        ref_base = ref_nn = ref_metrics = ref_metrics_base = ref_matrix_util = None
+        ref_base = ref_nn = ref_metrics = ref_metrics_base = ref_matrix_util = ref_splitters = None

@@ -425,6 +425,9 @@ struct RowCountSrc {
   // entries, rebuilt by set_floor; the passes then test a counter against its item's entry with one load and one
   // compare instead of computing its key.  Null: only the global bound `cmin` is used.
   unsigned short* cm_tab;
+  // the same bound without the slack of a whole count (rounding slack only): the queueing pass of for_each_queued tests
+  // a counter against it instead of computing the counter's float key (no int -> float conversion, no multiplies)
+  unsigned short* cq_tab;
   int count_bound;  // >= number of candidates of the row (0: unknown, stats() scans)
   const unsigned char* code_s;  // the coded popularities and their table again, as shared-memory pointers the compiler
   const float* tab_s;           // can see through (sk.code / sk.code_tab travel through the parameter struct: generic loads)
@@ -442,6 +445,13 @@ struct RowCountSrc {
           v = c < 1.0f ? 1 : (c > 65535.0f ? 65535 : (int)c);
         }
         cm_tab[threadIdx.x] = (unsigned short)v;
+        int vq = 1;
+        if (thr) {
+          // key = fl(fl(c * c) * r) >= thr implies c >= sqrt(thr / r) * (1 - 2^-21); 1e-4 covers that with room to spare
+          const float sq = sqrtf(__uint_as_float((unsigned)thr) / sk.code_tab[threadIdx.x]) * 0.9999f;
+          vq = sq < 1.0f ? 1 : (sq > 65535.0f ? 65535 : (int)ceilf(sq));
+        }
+        cq_tab[threadIdx.x] = (unsigned short)vq;
       }
       __syncthreads();
     }
@@ -513,7 +523,6 @@ struct RowCountSrc {
     __syncthreads();
     const uint4* c4 = reinterpret_cast<const uint4*>(cnt);
     const uint2* g8 = reinterpret_cast<const uint2*>(code_s + r0);
-    const unsigned fk = (unsigned)floor_key;  // cosine keys are float bit patterns
     for (int v0 = 0; v0 < nvec16; v0 += nt) {  // warp-uniform trip count: the warp queues together
       const int v = v0 + tid;
       unsigned hit = 0u;  // which of my eight counters reach the floor
@@ -524,10 +533,9 @@ struct RowCountSrc {
           const unsigned xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float a = (float)((xs[q >> 1] >> ((q & 1) * 16)) & 0xffffu);
-            const float r = tab_s[((q < 4 ? g.x : g.y) >> ((q & 3) * 8)) & 0xffu];
-            const unsigned k = __float_as_uint(__fmul_rn(__fmul_rn(a, a), r));
-            hit |= (k >= fk ? 1u : 0u) << q;
+            const unsigned cq = (xs[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
+            const unsigned need = cq_tab[((q < 4 ? g.x : g.y) >> ((q & 3) * 8)) & 0xffu];
+            hit |= (cq >= need ? 1u : 0u) << q;
           }
         }
       }
@@ -900,6 +908,7 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
   __shared__ int s_work;
   __shared__ float s_code_tab[256];
   __shared__ unsigned short s_cm_tab[256];
+  __shared__ unsigned short s_cq_tab[256];
   __shared__ int s_ex_idx[HEAVY_CAP], s_ex_cnt[HEAVY_CAP];
 
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -1100,7 +1109,7 @@ __global__ void __launch_bounds__(1024, 1) k_fit_rows(FitParams p) {
     // upper bound of the row's candidates: every slot when dense counts were loaded, else one per counter update
     int cbound = ns + nex;
     if (!p.g16 && pre_slot < 0) cbound = (int)min((u64)cbound, p.work[i]);
-    RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i, s_ex_idx, s_ex_cnt, nex, 1, (PACK16 && p.sk.code) ? s_cm_tab : nullptr, cbound,
+    RowCountSrc<PACK16> src{p.sk, cnt, r0, ns, i, s_ex_idx, s_ex_cnt, nex, 1, (PACK16 && p.sk.code) ? s_cm_tab : nullptr, (PACK16 && p.sk.code) ? s_cq_tab : nullptr, cbound,
                             reinterpret_cast<const unsigned char*>(cnt) + (size_t)p.R * (PACK16 ? 2 : 4), s_code_tab, 0ull, p.R >> 3};
     bool sorted = true;
     FIT_MARK(3);

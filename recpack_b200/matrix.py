@@ -40,6 +40,14 @@ def to_csr_matrix(X, binary: bool = False):
     return binary_structure(res)[0] if binary else res
 
 
+def _has_stored_zero(data: np.ndarray) -> bool:
+    """True when a stored value is zero.  The common case (all values positive) is settled by one SIMD min reduction,
+    2-3x cheaper than ``np.all`` on 20 M values."""
+    if data.dtype != np.bool_ and data.min() > 0:
+        return False
+    return not bool(np.all(data))
+
+
 def binary_structure(X: csr_matrix):
     """(canonical CSR, indptr int64, indices int32) of the binarised matrix.
 
@@ -53,7 +61,7 @@ def binary_structure(X: csr_matrix):
     if memo is None or memo[0] != sig:
         # validated once per matrix object (the checks are O(nnz) on the host); like scipy's own
         # has_canonical_format flag the memo assumes the arrays are not modified in place afterwards
-        if X.nnz and not np.all(X.data):
+        if X.nnz and _has_stored_zero(X.data):
             X = X.copy()
             X.eliminate_zeros()
         if not X.has_canonical_format:

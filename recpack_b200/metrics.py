@@ -39,6 +39,19 @@ def _matrix_signature(M):
     return matrix_signature(M)
 
 
+def _column_csr(vals: np.ndarray) -> csr_matrix:
+    """``csr_matrix(vals.reshape(-1, 1))`` (the layout of the reference's ``scores_``: one row per evaluated user, zeros
+    not stored) assembled directly instead of through scipy's dense -> COO -> CSR route."""
+    vals = np.ascontiguousarray(vals, dtype=np.float64)
+    nz = vals != 0
+    indptr = np.zeros(vals.shape[0] + 1, dtype=np.int32)
+    np.cumsum(nz, out=indptr[1:])
+    data = vals[nz]
+    out = csr_matrix((data, np.zeros(data.shape[0], dtype=np.int32), indptr), shape=(vals.shape[0], 1))
+    out.has_canonical_format = True
+    return out
+
+
 class GpuTopKMixin:
     """``calculate`` of MetricTopK (metrics/base.py:172-193) on the GPU: drop users without true items, rank the
     K best stored predictions per user, evaluate."""
@@ -92,7 +105,7 @@ class GpuListwiseMixin(GpuTopKMixin):
         if not isinstance(per_user, np.ndarray):
             engine.sync()
             (per_user,) = to_host(per_user)
-        self.scores_ = csr_matrix(per_user[0, users].reshape(-1, 1))
+        self.scores_ = _column_csr(per_user[0, users])
         self.sum_, self.n_users_ = float(sums[0]), int(n_users)  # device-side reduction (used by the sharded bench)
 
     @property

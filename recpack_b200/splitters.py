@@ -12,9 +12,12 @@ import numpy as np
 
 from .engine import get_engine
 
-try:  # subclass the reference's splitter when recpack is importable (same registry / isinstance behaviour)
-    from recpack.scenarios.splitters import FractionInteractionSplitter as _Base  # type: ignore
-except Exception:  # pragma: no cover - stand-alone mirror of the constructor (splitters.py:222-231)
+from . import _ref
+
+if _ref.HAVE_RECPACK and _ref.ref_splitters is not None:
+    # subclass the reference's splitter when recpack is importable (same registry / isinstance behaviour)
+    _Base = _ref.ref_splitters.FractionInteractionSplitter
+else:  # stand-alone mirror of the constructor (splitters.py:222-231)
 
     class _Base:  # type: ignore
         def __init__(self, in_frac, seed: int = None):
