@@ -301,6 +301,8 @@ def run_gpu(args):
     top_out = {"idx": torch.empty((nU, N_LIST), dtype=torch.int32, device=dev), "val": None,
                "len": torch.empty((nU,), dtype=torch.int32, device=dev)}
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)  # > L2 (126 MB)
+    red_d = torch.zeros(3, dtype=torch.float64, device=dev)
+    n_d = torch.zeros(1, dtype=torch.int64, device=dev)
     metrics = [("ndcg", 10), ("recall", 20)]
     phase_ms = {"fit": [], "exchange": [], "score": [], "gram_tc": [], "fit_rows": [], "predict": []}
 
@@ -316,8 +318,11 @@ def run_gpu(args):
             eng.model_load_topk(I, K_NEIGH, fit_out["idx"], fit_out["val"], fit_out["len"])
         ev[2].record()
         eng.predict_topn(nU, u_ptr, u_idx, N_LIST, mask_history=True, out=top_out)
-        sums, n_users, _ = eng.metrics_topn(nU, N_LIST, top_out["idx"], top_out["len"], y_ptr, y_idx, metrics, want_per_user=False)
-        red = torch.tensor([sums[0], sums[1], float(n_users)], dtype=torch.float64, device=dev)
+        # the metric sums stay on the device (no host round trip before the all-reduce): red = [sum NDCG, sum Recall, users]
+        eng.metrics_topn(nU, N_LIST, top_out["idx"], top_out["len"], y_ptr, y_idx, metrics, want_per_user=False,
+                         out_sums=red_d[:2], out_n_users=n_d)
+        red_d[2:3].copy_(n_d)
+        red = red_d
         if world > 1:
             dist.all_reduce(red)
         ev[3].record()

@@ -319,9 +319,12 @@ class Engine:
                                            _addr(out_idx, np.int32), _addr(out_len, np.int32)))
         return out_idx, out_len
 
-    def metrics_topn(self, U, N, top_idx, top_len, true_indptr, true_indices, metrics, want_per_user=True):
+    def metrics_topn(self, U, N, top_idx, top_len, true_indptr, true_indices, metrics, want_per_user=True, out_sums=None,
+                     out_n_users=None):
         """metrics: list of (kind, K).  Returns (sums float64[m], n_users int, per_user float64[m, U] or None).
-        The discount / IDCG tables are built here with numpy exactly as recpack/metrics/dcg.py:98-104 does."""
+        The discount / IDCG tables are built here with numpy exactly as recpack/metrics/dcg.py:98-104 does.
+        out_sums (float64[m]) / out_n_users (int64[1]) as torch CUDA tensors keep the reduction on the device: the call
+        is then stream-ordered without a host round trip and returns the two tensors instead of host values."""
         import itertools
 
         kinds = np.array([METRIC_CODES[k] for k, _ in metrics], dtype=np.int32)
@@ -331,13 +334,16 @@ class Engine:
         idcg = np.array([1] + list(itertools.accumulate(disc, lambda x, y: x + y)), dtype=np.float64)
         m = len(metrics)
         per_user = _empty_like_kind(top_idx, (m, U), np.float64) if want_per_user else None
-        sums = np.empty(m, dtype=np.float64)
-        n_users = np.zeros(1, dtype=np.int64)
+        on_device = out_sums is not None and out_n_users is not None
+        sums = out_sums if on_device else np.empty(m, dtype=np.float64)
+        n_users = out_n_users if on_device else np.zeros(1, dtype=np.int64)
         self._check(self._lib.rpk_metrics_topn(
             self._h, int(U), int(N), _addr(top_idx, np.int32), _addr(top_len, np.int32), _addr(true_indptr, np.int64),
             _addr(true_indices, np.int32), int(true_indices.shape[0]), m, _addr(kinds), _addr(Ks),
             _addr(np.ascontiguousarray(disc)), _addr(idcg), maxK, _addr(per_user, np.float64, allow_none=True),
-            _addr(sums), _addr(n_users)))
+            _addr(sums, np.float64), _addr(n_users, np.int64)))
+        if on_device:
+            return sums, n_users, per_user
         return sums, int(n_users[0]), per_user
 
 
