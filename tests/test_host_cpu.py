@@ -285,3 +285,58 @@ def test_only_the_binding_module_imports_recpack():
         if f.endswith(".py") and f != "_ref.py":
             text = open(os.path.join(pkg, f)).read()
             assert not re.search(r"^\s*(from|import)\s+recpack(\.|\s)", text, flags=re.M), f
+
+
+# ---- host helpers added in round 2 (no GPU needed)
+def test_stored_zero_check_matches_numpy_all():
+    from recpack_b200.matrix import _has_stored_zero
+
+    for arr in (np.ones(10, dtype=np.int32), np.array([1, 0, 2]), np.array([-1, 2, 3]), np.array([-1, 0, 3]),
+                np.array([True, True]), np.array([True, False]), np.array([0.5, 2.0]), np.array([0.5, 0.0]),
+                np.array([np.nan, 1.0])):
+        assert _has_stored_zero(arr) == (not bool(np.all(arr))), arr
+
+
+def test_score_column_equals_scipy_route():
+    from scipy.sparse import csr_matrix
+
+    from recpack_b200.metrics import _column_csr
+
+    for vals in (np.array([0.0, 0.25, 0.0, 1.0]), np.zeros(3), np.array([]), np.arange(1, 6, dtype=np.float64)):
+        want = csr_matrix(vals.reshape(-1, 1))
+        got = _column_csr(vals)
+        assert got.shape == want.shape and np.array_equal(got.indptr, want.indptr)
+        assert np.array_equal(got.indices, want.indices) and np.array_equal(got.data, want.data)
+        assert got.mean() == want.mean() if vals.size else True
+
+
+def test_splitter_validates_seed_and_handles_empty_tables_without_a_gpu():
+    """np.random.RandomState(seed + u) raises for seeds outside [0, 2^32) (scenarios/splitters.py:247); so does the
+    drop-in, before any device work."""
+    from recpack_b200.splitters import FractionInteractionSplitter, fraction_split_mask
+
+    with pytest.raises(ValueError):
+        fraction_split_mask(np.array([0, 7, 7]), 0.5, 2**32 - 3)
+    with pytest.raises(ValueError):
+        fraction_split_mask(np.array([0, 1]), 0.5, -1)
+    assert fraction_split_mask(np.zeros(0, dtype=np.int64), 0.5, 1).shape == (0,)
+    sp = FractionInteractionSplitter(0.8, seed=42)
+    assert sp.in_frac == 0.8 and sp.seed == 42 and sp.name == "FractionInteractionSplitter"
+
+
+def test_interaction_matrix_fast_path_declines_without_a_gpu():
+    import torch
+
+    from recpack_b200.matrix import interaction_matrix_structure
+
+    class Fake:
+        _df = None
+        shape = (2, 2)
+
+    assert interaction_matrix_structure(Fake()) is None
+    if not torch.cuda.is_available():
+        import pandas as pd
+
+        f = Fake()
+        f._df = pd.DataFrame({"uid": [0, 1], "iid": [1, 0]})
+        assert interaction_matrix_structure(f) is None
