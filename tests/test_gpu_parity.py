@@ -353,6 +353,32 @@ def test_predict_full_csr_matches_oracle_and_reference(engine, flags):
     engine.debug_flags(0)
 
 
+def test_predict_small_similarities_keep_relative_resolution():
+    """Conditional probability with pop_discount = 1 gives similarities ~ c / (n_i n_j) << 1 (round-1 advice: a fixed
+    2^-39 absolute resolution lost 1e-4 .. 1e-2 relative there).  The fixed-point scale is chosen per model from its
+    largest value, so scores stay within d_u * vmax * 2^-40 of the float64 sums X @ S -- here ~1e-12 relative."""
+    from recpack_b200 import ItemKNN
+    from recpack_b200.synth import synth_interactions
+
+    X = synth_interactions(3000, 400, 90_000, seed=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        algo = ItemKNN(K=60, similarity="conditional_probability", pop_discount=1.0).fit(X)
+        pred = algo.predict(X)
+    S = algo.similarity_matrix_
+    vmax = float(S.data.max())
+    assert vmax < 1e-2  # similarities far below 1: the regime the advice describes
+    ref = csr_matrix(csr_matrix(X).astype(np.float64) @ S)
+    ref.sort_indices()
+    pred = csr_matrix(pred)
+    pred.sort_indices()
+    assert np.array_equal(pred.indptr, ref.indptr) and np.array_equal(pred.indices, ref.indices)
+    d = np.repeat(np.diff(csr_matrix(X).indptr), np.diff(ref.indptr)).astype(np.float64)
+    err = np.abs(pred.data - ref.data)
+    assert np.all(err <= d * vmax * 2.0**-40 + 1e-300)
+    assert float((err / ref.data).max()) < 1e-9
+
+
 def test_predict_heavy_user_limb_chunks(engine):
     """A user with more than 4095 history items crosses the limb-normalisation path; identical
     similarity rows with value ~1 force the high-limb bound check."""
