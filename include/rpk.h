@@ -235,6 +235,27 @@ RPK_EXPORT int rpk_coverage_topn(rpk_ctx* ctx, int64_t U, int N, int K, int64_t 
                       int64_t* out_count, uint8_t* out_flags);
 
 /*
+ * Scoring with a REAL-VALUED input matrix: C = A @ S for a CSR A [rows x I] (e.g. time-decayed histories) and the CSR
+ * similarity matrix S [I x I] (ascending columns per row; values may be negative), float64 sums in scipy's csr_matmat
+ * order -- bit-identical to the reference's `X_decayed @ similarity_matrix_` of TARSItemKNN._predict
+ * (recpack/algorithms/time_aware_item_knn/base.py:137-149 -> algorithms/base.py:237-255).  Sums that are exactly zero
+ * are not stored.  mask_history removes the columns of A's own row first (pipelines/pipeline.py:174-175).
+ *   rpk_spgemm_topn   the N best stored entries per row by (value descending, column ascending); outputs as rpk_fit_topk_real
+ *   rpk_spgemm_count  stored entries per row (int64[rows])
+ *   rpk_spgemm_fill   the CSR rows (ascending columns) at out_indptr (int64[rows + 1], exclusive prefix of the counts)
+ */
+RPK_EXPORT int rpk_spgemm_topn(rpk_ctx* ctx, int64_t rows, int64_t a_nnz, const int64_t* a_indptr, const int32_t* a_indices,
+                    const double* a_values, int64_t I, int64_t s_nnz, const int64_t* s_indptr, const int32_t* s_indices,
+                    const double* s_values, int N, int mask_history, int32_t* out_idx, double* out_val, int32_t* out_len);
+RPK_EXPORT int rpk_spgemm_count(rpk_ctx* ctx, int64_t rows, int64_t a_nnz, const int64_t* a_indptr, const int32_t* a_indices,
+                     const double* a_values, int64_t I, int64_t s_nnz, const int64_t* s_indptr, const int32_t* s_indices,
+                     const double* s_values, int mask_history, int64_t* out_row_nnz);
+RPK_EXPORT int rpk_spgemm_fill(rpk_ctx* ctx, int64_t rows, int64_t a_nnz, const int64_t* a_indptr, const int32_t* a_indices,
+                    const double* a_values, int64_t I, int64_t s_nnz, const int64_t* s_indptr, const int32_t* s_indices,
+                    const double* s_values, int mask_history, const int64_t* out_indptr, int64_t out_nnz,
+                    int32_t* out_indices, double* out_values);
+
+/*
  * Data side: FractionInteractionSplitter.split (recpack/scenarios/splitters.py:233-263).  The interactions are given
  * grouped by user: user g has id uids[g] and the grouped positions seg[g] .. seg[g+1]-1, rows[] maps a grouped
  * position to the interaction's row in the caller's table (the reference's per-user order = table order).  For every

@@ -52,6 +52,12 @@ _SIGNATURES = {
     "rpk_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "rpk_trace_report": (C.c_char_p, [C.c_void_p]),
     "rpk_fit_config": (C.c_int, [C.c_void_p, C.c_int]),
+    "rpk_spgemm_topn": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, _f64p, C.c_int64, C.c_int64, _i64p, _i32p, _f64p,
+                                  C.c_int, C.c_int, _i32p, _f64p, _i32p]),
+    "rpk_spgemm_count": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, _f64p, C.c_int64, C.c_int64, _i64p, _i32p, _f64p,
+                                   C.c_int, _i64p]),
+    "rpk_spgemm_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, _i64p, _i32p, _f64p, C.c_int64, C.c_int64, _i64p, _i32p, _f64p,
+                                  C.c_int, _i64p, C.c_int64, _i32p, _f64p]),
     "rpk_split_fraction": (C.c_int, [C.c_void_p, C.c_int64, _i64p, _i64p, _i64p, C.c_int64, C.c_double, C.c_uint64, _vp]),
     "rpk_fit_strip_rows": (C.c_int, [C.c_void_p, C.c_int64]),
     "rpk_last_timings": (C.c_int, [C.c_void_p, _vp]),

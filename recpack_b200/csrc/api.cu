@@ -343,6 +343,34 @@ int rpk_fit_config(rpk_ctx* ctx, int dense_users) {
   RPK_API_END(ctx)
 }
 
+int rpk_spgemm_topn(rpk_ctx* ctx, int64_t rows, int64_t a_nnz, const int64_t* a_indptr, const int32_t* a_indices,
+                    const double* a_values, int64_t I, int64_t s_nnz, const int64_t* s_indptr, const int32_t* s_indices,
+                    const double* s_values, int N, int mask_history, int32_t* out_idx, double* out_val, int32_t* out_len) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_spgemm(ctx, rows, a_nnz, a_indptr, a_indices, a_values, I, s_nnz, s_indptr, s_indices, s_values, N, mask_history, 0,
+                  out_idx, out_val, out_len, nullptr, nullptr, 0, nullptr, nullptr);
+  RPK_API_END(ctx)
+}
+
+int rpk_spgemm_count(rpk_ctx* ctx, int64_t rows, int64_t a_nnz, const int64_t* a_indptr, const int32_t* a_indices,
+                     const double* a_values, int64_t I, int64_t s_nnz, const int64_t* s_indptr, const int32_t* s_indices,
+                     const double* s_values, int mask_history, int64_t* out_row_nnz) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_spgemm(ctx, rows, a_nnz, a_indptr, a_indices, a_values, I, s_nnz, s_indptr, s_indices, s_values, 1, mask_history, 1,
+                  nullptr, nullptr, nullptr, out_row_nnz, nullptr, 0, nullptr, nullptr);
+  RPK_API_END(ctx)
+}
+
+int rpk_spgemm_fill(rpk_ctx* ctx, int64_t rows, int64_t a_nnz, const int64_t* a_indptr, const int32_t* a_indices,
+                    const double* a_values, int64_t I, int64_t s_nnz, const int64_t* s_indptr, const int32_t* s_indices,
+                    const double* s_values, int mask_history, const int64_t* out_indptr, int64_t out_nnz, int32_t* out_indices,
+                    double* out_values) {
+  RPK_API_BEGIN(ctx)
+  rpk::run_spgemm(ctx, rows, a_nnz, a_indptr, a_indices, a_values, I, s_nnz, s_indptr, s_indices, s_values, 1, mask_history, 2,
+                  nullptr, nullptr, nullptr, nullptr, out_indptr, out_nnz, out_indices, out_values);
+  RPK_API_END(ctx)
+}
+
 int rpk_split_fraction(rpk_ctx* ctx, int64_t n_users, const int64_t* uids, const int64_t* seg, const int64_t* rows,
                        int64_t n_rows, double in_frac, uint64_t seed, uint8_t* out_in_mask) {
   RPK_API_BEGIN(ctx)

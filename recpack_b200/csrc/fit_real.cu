@@ -221,27 +221,38 @@ __device__ __forceinline__ int warp_lower_bound(const int* __restrict__ a, int n
   return min(hi, lo + __ffs(m) - 1);
 }
 
+// One kernel serves two products of the form  row(i) = sum over the entries k of a LIST of  a_k * B[k, :] :
+//   fit      list = users of item i (CSC of X, ascending), a_k = left value of (user, i), B = X (right values);
+//   scoring  list = row u of a real-valued matrix A (decayed histories), a_k = A's value, B = the similarity model.
 struct RealParams {
-  const int64_t* indptr;
+  const int64_t* indptr;  // B: CSR with ascending columns
   const int* indices;
-  const double* left;   // per CSR entry, null = 1.0 (binary left operand)
-  const double* right;  // per CSR entry
-  const int64_t* cscptr;
-  const int* csc_users;  // ascending per item
-  const int* csc_off;
+  const double* left;   // fit: per CSR entry of X, null = 1.0 (binary left operand)
+  const double* right;  // B's values
+  const int64_t* cscptr;  // the lists
+  const int* csc_users;   // ... their entries (row ids of B), ascending per list
+  const int* csc_off;     // fit: offset of item i inside each user's history (where `left` is read)
+  const double* left_entry;  // non-null: a_k stored per list entry (scoring)
   const double* row_scale;  // null = none
   const double* col_scale;  // null = none
-  const int* order;         // rows of this call, heaviest first (absolute item ids)
+  const int* order;         // rows of this call, heaviest first (absolute row ids)
   int nrows;
   int P, R, I, K;
   int64_t item_begin;
   int cap, direct_cap;
+  int diag;       // 1: column i of row i is an explicit zero that competes in the selection (fit: setdiag)
+  int mask_list;  // 1: the columns named by the list itself are removed (history removal in scoring)
+  int mode;       // 0: top-K lists; 1: count the stored entries per row; 2: write CSR rows (ascending columns)
   int* queue;
   int* scr_idx;  // [grid x (I + 1)]
   double* scr_val;
   int* out_idx;
   double* out_val;
   int* out_len;
+  long long* out_row_nnz;     // mode 1
+  const int64_t* out_indptr;  // mode 2
+  int* csr_indices;
+  double* csr_values;
 };
 
 __global__ void __launch_bounds__(1024, 1) k_real_rows(RealParams p) {
@@ -251,6 +262,7 @@ __global__ void __launch_bounds__(1024, 1) k_real_rows(RealParams p) {
   SelShared* sh = reinterpret_cast<SelShared*>(hist + SEL_BINS);
   double* acc = reinterpret_cast<double*>(smem + sel_smem_bytes(p.cap));
   __shared__ int s_row, s_cnt, s_diag;
+  __shared__ int s_wc[32];
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
   int* scr_idx = p.scr_idx + (int64_t)blockIdx.x * (p.I + 1);
   double* scr_val = p.scr_val + (int64_t)blockIdx.x * (p.I + 1);
@@ -280,9 +292,9 @@ __global__ void __launch_bounds__(1024, 1) k_real_rows(RealParams p) {
           const int d = (int)(p.indptr[u + 1] - hb);
           const int* h = p.indices + hb;
           const int lo = warp_lower_bound(h, d, c0, lane);
-          if (lo >= d || h[lo] >= c1) continue;  // nothing of this user in the slice (warp-uniform)
+          if (lo >= d || h[lo] >= c1) continue;  // nothing of this row of B in the slice (warp-uniform)
           const int hi = lo + warp_lower_bound(h + lo, d - lo, c1, lane);
-          const double a = p.left ? p.left[hb + p.csc_off[ub + k]] : 1.0;
+          const double a = p.left_entry ? p.left_entry[ub + k] : (p.left ? p.left[hb + p.csc_off[ub + k]] : 1.0);
           for (int t = lo + lane; t < hi; t += 32) {
             const int j = h[t];
             const double b = p.right[hb + t];
@@ -292,37 +304,75 @@ __global__ void __launch_bounds__(1024, 1) k_real_rows(RealParams p) {
         }
       }
       __syncthreads();
-      // non-zero sums -> scratch row (scaled); the diagonal is an explicit zero of the reference's matrix
-      const double rs = p.row_scale ? p.row_scale[i] : 1.0;
-      for (int t0 = 0; t0 < r1 - r0; t0 += nt) {
-        const int t = t0 + tid;
-        bool keep = false;
-        double v = 0.0;
-        const int j = r0 + t;
-        if (t < r1 - r0) {
-          if (j == i) {
-            keep = true;
-          } else {
-            v = acc[t];
-            if (v != 0.0) {
+      if (p.mask_list) {  // pipelines/pipeline.py:174-175: scores of history items are removed
+        for (int k = tid; k < nu; k += nt) {
+          const int j = p.csc_users[ub + k];
+          if (j >= r0 && j < r1) acc[j - r0] = 0.0;
+        }
+        __syncthreads();
+      }
+      if (p.mode == 0) {
+        // non-zero sums -> scratch row (scaled); the diagonal is an explicit zero of the reference's matrix
+        const double rs = p.row_scale ? p.row_scale[i] : 1.0;
+        for (int t0 = 0; t0 < r1 - r0; t0 += nt) {
+          const int t = t0 + tid;
+          bool keep = false;
+          double v = 0.0;
+          const int j = r0 + t;
+          if (t < r1 - r0) {
+            if (p.diag && j == i) {
               keep = true;
-              if (p.row_scale) v = __dmul_rn(rs, v);
-              if (p.col_scale) v = __dmul_rn(v, p.col_scale[j]);
-              if (v == 0.0) keep = false;  // underflow to zero: a zero product is not stored either
+            } else {
+              v = acc[t];
+              if (v != 0.0) {
+                keep = true;
+                if (p.row_scale) v = __dmul_rn(rs, v);
+                if (p.col_scale) v = __dmul_rn(v, p.col_scale[j]);
+                if (v == 0.0) keep = false;  // underflow to zero: a zero product is not stored either
+              }
             }
           }
+          const unsigned m = __ballot_sync(0xffffffffu, keep);
+          int base = 0;
+          if (lane == 0 && m) base = atomicAdd(&s_cnt, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (keep) {
+            const int pos = base + __popc(m & ((1u << lane) - 1u));
+            scr_idx[pos] = j;
+            scr_val[pos] = v;
+          }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, keep);
-        int base = 0;
-        if (lane == 0 && m) base = atomicAdd(&s_cnt, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (keep) {
-          const int pos = base + __popc(m & ((1u << lane) - 1u));
-          scr_idx[pos] = j;
-          scr_val[pos] = v;
+        __syncthreads();
+      } else {
+        // stored entries of the row in ascending column order: count them (mode 1) or write them (mode 2)
+        const int64_t row_base = p.mode == 2 ? p.out_indptr[i] : 0;
+        for (int t0 = 0; t0 < r1 - r0; t0 += nt) {
+          const int t = t0 + tid;
+          const double v = t < r1 - r0 ? acc[t] : 0.0;
+          const bool keep = v != 0.0;
+          const unsigned m = __ballot_sync(0xffffffffu, keep);
+          if (lane == 0) s_wc[warp] = __popc(m);
+          __syncthreads();
+          int before = 0, all = 0;
+          for (int w = 0; w < nw; ++w) {
+            const int cw = s_wc[w];
+            before += w < warp ? cw : 0;
+            all += cw;
+          }
+          if (keep && p.mode == 2) {
+            const int64_t pos = row_base + s_cnt + before + __popc(m & ((1u << lane) - 1u));
+            p.csr_indices[pos] = r0 + t;
+            p.csr_values[pos] = v;
+          }
+          __syncthreads();
+          if (tid == 0) s_cnt += all;
         }
+        __syncthreads();
       }
-      __syncthreads();
+    }
+    if (p.mode != 0) {
+      if (p.mode == 1 && tid == 0) p.out_row_nnz[i] = s_cnt;
+      continue;
     }
     const int ns = s_cnt;
     int m = 0;
@@ -332,7 +382,7 @@ __global__ void __launch_bounds__(1024, 1) k_real_rows(RealParams p) {
     }
     __syncthreads();
     for (int t = tid; t < m; t += nt)
-      if (list[t].idx == i) s_diag = t;
+      if (p.diag && list[t].idx == i) s_diag = t;
     __syncthreads();
     const int dpos = s_diag;
     const int64_t ob = ((int64_t)i - p.item_begin) * p.K;
@@ -348,6 +398,21 @@ __global__ void __launch_bounds__(1024, 1) k_real_rows(RealParams p) {
       }
     }
     if (tid == 0) p.out_len[i - p.item_begin] = len;
+  }
+}
+
+// Work of a scoring row: the entries of B it touches.
+__global__ void k_spgemm_work(const int64_t* __restrict__ a_ptr, const int* __restrict__ a_idx, const int64_t* __restrict__ b_ptr,
+                              int64_t rows, u64* __restrict__ work) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    u64 w = 0;
+    for (int64_t k = a_ptr[r] + lane; k < a_ptr[r + 1]; k += 32) w += (u64)(b_ptr[a_idx[k] + 1] - b_ptr[a_idx[k]]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (lane == 0) work[r] = w + 1;
   }
 }
 
@@ -477,8 +542,16 @@ void run_fit_real(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* 
     rp.cscptr = cscptr;
     rp.csc_users = csc_users;
     rp.csc_off = csc_off;
+    rp.left_entry = nullptr;
     rp.row_scale = row_scale;
     rp.col_scale = col_scale;
+    rp.diag = 1;
+    rp.mask_list = 0;
+    rp.mode = 0;
+    rp.out_row_nnz = nullptr;
+    rp.out_indptr = nullptr;
+    rp.csr_indices = nullptr;
+    rp.csr_values = nullptr;
     rp.order = order;
     rp.nrows = (int)nrows;
     rp.P = P;
@@ -501,6 +574,130 @@ void run_fit_real(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* 
   o_idx.finish(c);
   o_val.finish(c);
   o_len.finish(c);
+  finish_call(c);
+}
+
+// C = A @ B for a real-valued CSR A [rows x I] and a CSR B [I x I] with ascending columns (the similarity model), float64
+// in scipy's csr_matmat order (bit-identical sums): per-row top-N lists (mode 0), stored entries per row (mode 1) or the
+// CSR rows themselves (mode 2, out_indptr from the counts).  Replaces `X_decayed @ similarity_matrix_` of
+// TARSItemKNN._predict (time_aware_item_knn/base.py:137-149 -> algorithms/base.py:237-255) and, with mask_history,
+// pipelines/pipeline.py:174-175.
+void run_spgemm(rpk_ctx* c, int64_t rows, int64_t a_nnz, const int64_t* a_indptr_u, const int32_t* a_indices_u,
+                const double* a_values_u, int64_t I, int64_t b_nnz, const int64_t* b_indptr_u, const int32_t* b_indices_u,
+                const double* b_values_u, int N, int mask_history, int mode, int32_t* out_idx_u, double* out_val_u,
+                int32_t* out_len_u, int64_t* out_row_nnz_u, const int64_t* out_indptr_u, int64_t out_nnz, int32_t* csr_indices_u,
+                double* csr_values_u) {
+  RPK_REQUIRE(rows >= 0 && I >= 0 && a_nnz >= 0 && b_nnz >= 0, "negative dimension");
+  RPK_REQUIRE(I < (int64_t)1 << 24, "more than 2^24 items are not supported");
+  RPK_REQUIRE(rows < (int64_t)1 << 31, "more than 2^31 rows are not supported");
+  RPK_REQUIRE(mode >= 0 && mode <= 2, "bad mode");
+  if (mode == 0) {
+    RPK_REQUIRE(N >= 1 && N <= 4096, "N must be in [1, 4096]");
+    RPK_REQUIRE(out_idx_u && out_val_u && out_len_u, "out_idx / out_val / out_len must not be null");
+  } else if (mode == 1) {
+    RPK_REQUIRE(out_row_nnz_u, "out_row_nnz must not be null");
+    N = 1;
+  } else {
+    RPK_REQUIRE(out_indptr_u && (out_nnz == 0 || (csr_indices_u && csr_values_u)), "CSR outputs must not be null");
+    N = 1;
+  }
+  cudaStream_t st = c->stream;
+  const int64_t* a_ptr = stage_in(c, a_indptr_u, (size_t)rows + 1, "sg_a_ptr");
+  const int32_t* a_idx = stage_in(c, a_indices_u, (size_t)a_nnz, "sg_a_idx");
+  const double* a_val = stage_in(c, a_values_u, (size_t)a_nnz, "sg_a_val");
+  const int64_t* b_ptr = stage_in(c, b_indptr_u, (size_t)I + 1, "sg_b_ptr");
+  const int32_t* b_idx = stage_in(c, b_indices_u, (size_t)b_nnz, "sg_b_idx");
+  const double* b_val = stage_in(c, b_values_u, (size_t)b_nnz, "sg_b_val");
+  const int64_t* o_ptr = mode == 2 ? stage_in(c, out_indptr_u, (size_t)rows + 1, "sg_o_ptr") : nullptr;
+  Out<int32_t> o_idx, o_len, o_ci;
+  Out<double> o_val, o_cv;
+  Out<int64_t> o_cnt;
+  if (mode == 0) {
+    o_idx.init(c, out_idx_u, (size_t)rows * N, "sg_out_idx");
+    o_val.init(c, out_val_u, (size_t)rows * N, "sg_out_val");
+    o_len.init(c, out_len_u, (size_t)rows, "sg_out_len");
+  } else if (mode == 1) {
+    o_cnt.init(c, out_row_nnz_u, (size_t)rows, "sg_out_cnt");
+  } else {
+    o_ci.init(c, csr_indices_u, (size_t)out_nnz, "sg_out_ci");
+    o_cv.init(c, csr_values_u, (size_t)out_nnz, "sg_out_cv");
+  }
+  c->mark("spgemm: begin");
+  if (rows > 0) {
+    u64* work = c->buf<u64>("sg_work", (size_t)rows);
+    int* order = c->buf<int>("sg_order", (size_t)rows);
+    int* bcnt = c->buf<int>("sg_bcnt", 65 * 2 + 2);
+    int* boff = bcnt + 65;
+    int* queue = c->buf<int>("sg_queue", 4);
+    RPK_CUDA(cudaMemsetAsync(bcnt, 0, sizeof(int) * (65 * 2 + 2), st));
+    RPK_CUDA(cudaMemsetAsync(queue, 0, sizeof(int) * 4, st));
+    k_spgemm_work<<<(int)std::min<int64_t>((rows * 32 + 255) / 256, (int64_t)c->sm_count * 16), 256, 0, st>>>(a_ptr, a_idx, b_ptr, rows,
+                                                                                                        work);
+    RPK_LAUNCH_CHECK(c);
+    k_bucket_count<<<ceil_div(rows, 256), 256, 0, st>>>(work, 0, rows, bcnt);
+    RPK_LAUNCH_CHECK(c);
+    k_bucket_offsets<<<1, 32, 0, st>>>(bcnt, boff);
+    RPK_LAUNCH_CHECK(c);
+    k_bucket_scatter<<<ceil_div(rows, 256), 256, 0, st>>>(work, 0, rows, boff, order);
+    RPK_LAUNCH_CHECK(c);
+    const bool tiny = c->flags & DBG_TINY_LIST;
+    const int cap = std::max(tiny ? 64 : 1024, next_pow2(2 * N));
+    const int direct_cap = tiny ? N : cap;
+    const size_t fixed = sel_smem_bytes(cap);
+    RPK_REQUIRE((size_t)c->smem_max > fixed + 4096 + 2048, "N too large for shared memory");
+    const size_t avail = (size_t)c->smem_max - fixed - 2048;
+    int64_t Rmax = (int64_t)(avail / sizeof(double)) & ~(int64_t)7;
+    int P = (int)((std::max<int64_t>(I, 1) + Rmax - 1) / Rmax);
+    if (P < 1) P = 1;
+    if ((c->flags & DBG_MULTI_PASS) && P < 2 && I >= 16) P = 2;
+    const int R = (int)(((std::max<int64_t>(I, 1) + P - 1) / P + 7) & ~(int64_t)7);
+    const size_t smem = fixed + (size_t)R * sizeof(double);
+    const int nt = R >= 8192 ? 1024 : (R >= 1024 ? 256 : 64);
+    RPK_CUDA(cudaFuncSetAttribute(k_real_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(rows, (int64_t)c->sm_count));
+    RealParams rp;
+    rp.indptr = b_ptr;
+    rp.indices = b_idx;
+    rp.left = nullptr;
+    rp.right = b_val;
+    rp.cscptr = a_ptr;
+    rp.csc_users = a_idx;
+    rp.csc_off = nullptr;
+    rp.left_entry = a_val;
+    rp.row_scale = nullptr;
+    rp.col_scale = nullptr;
+    rp.order = order;
+    rp.nrows = (int)rows;
+    rp.P = P;
+    rp.R = R;
+    rp.I = (int)I;
+    rp.K = N;
+    rp.item_begin = 0;
+    rp.cap = cap;
+    rp.direct_cap = direct_cap;
+    rp.diag = 0;
+    rp.mask_list = mask_history ? 1 : 0;
+    rp.mode = mode;
+    rp.queue = queue;
+    rp.scr_idx = c->buf<int>("fr_scr_idx", mode == 0 ? (size_t)grid * (size_t)(I + 1) : 16);
+    rp.scr_val = c->buf<double>("fr_scr_val", mode == 0 ? (size_t)grid * (size_t)(I + 1) : 16);
+    rp.out_idx = o_idx.dev;
+    rp.out_val = o_val.dev;
+    rp.out_len = o_len.dev;
+    rp.out_row_nnz = reinterpret_cast<long long*>(o_cnt.dev);
+    rp.out_indptr = o_ptr;
+    rp.csr_indices = o_ci.dev;
+    rp.csr_values = o_cv.dev;
+    k_real_rows<<<grid, nt, smem, st>>>(rp);
+    RPK_LAUNCH_CHECK(c);
+  }
+  c->mark("spgemm: rows");
+  o_idx.finish(c);
+  o_val.finish(c);
+  o_len.finish(c);
+  o_cnt.finish(c);
+  o_ci.finish(c);
+  o_cv.finish(c);
   finish_call(c);
 }
 

@@ -44,6 +44,10 @@ void run_metrics_topn(rpk_ctx* c, int64_t U, int N, const int32_t* top_idx, cons
 void run_coverage_topn(rpk_ctx* c, int64_t U, int N, int K, int64_t I, const int32_t* top_idx, const int32_t* top_len,
                        const int64_t* true_indptr, int64_t* out_count, uint8_t* out_flags);
 
+void run_spgemm(rpk_ctx* c, int64_t rows, int64_t a_nnz, const int64_t* a_indptr, const int32_t* a_indices, const double* a_values,
+                int64_t I, int64_t b_nnz, const int64_t* b_indptr, const int32_t* b_indices, const double* b_values, int N,
+                int mask_history, int mode, int32_t* out_idx, double* out_val, int32_t* out_len, int64_t* out_row_nnz,
+                const int64_t* out_indptr, int64_t out_nnz, int32_t* csr_indices, double* csr_values);
 void run_split_fraction(rpk_ctx* c, int64_t n_users, const int64_t* uids, const int64_t* seg, const int64_t* rows,
                         int64_t n_rows, double in_frac, uint64_t seed, uint8_t* out_in_mask);
 void run_gram_dense_f64(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* indptr, const int32_t* indices, double* out_G);

@@ -162,6 +162,43 @@ class Engine:
     def fit_config(self, dense_users: int = -1):
         self._check(self._lib.rpk_fit_config(self._h, int(dense_users)))
 
+    # -- real-valued scoring: C = A @ S in float64, scipy's summation order ------------------------------
+    @staticmethod
+    def _csr_args(M):
+        return (np.ascontiguousarray(M.indptr, dtype=np.int64), np.ascontiguousarray(M.indices, dtype=np.int32),
+                np.ascontiguousarray(M.data, dtype=np.float64))
+
+    def spgemm_topn(self, A, S, N, mask_history=False):
+        """rpk_spgemm_topn for scipy CSR A [rows x I] and S [I x I] (sorted indices).  Returns dict(idx, val, len)."""
+        rows, I = A.shape
+        ap, ai, av = self._csr_args(A)
+        sp_, si, sv = self._csr_args(S)
+        out = {"idx": np.empty((rows, N), dtype=np.int32), "val": np.empty((rows, N), dtype=np.float64),
+               "len": np.empty((rows,), dtype=np.int32)}
+        self._check(self._lib.rpk_spgemm_topn(self._h, int(rows), int(ai.shape[0]), _addr(ap), _addr(ai), _addr(av), int(I),
+                                              int(si.shape[0]), _addr(sp_), _addr(si), _addr(sv), int(N), int(bool(mask_history)),
+                                              _addr(out["idx"]), _addr(out["val"]), _addr(out["len"])))
+        return out
+
+    def spgemm_csr(self, A, S, mask_history=False):
+        """A @ S as (indptr int64, indices int32, values float64), ascending columns (rpk_spgemm_count + _fill)."""
+        rows, I = A.shape
+        ap, ai, av = self._csr_args(A)
+        sp_, si, sv = self._csr_args(S)
+        cnt = np.zeros(rows, dtype=np.int64)
+        self._check(self._lib.rpk_spgemm_count(self._h, int(rows), int(ai.shape[0]), _addr(ap), _addr(ai), _addr(av), int(I),
+                                               int(si.shape[0]), _addr(sp_), _addr(si), _addr(sv), int(bool(mask_history)),
+                                               _addr(cnt)))
+        indptr = np.zeros(rows + 1, dtype=np.int64)
+        np.cumsum(cnt, out=indptr[1:])
+        nnz = int(indptr[-1])
+        indices = np.empty(nnz, dtype=np.int32)
+        values = np.empty(nnz, dtype=np.float64)
+        self._check(self._lib.rpk_spgemm_fill(self._h, int(rows), int(ai.shape[0]), _addr(ap), _addr(ai), _addr(av), int(I),
+                                              int(si.shape[0]), _addr(sp_), _addr(si), _addr(sv), int(bool(mask_history)),
+                                              _addr(indptr), nnz, _addr(indices), _addr(values)))
+        return indptr, indices, values
+
     def split_fraction(self, uids, seg, rows, in_frac, seed):
         """rpk_split_fraction: uint8 mask over the table rows, 1 = data_in (see include/rpk.h)."""
         n_rows = int(rows.shape[0])

@@ -83,19 +83,17 @@ class ItemKNN(GpuSimilarityMixin, _ItemKNNBase):
             self._set_device_fit(out, I, engine.device)
 
 
-def pearson_top_k(X: csr_matrix, K: int) -> csr_matrix:
-    """``get_top_K_values(compute_pearson_similarity(X), K)`` (nearest_neighbour.py:87-111, util.py:80-96) without the
-    item x item matrix: ratings are centred per item over the positive entries, the cosine Gram of the centred matrix and
-    the per-row selection run on the GPU (rpk_fit_topk_real).  Similarities can be negative, so the result is a similarity
-    matrix for inspection / the TARSItemKNN family, not a model for the fixed-point scorer of ``ItemKNN.predict``."""
+def pearson_centred(X: csr_matrix) -> csr_matrix:
+    """The matrix compute_pearson_similarity hands to the cosine (nearest_neighbour.py:100-108): every positive entry
+    minus the mean of its item's positive entries; entries that become zero are not stored."""
     if not isinstance(X, csr_matrix):
-        raise TypeError("pearson_top_k expects a scipy csr_matrix")
+        raise TypeError("expected a scipy csr_matrix")
     X = X.astype(np.float64).tocsr()
     X.sum_duplicates()
     X.eliminate_zeros()
     if (X.data == 1).sum() == X.nnz:
         raise ValueError("Pearson similarity can not be computed on a binary matrix.")
-    U, I = X.shape
+    I = X.shape[1]
     pos = X.data > 0
     count = np.bincount(X.indices[pos], minlength=I)
     avg = np.bincount(X.indices, weights=X.data, minlength=I).astype(np.float64)
@@ -105,7 +103,28 @@ def pearson_top_k(X: csr_matrix, K: int) -> csr_matrix:
     data[pos] = data[pos] - avg[X.indices[pos]]
     C = csr_matrix((data, X.indices.copy(), X.indptr.copy()), shape=X.shape)
     C.eliminate_zeros()  # the sparse subtraction of the reference stores no zero results
-    engine = get_engine()
-    out = engine.fit_topk_real(U, I, np.ascontiguousarray(C.indptr, dtype=np.int64), np.ascontiguousarray(C.indices, dtype=np.int32),
-                               np.ascontiguousarray(C.data, dtype=np.float64), int(K), similarity="cosine")
+    return C
+
+
+def real_top_k(X: csr_matrix, K: int, similarity: str = "cosine") -> csr_matrix:
+    """``get_top_K_values(compute_<similarity>(X), K)`` for a real-valued CSR X on the GPU (rpk_fit_topk_real);
+    similarity in {"cosine", "conditional_probability", "pearson"}."""
+    if similarity == "pearson":
+        X, similarity = pearson_centred(X), "cosine"
+    else:
+        X = csr_matrix(X).astype(np.float64)
+        X.sum_duplicates()
+        X.eliminate_zeros()
+    U, I = X.shape
+    out = get_engine().fit_topk_real(U, I, np.ascontiguousarray(X.indptr, dtype=np.int64),
+                                     np.ascontiguousarray(X.indices, dtype=np.int32),
+                                     np.ascontiguousarray(X.data, dtype=np.float64), int(K), similarity=similarity)
     return lists_to_csr(out["idx"], out["val"], out["len"], I)
+
+
+def pearson_top_k(X: csr_matrix, K: int) -> csr_matrix:
+    """``get_top_K_values(compute_pearson_similarity(X), K)`` (nearest_neighbour.py:87-111, util.py:80-96) without the
+    item x item matrix: ratings are centred per item over the positive entries, the cosine Gram of the centred matrix and
+    the per-row selection run on the GPU (rpk_fit_topk_real).  Similarities can be negative, so the result is a similarity
+    matrix for the TARSItemKNN family (scored by rpk_spgemm_*), not a model for the fixed-point scorer of ``ItemKNN.predict``."""
+    return real_top_k(X, K, "pearson")

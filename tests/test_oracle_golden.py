@@ -283,3 +283,13 @@ def test_fraction_split_oracle_reproduces_reference(name):
     mask = orc.ref_fraction_split_mask(g["uid"], float(g["in_frac"]), int(g["seed"]))
     assert np.array_equal(np.sort(g["interactionid"][mask]), g["in_ids"])
     assert np.array_equal(np.sort(g["interactionid"][~mask]), g["out_ids"])
+
+
+@pytest.mark.parametrize("name", ["tars_cosine_exp", "tars_condprob_linear", "tars_pearson_vaz", "tars_pearson_bigK", "tars_liu2012",
+                                  "tars_lee", "tars_ding_nofitdecay"])
+def test_tars_goldens_canonical_topk_is_the_references_up_to_ties(name):
+    """Fixtures of tests/golden/make_golden_tars.py: the canonical selection from the reference's full similarity matrix
+    keeps what the reference's get_top_K_values keeps (tie-aware), negatives and the competing diagonal zero included."""
+    g = load_golden(name)
+    K = int(g["K"])
+    _kept_sets_tie_aware(orc.canon_topk_of_full(unpack(g, "full"), K), unpack(g, "S"), unpack(g, "full"), K)
