@@ -41,7 +41,6 @@ struct RealRowSrc {
   const int* idx;
   const double* val;
   int ns;
-  __device__ __forceinline__ int nslots() const { return ns; }
   __device__ __forceinline__ u64 margin() const { return 0ull; }
   __device__ __forceinline__ void set_floor(u64) {}
   __device__ __forceinline__ void stats(SelShared* sh) const { generic_stats(*this, sh); }
@@ -200,25 +199,15 @@ __global__ void k_real_recip(const int* __restrict__ n, int64_t I, double* __res
   if (i < I) out[i] = n[i] > 0 ? __ddiv_rn(1.0, (double)n[i]) : 0.0;
 }
 
-// First position in a[0, n) whose value is >= key; all lanes of the warp pass the same arguments.
-__device__ __forceinline__ int warp_lower_bound(const int* __restrict__ a, int n, int key, int lane) {
+// First position in a[0, n) whose value is >= key (per lane: every lane searches its own array).
+__device__ __forceinline__ int lane_lower_bound(const int* __restrict__ a, int n, int key) {
   int lo = 0, hi = n;
-  while (hi - lo > 32) {
-    const int step = (hi - lo + 31) >> 5;
-    const int probe = lo + (lane + 1) * step - 1;
-    const bool ge = probe >= hi ? true : a[probe] >= key;
-    const unsigned m = __ballot_sync(0xffffffffu, ge);
-    if (m == 0u) return hi;
-    const int f = __ffs(m) - 1;
-    const int nhi = min(hi, lo + (f + 1) * step - 1);  // a[probe of lane f] >= key: the answer is at or before it
-    lo = lo + f * step;
-    hi = nhi;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1;
+    else hi = mid;
   }
-  const int probe = lo + lane;
-  const bool ge = probe >= hi ? true : a[probe] >= key;
-  const unsigned m = __ballot_sync(0xffffffffu, ge);
-  if (m == 0u) return hi;
-  return min(hi, lo + __ffs(m) - 1);
+  return lo;
 }
 
 // One kernel serves two products of the form  row(i) = sum over the entries k of a LIST of  a_k * B[k, :] :
@@ -286,21 +275,39 @@ __global__ void __launch_bounds__(1024, 1) k_real_rows(RealParams p) {
       const int per = (r1 - r0 + nw - 1) / nw;
       const int c0 = r0 + warp * per, c1 = min(r1, c0 + per);
       if (c0 < c1) {
-        for (int k = 0; k < nu; ++k) {
-          const int u = p.csc_users[ub + k];
-          const int64_t hb = p.indptr[u];
-          const int d = (int)(p.indptr[u + 1] - hb);
-          const int* h = p.indices + hb;
-          const int lo = warp_lower_bound(h, d, c0, lane);
-          if (lo >= d || h[lo] >= c1) continue;  // nothing of this row of B in the slice (warp-uniform)
-          const int hi = lo + warp_lower_bound(h + lo, d - lo, c1, lane);
-          const double a = p.left_entry ? p.left_entry[ub + k] : (p.left ? p.left[hb + p.csc_off[ub + k]] : 1.0);
-          for (int t = lo + lane; t < hi; t += 32) {
-            const int j = h[t];
-            const double b = p.right[hb + t];
-            acc[j - r0] = __dadd_rn(acc[j - r0], __dmul_rn(a, b));
+        // 32 list entries at a time, one per lane: every lane finds the part of ITS row of B that falls into the warp's
+        // slice (two binary searches, all lanes busy), then the warp applies the 32 parts one after the other in list
+        // order -- the order the reference adds them in -- with its lanes spread over the part's entries.
+        for (int k0 = 0; k0 < nu; k0 += 32) {
+          const int k = k0 + lane;
+          int64_t hb = 0;
+          int lo = 0, cnt = 0;
+          double a = 0.0;
+          if (k < nu) {
+            const int u = p.csc_users[ub + k];
+            hb = p.indptr[u];
+            const int d = (int)(p.indptr[u + 1] - hb);
+            const int* h = p.indices + hb;
+            lo = lane_lower_bound(h, d, c0);
+            if (lo < d && h[lo] < c1) {
+              cnt = lane_lower_bound(h + lo, d - lo, c1);
+              a = p.left_entry ? p.left_entry[ub + k] : (p.left ? p.left[hb + p.csc_off[ub + k]] : 1.0);
+            }
           }
-          __syncwarp();
+          unsigned todo = __ballot_sync(0xffffffffu, cnt > 0);
+          while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const int64_t hb_l = __shfl_sync(0xffffffffu, hb, l) + __shfl_sync(0xffffffffu, lo, l);
+            const int cnt_l = __shfl_sync(0xffffffffu, cnt, l);
+            const double a_l = __shfl_sync(0xffffffffu, a, l);
+            for (int t = lane; t < cnt_l; t += 32) {
+              const int j = p.indices[hb_l + t];
+              const double b = p.right[hb_l + t];
+              acc[j - r0] = __dadd_rn(acc[j - r0], __dmul_rn(a_l, b));
+            }
+            __syncwarp();
+          }
         }
       }
       __syncthreads();
