@@ -222,6 +222,8 @@ struct RealParams {
   const int* csc_users;   // ... their entries (row ids of B), ascending per list
   const int* csc_off;     // fit: offset of item i inside each user's history (where `left` is read)
   const double* left_entry;  // non-null: a_k stored per list entry (scoring)
+  const int* split;  // non-null: [rows of B x split_w] positions of the slice boundaries inside every row of B (k_real_split)
+  int split_w;       // = P * (warps + 1)
   const double* row_scale;  // null = none
   const double* col_scale;  // null = none
   const int* order;         // rows of this call, heaviest first (absolute row ids)
@@ -287,12 +289,16 @@ __global__ void __launch_bounds__(1024, 1) k_real_rows(RealParams p) {
             const int u = p.csc_users[ub + k];
             hb = p.indptr[u];
             const int d = (int)(p.indptr[u + 1] - hb);
-            const int* h = p.indices + hb;
-            lo = lane_lower_bound(h, d, c0);
-            if (lo < d && h[lo] < c1) {
-              cnt = lane_lower_bound(h + lo, d - lo, c1);
-              a = p.left_entry ? p.left_entry[ub + k] : (p.left ? p.left[hb + p.csc_off[ub + k]] : 1.0);
+            if (p.split) {
+              const int* sp = p.split + (int64_t)u * p.split_w + pass * (nw + 1) + warp;
+              lo = sp[0];
+              cnt = sp[1] - lo;
+            } else {
+              const int* h = p.indices + hb;
+              lo = lane_lower_bound(h, d, c0);
+              if (lo < d && h[lo] < c1) cnt = lane_lower_bound(h + lo, d - lo, c1);
             }
+            if (cnt > 0) a = p.left_entry ? p.left_entry[ub + k] : (p.left ? p.left[hb + p.csc_off[ub + k]] : 1.0);
           }
           unsigned todo = __ballot_sync(0xffffffffu, cnt > 0);
           while (todo) {
@@ -408,6 +414,24 @@ __global__ void __launch_bounds__(1024, 1) k_real_rows(RealParams p) {
   }
 }
 
+// split[r * W + p * (nw + 1) + w] = first position in row r of B whose column is >= the lower bound of the slice of warp w
+// in column range p (w = nw: the end of the range): the row kernel then reads two table entries per (list entry, slice)
+// instead of searching the row of B again for every row of the product that touches it.
+__global__ void k_real_split(const int64_t* __restrict__ indptr, const int* __restrict__ indices, int64_t nrows_b, int I, int P, int R,
+                             int nw, int* __restrict__ split) {
+  const int W = P * (nw + 1);
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nrows_b * W) return;
+  const int64_t r = t / W;
+  const int s = (int)(t - r * W);
+  const int pass = s / (nw + 1), w = s - pass * (nw + 1);
+  const int r0 = pass * R, r1 = min(I, r0 + R);
+  const int per = (r1 - r0 + nw - 1) / nw;
+  const int bound = min(r1, r0 + w * per);
+  const int64_t hb = indptr[r];
+  split[t] = lane_lower_bound(indices + hb, (int)(indptr[r + 1] - hb), bound);
+}
+
 // Work of a scoring row: the entries of B it touches.
 __global__ void k_spgemm_work(const int64_t* __restrict__ a_ptr, const int* __restrict__ a_idx, const int64_t* __restrict__ b_ptr,
                               int64_t rows, u64* __restrict__ work) {
@@ -421,6 +445,19 @@ __global__ void k_spgemm_work(const int64_t* __restrict__ a_ptr, const int* __re
     for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
     if (lane == 0) work[r] = w + 1;
   }
+}
+
+// Slice-boundary table of B for the row kernel (null when it would not fit comfortably: the kernel then searches).
+static const int* build_split(rpk_ctx* c, const int64_t* b_ptr, const int* b_idx, int64_t nrows_b, int64_t I, int P, int R, int nt,
+                              int* split_w) {
+  const int nw = nt / 32;
+  const int64_t W = (int64_t)P * (nw + 1);
+  *split_w = (int)W;
+  if (nrows_b == 0 || nrows_b * W > ((int64_t)1 << 29)) return nullptr;  // > 2 GB of positions
+  int* split = c->buf<int>("fr_split", (size_t)(nrows_b * W));
+  k_real_split<<<ceil_div(nrows_b * W, 256), 256, 0, c->stream>>>(b_ptr, b_idx, nrows_b, (int)I, P, R, nw, split);
+  RPK_LAUNCH_CHECK(c);
+  return split;
 }
 
 int next_pow2(int v) {
@@ -550,6 +587,7 @@ void run_fit_real(rpk_ctx* c, int64_t U, int64_t I, int64_t nnz, const int64_t* 
     rp.csc_users = csc_users;
     rp.csc_off = csc_off;
     rp.left_entry = nullptr;
+    rp.split = build_split(c, indptr, indices, U, I, P, R, nt, &rp.split_w);
     rp.row_scale = row_scale;
     rp.col_scale = col_scale;
     rp.diag = 1;
@@ -671,6 +709,7 @@ void run_spgemm(rpk_ctx* c, int64_t rows, int64_t a_nnz, const int64_t* a_indptr
     rp.csc_users = a_idx;
     rp.csc_off = nullptr;
     rp.left_entry = a_val;
+    rp.split = build_split(c, b_ptr, b_idx, I, I, P, R, nt, &rp.split_w);
     rp.row_scale = nullptr;
     rp.col_scale = nullptr;
     rp.order = order;
