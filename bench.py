@@ -246,6 +246,14 @@ def run_reference(args):
 def run_gpu(args):
     import torch
 
+    # a user of the drop-in has recpack installed: with the reference on the path (baseline/_ref, installed by
+    # baseline/install_ref.sh) the classes timed by the e2e leg SUBCLASS the reference's own (recpack_b200/_ref.py)
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref_dir, "recpack")):
+        for p_ in (os.path.join(ROOT, "baseline", "stubs"), ref_dir):
+            if p_ not in sys.path:
+                sys.path.insert(0, p_)
+
     from recpack_b200.distributed import ShardExchange, fit_work_per_item, score_work_per_user, shard_bounds
     from recpack_b200.engine import get_engine
 
@@ -548,10 +556,18 @@ def run_e2e(args, train, test_out, eng, steps):
     d2h = U * N_LIST * 12 + U * 4 + 2 * (U * 8 + 16) + 8
     return {"value": U / t, "unit": UNIT, "seconds": t, "step_seconds": [round(x, 5) for x in times], "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
             "ndcg10": float(v[0]), "recall20": float(v[1]),
+            "classes": "subclasses of recpack's ItemKNN / NDCGK / RecallK (reference importable from baseline/_ref)"
+                       if _have_recpack() else "stand-alone mirror classes (recpack not importable)",
             "path": "drop-in classes: ItemKNN(...).fit(X) -> predict(X) -> NDCGK(10) / RecallK(20).calculate with scipy CSR inputs in pinned "
                     "host memory; the top-N prediction matrix (indices, scores) and the per-user metric values come back to the host",
             "note": "similarity_matrix_ is not materialised inside the timed region: the top-K lists stay on the device until the "
                     "attribute is first read (the reference's fit leaves S on the host; here that is 142 MB D2H + one CSR build on demand)"}
+
+
+def _have_recpack():
+    from recpack_b200 import _ref
+
+    return bool(_ref.HAVE_RECPACK)
 
 
 def _emit(line):
